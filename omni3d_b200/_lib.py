@@ -1,0 +1,53 @@
+"""ctypes binding of libc3d.so (C ABI declared in include/c3d.h).  No torch types cross it."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libc3d.so")
+_lib = None
+
+C3D_OK, C3D_EINVAL, C3D_EWORKSPACE, C3D_ECUDA = 0, -1, -2, -3
+
+
+class C3DError(RuntimeError):
+    pass
+
+
+def _sig(lib, name, restype, argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = argtypes
+    return fn
+
+
+def lib():
+    """Load libc3d.so or raise — the product path has no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise C3DError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C omni3d_b200/csrc). omni3d_b200 has no CPU / library fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32, f32, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_size_t
+    _sig(L, "c3d_last_error", ctypes.c_char_p, [])
+    _sig(L, "c3d_abi_version", i32, [])
+    _sig(L, "c3d_iou_box3d_workspace_bytes", sz, [i64, i64])
+    _sig(L, "c3d_iou_box3d", i32, [vp, i64, vp, i64, vp, vp, vp, vp, sz, vp])
+    _sig(L, "c3d_iou_box3d_paired", i32, [vp, vp, i64, vp, vp, vp, vp, sz, vp])
+    _sig(L, "c3d_box3d_overlap", i32, [vp, i64, vp, i64, f32, f32, vp, vp, vp, sz, vp])
+    _lib = L
+    return L
+
+
+def check(code):
+    if code != C3D_OK:
+        raise C3DError(f"libc3d error {code}: {lib().c3d_last_error().decode()}")
+
+
+# every symbol include/c3d.h declares (tests/test_abi.py checks the .so exports each one)
+EXPORTS = [
+    "c3d_last_error", "c3d_abi_version", "c3d_iou_box3d_workspace_bytes", "c3d_iou_box3d",
+    "c3d_iou_box3d_paired", "c3d_box3d_overlap",
+]
