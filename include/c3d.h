@@ -61,6 +61,36 @@ int32_t c3d_box3d_overlap(const float* boxes_dt, int64_t n_dt, const float* boxe
                           float eps_coplanar, float eps_nonzero, float* iou, int32_t* n_bad,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * NHWC bf16 implicit-GEMM convolution on tcgen05 tensor cores (TMA-staged, fp32 accumulate in TMEM).
+ * Replaces the cuDNN calls behind nn.Conv2d in cubercnn/modeling/backbone/dla.py:43-51,159-161,
+ * 211-214,241-243,287-297, the detectron2 FPN convs built at dla.py:500-506 / resnet.py:88-95 and
+ * the StandardRPNHead convs (configs/Base.yaml:49).  Data-gradient = the same entry point with
+ * flipped/transposed weights; weight-gradient = c3d_conv2d_wgrad.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t N, H, W, Cin;      /* input  (N,H,W,Cin)  bf16, pixel stride x_pix_stride elements (0 => Cin) */
+  int32_t Cout, KH, KW;      /* weight (Cout,KH,KW,Cin) bf16 contiguous */
+  int32_t stride, pad;       /* stride 1 or 2 (same in h and w), symmetric zero padding */
+  int32_t relu;              /* epilogue: max(.,0) after bias/addend */
+  int32_t out_fp32;          /* output fp32 instead of bf16 */
+  int32_t add_mode;          /* 0 none; 1 addend (N,Ho,Wo,Cout); 2 addend (N,Ho/2,Wo/2,Cout) nearest-up x2 (FPN) */
+  int64_t x_pix_stride, y_pix_stride, add_pix_stride;   /* elements; 0 => dense */
+} c3d_conv_desc;
+
+/* number of 128-pixel output tiles (= rows of the BatchNorm partial-statistics buffer) and tile shape */
+int32_t c3d_conv2d_tiles(const c3d_conv_desc* d, int32_t* tiles_m, int32_t* tile_h, int32_t* tile_w);
+
+/* y = conv(x, w) [+ bias] [+ addend] [relu].  stats (may be NULL): fp32 [tiles_m][2][Cout] per-tile
+ * partial (sum, sum of squares) of the raw fp32 conv output, for train-mode BatchNorm. */
+int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const void* w, const float* bias,
+                       const void* addend, void* y, float* stats, void* stream);
+
+/* dw[Cout][KH][KW][Cin] (fp32) += the weight gradient of the convolution described by d, from the
+ * forward input x (N,H,W,Cin) and the output gradient dy (N,Ho,Wo,Cout), both bf16 NHWC.
+ * Split-K over pixels with fp32 atomics: the caller zeroes (or pre-loads) dw. */
+int32_t c3d_conv2d_wgrad(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

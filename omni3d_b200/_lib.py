@@ -49,5 +49,5 @@ def check(code):
 # every symbol include/c3d.h declares (tests/test_abi.py checks the .so exports each one)
 EXPORTS = [
     "c3d_last_error", "c3d_abi_version", "c3d_iou_box3d_workspace_bytes", "c3d_iou_box3d",
-    "c3d_iou_box3d_paired", "c3d_box3d_overlap",
+    "c3d_iou_box3d_paired", "c3d_box3d_overlap", "c3d_conv2d_tiles", "c3d_conv2d_fwd", "c3d_conv2d_wgrad",
 ]

@@ -1,0 +1,596 @@
+// conv_tc.cu — NHWC bf16 implicit-GEMM convolution on the 5th-gen tensor cores (sm_100a).
+//
+// Replaces the cuDNN convolutions the reference reaches through nn.Conv2d in
+//   cubercnn/modeling/backbone/dla.py:43-51,159-161,211-214,241-243,287-297 (DLA34 bottom-up),
+//   detectron2 FPN lateral/output convs (built at dla.py:500-506, resnet.py:88-95) and
+//   detectron2 StandardRPNHead (configs/Base.yaml:49)
+// for forward and (with flipped/transposed weights) data-gradient passes.
+//
+// GEMM view: M = output pixels, N = Cout, K = KH*KW*Cin.  One CTA computes a 128-pixel x BLOCK_N
+// tile.  A (activations): for every filter tap one 4-D TMA box [1][TH][TW][BLOCK_K] at the tap's
+// shifted coordinates — TMA out-of-bounds zero fill *is* the convolution padding and the
+// element-stride field *is* the convolution stride — landing in shared memory as the canonical
+// K-major 128B/64B/32B-swizzled UMMA operand (TH*TW <= 128 rows).  B (weights, [Cout][KH*KW*Cin]
+// bf16): 2-D TMA box.  tcgen05.mma (cta_group::1, M=128) accumulates in TMEM; warp-specialised:
+// warp0 = TMA producer, warp1 = MMA issuer, warps 2-5 = epilogue (tcgen05.ld -> bias / addend /
+// ReLU / BatchNorm partial statistics -> bf16|fp32 NHWC stores).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "c3d_common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace c3d {
+
+using bf16 = __nv_bfloat16;
+
+struct ConvKParams {
+  int N, Ho, Wo, Cout;
+  int KH, KW, stride, pad;
+  int TH, TW, tiles_h, tiles_w;
+  int kc_blocks;             // Cin / BLOCK_K
+  int Cin;
+  const float* bias;         // [Cout] or null
+  int relu;
+  int out_fp32;
+  int add_mode;              // 0 none, 1 same-size, 2 nearest-up2 (addend (N,Ho/2,Wo/2,add_pix_stride))
+  const bf16* addend;
+  long long add_pix_stride;
+  void* out;
+  long long out_pix_stride;  // elements
+  float* stats;              // [tiles_m][2][Cout] partial (sum, sum of squares) or null
+};
+
+template <int BLOCK_N, int BLOCK_K, int STAGES>
+struct ConvSmem {
+  static constexpr int kABytes = 128 * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;       // both multiples of 1024 for BLOCK_N>=32|BK=64
+  static constexpr int kTileBytes = ((kStageBytes + 1023) / 1024) * 1024;
+  static constexpr int kBarOffset = STAGES * kTileBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 4 * 32 * 2 * 4 + 1024 /*align slack*/;
+};
+
+template <int BLOCK_N, int BLOCK_K, int STAGES>
+__global__ void __launch_bounds__(192)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+               const ConvKParams P) {
+  using S = ConvSmem<BLOCK_N, BLOCK_K, STAGES>;
+  constexpr int kSwizzle = BLOCK_K * 2;                       // bytes per smem row = swizzle span
+  constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N; // power of two >= 32
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* red = reinterpret_cast<float*>(smem + S::kBarOffset + 256);   // [4 warps][2][32]... used as [4][2][16]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int tile_m = blockIdx.x;
+  const int tw_i = tile_m % P.tiles_w;
+  const int th_i = (tile_m / P.tiles_w) % P.tiles_h;
+  const int img = tile_m / (P.tiles_w * P.tiles_h);
+  const int ho0 = th_i * P.TH, wo0 = tw_i * P.TW;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int num_kb = P.KH * P.KW * P.kc_blocks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_x);
+    ptx::prefetch_tensormap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<kTmemCols>(tmem_ptr);
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (ptx::elect_one()) {
+      const uint32_t a_bytes = (uint32_t)(P.TH * P.TW * BLOCK_K * 2);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / P.kc_blocks, kc = kb - tap * P.kc_blocks;
+        const int kh = tap / P.KW, kw = tap - kh * P.KW;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * S::kTileBytes;
+        uint8_t* sb = sa + S::kABytes;
+        ptx::mbar_expect_tx(&full_bar[stage], a_bytes + (uint32_t)S::kBBytes);
+        ptx::tma_load_4d(sa, &tmap_x, &full_bar[stage], kc * BLOCK_K, wo0 * P.stride + kw - P.pad,
+                         ho0 * P.stride + kh - P.pad, img);
+        ptx::tma_load_2d(sb, &tmap_w, &full_bar[stage], tap * P.Cin + kc * BLOCK_K, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N < 16 ? 16 : BLOCK_N, 0, 0);
+      constexpr uint32_t lt = ptx::swizzle_layout_type(kSwizzle);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tcgen05_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + stage * S::kTileBytes);
+        const uint32_t sb = sa + S::kABytes;
+        const uint64_t da = ptx::make_smem_desc(sa, 16, 8 * kSwizzle, lt);
+        const uint64_t db = ptx::make_smem_desc(sb, 16, 8 * kSwizzle, lt);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in the (addr>>4) field
+          ptx::umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty_bar[stage]);     // frees the smem slot when these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      ptx::umma_commit(tmem_full_bar);           // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // tile row = TMEM lane
+    const int ty = r / P.TW, tx = r - ty * P.TW;
+    const int ho = ho0 + ty, wo = wo0 + tx;
+    const bool valid = (r < P.TH * P.TW) && (ho < P.Ho) && (wo < P.Wo);
+    const long long pix = ((long long)img * P.Ho + ho) * P.Wo + wo;
+    long long apix = 0;
+    if (P.add_mode == 1) apix = pix;
+    else if (P.add_mode == 2) apix = ((long long)img * (P.Ho >> 1) + (ho >> 1)) * (P.Wo >> 1) + (wo >> 1);
+
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tcgen05_fence_after();
+    constexpr int kChunks = (BLOCK_N + 15) / 16;
+#pragma unroll 1
+    for (int ch = 0; ch < kChunks; ++ch) {
+      uint32_t v[16];
+      ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), v);
+      ptx::tmem_ld_wait();
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+      const int c0 = n0 + ch * 16;
+      if (P.stats) {
+        // per-channel sum / sum-of-squares over the valid rows of this tile (raw fp32 accumulators).
+        // butterfly transpose-reduce: after 4 halving steps + 1, lane l holds channel (l & 15)'s
+        // total over its 16-lane half... we keep it simple & exact-order: two halves then combine.
+        float s[16], s2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { float x = valid ? f[i] : 0.f; s[i] = x; s2[i] = x * x; }
+        // reduce across the 32 lanes of the warp: log-step exchange keeping 16 -> 8 -> 4 -> 2 -> 1 values
+#pragma unroll
+        for (int step = 0; step < 4; ++step) {
+          const int half = 8 >> step;                 // values kept after this step
+          const int mask = 1 << step;                 // partner lane distance
+          const bool upper = (lane & mask) != 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < half) {
+              float send = upper ? s[i] : s[i + half];
+              float keep = upper ? s[i + half] : s[i];
+              float send2 = upper ? s2[i] : s2[i + half];
+              float keep2 = upper ? s2[i + half] : s2[i];
+              s[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+              s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, mask);
+            }
+          }
+        }
+        // now lane holds channel index cidx = bitrev-ish of (lane & 15): bit step of lane selects the
+        // upper/lower half at that step => channel = sum_{step} ((lane>>step)&1) * (8>>step)
+        s[0] += __shfl_xor_sync(0xffffffffu, s[0], 16);
+        s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 16);
+        const int cidx = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
+        if (lane < 16) { red[(q * 2 + 0) * 16 + cidx] = s[0]; red[(q * 2 + 1) * 16 + cidx] = s2[0]; }
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        if (q == 0 && lane < 16 && (c0 + lane) < P.Cout) {
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { a += red[(w * 2 + 0) * 16 + lane]; b += red[(w * 2 + 1) * 16 + lane]; }
+          float* dst = P.stats + (size_t)tile_m * 2 * P.Cout;
+          dst[c0 + lane] = a;
+          dst[P.Cout + c0 + lane] = b;
+        }
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      }
+      if (valid && c0 < P.Cout) {
+        if (P.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] += __ldg(P.bias + c0 + i);
+        }
+        if (P.add_mode) {
+          const uint4* ap = reinterpret_cast<const uint4*>(P.addend + apix * P.add_pix_stride + c0);
+          uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+          const bf16* h0 = reinterpret_cast<const bf16*>(&a0);
+          const bf16* h1 = reinterpret_cast<const bf16*>(&a1);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { f[i] += __bfloat162float(h0[i]); f[8 + i] += __bfloat162float(h1[i]); }
+        }
+        if (P.relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (P.out_fp32) {
+          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix * P.out_pix_stride + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        } else {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + pix * P.out_pix_stride + c0);
+          op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+    }
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+static CUtensorMapSwizzle swz(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+// choose the output tile (TH x TW <= 128 rows) maximising useful rows
+static void pick_tile(int Ho, int Wo, int stride, int* TH, int* TW) {
+  double best = -1; int bth = 1, btw = 1;
+  for (int tw = 1; tw <= 128 && tw <= Wo; ++tw) {
+    if (tw * stride > 256) break;
+    int th = 128 / tw; if (th > Ho) th = Ho;
+    if (th * stride > 256) th = 256 / stride;
+    if (th < 1) continue;
+    long long tiles = (long long)((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
+    double eff = (double)Ho * Wo / (double)(tiles * 128);
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > btw)) { best = eff; bth = th; btw = tw; }
+  }
+  *TH = bth; *TW = btw;
+}
+
+template <int BN, int BK, int ST>
+static int32_t launch_conv(const CUtensorMap& mx, const CUtensorMap& mw, const ConvKParams& P, dim3 grid,
+                           cudaStream_t st) {
+  using S = ConvSmem<BN, BK, ST>;
+  auto kern = conv_tc_kernel<BN, BK, ST>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) return set_error(C3D_ECUDA, "conv smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  kern<<<grid, 192, S::kTotal, st>>>(mx, mw, P);
+  return check_launch("conv_tc_kernel");
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient: dW[co][kh][kw][ci] += sum_pixels dY[p][co] * X[p*stride + tap - pad][ci].
+// GEMM view per tap: M = Cout (128 per CTA), N = Cin tile, K = pixels.  Both operands are
+// "MN-major" for the tensor core (the contiguous NHWC channel axis is M resp. N, pixels are K):
+// the very same 4-D TMA boxes as the forward pass ([RH][RW][64 channels], 128B swizzle) are
+// consumed through MN-major shared-memory descriptors.  Grid = (pixel-range split, tap, co/ci
+// tile); split-K partials are reduced with fp32 atomics straight into the gradient arena.
+struct WgradKParams {
+  int N, Ho, Wo, Cout, Cin;
+  int KH, KW, stride, pad;
+  int RH, RW, tiles_h, tiles_w;
+  int num_tiles, tiles_per_split;
+  int ci_tiles;
+  float* dw;                  // [Cout][KH][KW][Cin] fp32, accumulated with atomics
+};
+
+template <int BLOCK_N, int STAGES>
+struct WgradSmem {
+  static constexpr int kChunk = 128 * 128;                    // one [<=128 px][64 ch] sub-tile slot
+  static constexpr int kStageBytes = kChunk * (2 + BLOCK_N / 64);
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                     const WgradKParams P) {
+  using S = WgradSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int split = blockIdx.x, tap = blockIdx.y;
+  const int co_tile = blockIdx.z / P.ci_tiles, ci_tile = blockIdx.z - co_tile * P.ci_tiles;
+  const int co0 = co_tile * 128, ci0 = ci_tile * BLOCK_N;
+  const int kh = tap / P.KW, kw = tap - kh * P.KW;
+  const int t_begin = split * P.tiles_per_split;
+  const int t_end = min(P.num_tiles, t_begin + P.tiles_per_split);
+  const int R = P.RH * P.RW;
+  const int a_chunks = (P.Cout - co0) > 64 ? 2 : 1;
+  int b_chunks = (P.Cin - ci0 + 63) / 64; if (b_chunks > BLOCK_N / 64) b_chunks = BLOCK_N / 64;
+
+  if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&tmap_dy); ptx::prefetch_tensormap(&tmap_x); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<BLOCK_N>(tmem_ptr);
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (t_begin < t_end) {
+    if (warp == 0) {
+      if (ptx::elect_one()) {
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t bytes = (uint32_t)(R * 128 * (a_chunks + b_chunks));
+        for (int t = t_begin; t < t_end; ++t) {
+          const int tw_i = t % P.tiles_w, th_i = (t / P.tiles_w) % P.tiles_h, img = t / (P.tiles_w * P.tiles_h);
+          const int ho0 = th_i * P.RH, wo0 = tw_i * P.RW;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          ptx::mbar_expect_tx(&full_bar[stage], bytes);
+          for (int c = 0; c < a_chunks; ++c)
+            ptx::tma_load_4d(sa + c * S::kChunk, &tmap_dy, &full_bar[stage], co0 + 64 * c, wo0, ho0, img);
+          for (int c = 0; c < b_chunks; ++c)
+            ptx::tma_load_4d(sa + (2 + c) * S::kChunk, &tmap_x, &full_bar[stage], ci0 + 64 * c,
+                             wo0 * P.stride + kw - P.pad, ho0 * P.stride + kh - P.pad, img);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (ptx::elect_one()) {
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N, 1, 1);
+        int stage = 0; uint32_t phase = 0;
+        const int ksteps = R / 16;
+        for (int t = t_begin; t < t_end; ++t) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tcgen05_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sb = sa + 2 * S::kChunk;
+          // MN-major, 128B swizzle: LBO = distance between 64-channel chunks, SBO = 8 pixel rows
+          const uint64_t da = ptx::make_smem_desc(sa, S::kChunk, 1024, 2);
+          const uint64_t db = ptx::make_smem_desc(sb, S::kChunk, 1024, 2);
+          for (int k = 0; k < ksteps; ++k) {
+            // 16 pixel rows = 2048 bytes per K step: +128 in the (addr>>4) field
+            ptx::umma_bf16(tmem_base, da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc,
+                           (t != t_begin || k != 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(tmem_full_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      const int co = co0 + q * 32 + lane;
+      ptx::mbar_wait(tmem_full_bar, 0);
+      ptx::tcgen05_fence_after();
+      const int n_valid = min(BLOCK_N, P.Cin - ci0);
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 16; ++ch) {
+        if (ch * 16 >= n_valid) break;                    // warp-uniform
+        uint32_t v[16];
+        ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), v);
+        ptx::tmem_ld_wait();
+        if (co < P.Cout) {
+          float* dst = P.dw + ((size_t)co * (P.KH * P.KW) + tap) * P.Cin + ci0 + ch * 16;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+        }
+      }
+    }
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc<BLOCK_N>(tmem_base);
+  }
+}
+
+// pixel box for wgrad: RH*RW must be a multiple of 16 (UMMA K) and <= 128
+static void pick_tile_k(int Ho, int Wo, int stride, int* RH, int* RW) {
+  double best = -1; int bth = 1, btw = 16;
+  for (int tw = 1; tw <= 128; ++tw) {
+    if (tw * stride > 256) break;
+    if (tw > Wo && tw != 16) continue;
+    for (int th = 1; th * tw <= 128; ++th) {
+      if ((th * tw) % 16 != 0 || th * stride > 256) continue;
+      long long tiles = (long long)((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
+      double eff = (double)Ho * Wo / (double)(tiles * th * tw) * (th * tw >= 64 ? 1.0 : 0.9);
+      if (eff > best + 1e-9 || (eff > best - 1e-9 && th * tw > bth * btw)) { best = eff; bth = th; btw = tw; }
+    }
+  }
+  *RH = bth; *RW = btw;
+}
+
+template <int BN, int ST>
+static int32_t launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgradKParams& P, dim3 grid,
+                            cudaStream_t st) {
+  using S = WgradSmem<BN, ST>;
+  auto kern = conv_wgrad_tc_kernel<BN, ST>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) return set_error(C3D_ECUDA, "wgrad smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  kern<<<grid, 192, S::kTotal, st>>>(mdy, mx, P);
+  return check_launch("conv_wgrad_tc_kernel");
+}
+
+}  // namespace c3d
+
+using namespace c3d;
+
+extern "C" int32_t c3d_conv2d_tiles(const c3d_conv_desc* d, int32_t* tiles_m, int32_t* TH, int32_t* TW) {
+  if (!d) return set_error(C3D_EINVAL, "null desc");
+  int Ho = (d->H + 2 * d->pad - d->KH) / d->stride + 1;
+  int Wo = (d->W + 2 * d->pad - d->KW) / d->stride + 1;
+  int th, tw;
+  pick_tile(Ho, Wo, d->stride, &th, &tw);
+  if (TH) *TH = th;
+  if (TW) *TW = tw;
+  if (tiles_m) *tiles_m = d->N * ((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
+  return C3D_OK;
+}
+
+extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const void* w, const float* bias,
+                                  const void* addend, void* y, float* stats, void* stream) {
+  if (!d || !x || !w || !y) return set_error(C3D_EINVAL, "conv2d: null pointer");
+  const int Cin = d->Cin, Cout = d->Cout;
+  if (Cin % 16 != 0 || Cin <= 0) return set_error(C3D_EINVAL, "conv2d: Cin=%d must be a multiple of 16", Cin);
+  if (Cout % 16 != 0 || Cout <= 0) return set_error(C3D_EINVAL, "conv2d: Cout=%d must be a multiple of 16", Cout);
+  if (d->stride < 1 || d->stride > 2) return set_error(C3D_EINVAL, "conv2d: stride %d unsupported", d->stride);
+  const int BK = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
+  int BN = 128;
+  if (Cout % 128 != 0) BN = (Cout % 64 == 0) ? 64 : (Cout % 32 == 0 ? 32 : 16);
+  const int Ho = (d->H + 2 * d->pad - d->KH) / d->stride + 1;
+  const int Wo = (d->W + 2 * d->pad - d->KW) / d->stride + 1;
+  if (d->add_mode == 2 && ((Ho & 1) || (Wo & 1))) return set_error(C3D_EINVAL, "conv2d: up2 addend needs even output");
+  if (d->add_mode && !addend) return set_error(C3D_EINVAL, "conv2d: addend missing");
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error(C3D_ECUDA, "cuTensorMapEncodeTiled unavailable");
+
+  ConvKParams P;
+  P.N = d->N; P.Ho = Ho; P.Wo = Wo; P.Cout = Cout; P.KH = d->KH; P.KW = d->KW; P.stride = d->stride; P.pad = d->pad;
+  pick_tile(Ho, Wo, d->stride, &P.TH, &P.TW);
+  P.tiles_h = (Ho + P.TH - 1) / P.TH; P.tiles_w = (Wo + P.TW - 1) / P.TW;
+  P.kc_blocks = Cin / BK; P.Cin = Cin;
+  P.bias = bias; P.relu = d->relu; P.out_fp32 = d->out_fp32; P.add_mode = d->add_mode;
+  P.addend = static_cast<const bf16*>(addend);
+  P.add_pix_stride = d->add_pix_stride ? d->add_pix_stride : Cout;
+  P.out = y; P.out_pix_stride = d->y_pix_stride ? d->y_pix_stride : Cout;
+  P.stats = stats;
+  const long long xps = d->x_pix_stride ? d->x_pix_stride : Cin;
+
+  CUtensorMap mx, mw;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)xps * 2, (cuuint64_t)xps * 2 * d->W, (cuuint64_t)xps * 2 * d->W * d->H};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(P.TW * d->stride), (cuuint32_t)(P.TH * d->stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz(BK * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(C3D_ECUDA, "encode x tensormap failed: %d", (int)r);
+  }
+  {
+    const long long Kt = (long long)d->KH * d->KW * Cin;
+    cuuint64_t dims[2] = {(cuuint64_t)Kt, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)Kt * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz(BK * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(C3D_ECUDA, "encode w tensormap failed: %d", (int)r);
+  }
+  dim3 grid((unsigned)(d->N * P.tiles_h * P.tiles_w), (unsigned)(Cout / BN));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define C3D_CONV_CASE(bn, bk, stg) \
+  if (BN == bn && BK == bk) return launch_conv<bn, bk, stg>(mx, mw, P, grid, st);
+  C3D_CONV_CASE(128, 64, 3)
+  C3D_CONV_CASE(64, 64, 4)
+  C3D_CONV_CASE(32, 64, 4)
+  C3D_CONV_CASE(16, 64, 4)
+  C3D_CONV_CASE(128, 32, 4)
+  C3D_CONV_CASE(64, 32, 4)
+  C3D_CONV_CASE(32, 32, 4)
+  C3D_CONV_CASE(16, 32, 4)
+  C3D_CONV_CASE(128, 16, 4)
+  C3D_CONV_CASE(64, 16, 4)
+  C3D_CONV_CASE(32, 16, 4)
+  C3D_CONV_CASE(16, 16, 4)
+#undef C3D_CONV_CASE
+  return set_error(C3D_EINVAL, "conv2d: no kernel for BN=%d BK=%d", BN, BK);
+}
+
+extern "C" int32_t c3d_conv2d_wgrad(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
+  if (!d || !x || !dy || !dw) return set_error(C3D_EINVAL, "wgrad: null pointer");
+  const int Cin = d->Cin, Cout = d->Cout;
+  if (Cin % 8 != 0 || Cout % 8 != 0) return set_error(C3D_EINVAL, "wgrad: channels must be multiples of 8");
+  if (d->stride < 1 || d->stride > 2) return set_error(C3D_EINVAL, "wgrad: stride %d unsupported", d->stride);
+  const int Ho = (d->H + 2 * d->pad - d->KH) / d->stride + 1;
+  const int Wo = (d->W + 2 * d->pad - d->KW) / d->stride + 1;
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error(C3D_ECUDA, "cuTensorMapEncodeTiled unavailable");
+  WgradKParams P;
+  P.N = d->N; P.Ho = Ho; P.Wo = Wo; P.Cout = Cout; P.Cin = Cin;
+  P.KH = d->KH; P.KW = d->KW; P.stride = d->stride; P.pad = d->pad;
+  pick_tile_k(Ho, Wo, d->stride, &P.RH, &P.RW);
+  P.tiles_h = (Ho + P.RH - 1) / P.RH; P.tiles_w = (Wo + P.RW - 1) / P.RW;
+  P.num_tiles = d->N * P.tiles_h * P.tiles_w;
+  const int BN = Cin > 128 ? 256 : (Cin > 64 ? 128 : 64);
+  P.ci_tiles = (Cin + BN - 1) / BN;
+  const int co_tiles = (Cout + 127) / 128;
+  const int taps = d->KH * d->KW;
+  // split the pixel range so the grid is ~4 waves of 148 SMs
+  long long base = (long long)taps * co_tiles * P.ci_tiles;
+  int splits = (int)((4LL * kNumSMs + base - 1) / base);
+  if (splits > P.num_tiles) splits = P.num_tiles;
+  if (splits < 1) splits = 1;
+  P.tiles_per_split = (P.num_tiles + splits - 1) / splits;
+  splits = (P.num_tiles + P.tiles_per_split - 1) / P.tiles_per_split;
+  P.dw = dw;
+  const long long xps = d->x_pix_stride ? d->x_pix_stride : Cin;
+  const long long yps = d->y_pix_stride ? d->y_pix_stride : Cout;
+  CUtensorMap mdy, mx;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)yps * 2, (cuuint64_t)yps * 2 * Wo, (cuuint64_t)yps * 2 * Wo * Ho};
+    cuuint32_t box[4] = {64, (cuuint32_t)P.RW, (cuuint32_t)P.RH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&mdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(C3D_ECUDA, "encode dy tensormap failed: %d", (int)r);
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)xps * 2, (cuuint64_t)xps * 2 * d->W, (cuuint64_t)xps * 2 * d->W * d->H};
+    cuuint32_t box[4] = {64, (cuuint32_t)(P.RW * d->stride), (cuuint32_t)(P.RH * d->stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(C3D_ECUDA, "encode x tensormap failed: %d", (int)r);
+  }
+  dim3 grid((unsigned)splits, (unsigned)taps, (unsigned)(co_tiles * P.ci_tiles));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (BN == 256) return launch_wgrad<256, 2>(mdy, mx, P, grid, st);
+  if (BN == 128) return launch_wgrad<128, 3>(mdy, mx, P, grid, st);
+  return launch_wgrad<64, 4>(mdy, mx, P, grid, st);
+}
