@@ -163,9 +163,8 @@ def configurable(init_func=None, *, from_config=None):
     if init_func is not None:
         @functools.wraps(init_func)
         def wrapped(self, *args, **kwargs):
-            fc = type(self).from_config
             if _called_with_cfg(*args, **kwargs):
-                explicit = _get_args_from_config(fc, *args, **kwargs)
+                explicit = _get_args_from_config(type(self).from_config, *args, **kwargs)
                 init_func(self, **explicit)
             else:
                 init_func(self, *args, **kwargs)

@@ -18,11 +18,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 D2LITE = os.path.join(HERE, "d2lite")
 
 
+class _AnyMeta(type):
+    def __getattr__(cls, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return lambda *a, **k: None
+
+
 class _Stub(types.ModuleType):
     def __getattr__(self, name):
         if name.startswith("__"):
             raise AttributeError(name)
-        cls = type(name, (), {"__init__": lambda self, *a, **k: None, "__call__": lambda self, *a, **k: None})
+        cls = _AnyMeta(name, (), {"__init__": lambda self, *a, **k: None, "__call__": lambda self, *a, **k: None,
+                                  "__getattr__": lambda self, n: (lambda *a, **k: None)})
         setattr(self, name, cls)
         return cls
 
