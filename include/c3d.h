@@ -91,6 +91,73 @@ int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const void* w, con
  * Split-K over pixels with fp32 atomics: the caller zeroes (or pre-loads) dw. */
 int32_t c3d_conv2d_wgrad(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * HBM-bound NHWC bf16 kernels around the convolutions.
+ * Replace nn.BatchNorm2d(train) + ReLU + residual add (cubercnn/modeling/backbone/dla.py:17,58-66,
+ * 168-172), nn.MaxPool2d(2,2) (dla.py:209), GeneralizedRCNN.preprocess_image (rcnn3d.py:46,87) and the
+ * SGD step + per-parameter finite check (tools/train_net.py:226-252, cubercnn/solver/build.py:47-56).
+ * ------------------------------------------------------------------------------------------ */
+/* per-channel batch statistics from the conv epilogue partials [rows][2][C] -> mean, rstd (+ running stats) */
+int32_t c3d_bn_finalize(const float* partial, int32_t rows, int32_t C, double count, float eps, float momentum,
+                        float* running_mean, float* running_var, float* mean_out, float* rstd_out, void* stream);
+/* out = [relu]((y-mean)*rstd*gamma+beta [+ residual]); y,out,residual bf16 (P pixels x C) */
+int32_t c3d_bn_apply(const void* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                     const void* residual, int32_t relu, void* out, int64_t P, int32_t C, int64_t res_stride,
+                     int64_t out_stride, void* stream);
+/* rows of the `partial` scratch needed by c3d_bn_bwd */
+int32_t c3d_bn_bwd_blocks(int64_t P, int32_t C);
+/* BatchNorm(+ReLU,+residual) backward: dy (bf16) w.r.t. the conv output, dgamma/dbeta accumulated (+=),
+ * optional dres = masked dout for the residual branch. partial: fp32 [blocks][2][C]; coef: fp32 [3][C]. */
+int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, const float* mean, const float* rstd,
+                   const float* gamma, int32_t relu, float* partial, float* coef, float* dgamma, float* dbeta,
+                   void* dy, void* dres, int64_t P, int32_t C, int64_t dout_stride, int64_t out_stride,
+                   int64_t dres_stride, void* stream);
+int32_t c3d_maxpool2_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int64_t x_stride,
+                         int64_t y_stride, void* stream);
+int32_t c3d_maxpool2_bwd(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C,
+                         int64_t x_stride, int64_t dy_stride, void* stream);
+/* (3,H,W) fp32 BGR image -> (Hp,Wp,Cp) bf16 NHWC slot: (x-mean)/std in channels 0..2, zeros elsewhere */
+int32_t c3d_preprocess_image(const float* img, int32_t H, int32_t W, void* out_slot, int32_t Hp, int32_t Wp,
+                             int32_t Cp, const float* mean3_host, const float* std3_host, void* stream);
+/* flag |= 1 if any gradient element is NaN/Inf */
+int32_t c3d_grad_finite(const float* g, int64_t n, int32_t* flag, void* stream);
+/* torch.optim.SGD(momentum, weight_decay) over a flat arena; no-op if *skip_flag != 0 */
+int32_t c3d_sgd_momentum(float* p, const float* g, float* mom, int64_t n, float lr, float momentum,
+                         float weight_decay, float grad_scale, const int32_t* skip_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-level ROIAlign (aligned=True, sampling_ratio 0) on NHWC bf16 FPN maps.
+ * Replaces detectron2 ROIPooler/ROIAlignV2 at cubercnn/modeling/roi_heads/roi_heads.py:267,362.
+ * rois: fp32 [R][6] = (batch index, level index, x1, y1, x2, y2).  out: bf16 [R][ph][pw][C].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* feat[5];   /* level l: bf16 (N,H[l],W[l],C) */
+  void* grad[5];         /* backward only: fp32 (N,H[l],W[l],C), accumulated with atomics */
+  int32_t H[5], W[5];
+  float scale[5];
+  int32_t num_levels;
+} c3d_roi_levels;
+int32_t c3d_roi_align_fwd(const c3d_roi_levels* levels, const float* rois, int32_t R, int32_t C, int32_t pooled_h,
+                          int32_t pooled_w, void* out, void* stream);
+int32_t c3d_roi_align_bwd(const c3d_roi_levels* levels, const float* rois, int32_t R, int32_t C, int32_t pooled_h,
+                          int32_t pooled_w, const void* dout, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched greedy NMS (all images, two launches, no host sync).
+ * Replaces torchvision nms behind detectron2 batched_nms in find_top_rpn_proposals (SURVEY A.3;
+ * configs/Base.yaml:51-54).  boxes: fp32 [B][n][4] sorted by score desc per image (already shifted by the
+ * per-level coordinate-trick offsets), nvalid[B] valid candidates.  keep_idx: int32 [B][max_keep] indices
+ * into the sorted list in score order (-1 padded); keep_cnt[B].  n <= 8192.
+ * cats (fp32 [B][n], may be NULL) = per-box category (FPN level); maxc (fp32 [B]) = per-image max coordinate:
+ * images with 4*nvalid <= trick_max_numel use torchvision's coordinate trick (shift by cat*(maxc+1)),
+ * larger ones plain same-category suppression — the two code paths of torchvision.ops.batched_nms.
+ * ------------------------------------------------------------------------------------------ */
+size_t c3d_nms_workspace_bytes(int32_t B, int32_t n);
+int32_t c3d_nms_batched(const float* boxes, const int32_t* nvalid, const float* cats, const float* maxc,
+                        int32_t trick_max_numel, int32_t B, int32_t n, float iou_thresh,
+                        int32_t max_keep, int32_t* keep_idx, int32_t* keep_cnt, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

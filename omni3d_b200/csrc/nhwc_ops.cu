@@ -1,0 +1,379 @@
+// nhwc_ops.cu — HBM-bound NHWC bf16 kernels around the tensor-core convolutions (sm_100a):
+// train-mode BatchNorm (finalize / apply+residual+ReLU / backward reduce+apply), 2x2 max-pool,
+// image normalisation + channel padding, fused SGD-momentum with finite check.
+//
+// Replaces the ATen/cuDNN calls behind nn.BatchNorm2d + ReLU + residual add
+// (cubercnn/modeling/backbone/dla.py:17,58-66,168-172), nn.MaxPool2d (dla.py:209),
+// GeneralizedRCNN.preprocess_image (called at rcnn3d.py:46,87) and the optimizer step +
+// per-parameter finite check (tools/train_net.py:226-252, cubercnn/solver/build.py:47-56).
+// All kernels: 16-byte vector loads (8 bf16 channels per thread), channel-innermost coalescing,
+// grid = multiple of 148 SMs with grid-stride loops; no tensor cores (byte work).
+#include <cuda_bf16.h>
+#include "c3d_common.cuh"
+
+namespace c3d {
+using bf16 = __nv_bfloat16;
+
+struct V8 { float v[8]; };
+__device__ __forceinline__ V8 ld8(const bf16* p) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  V8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y; }
+  return r;
+}
+__device__ __forceinline__ void st8(bf16* p, const V8& a) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(a.v[2 * i], a.v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+static inline int grid_for(long long work_items, int threads) {
+  long long b = (work_items + threads - 1) / threads;
+  long long cap = (long long)kNumSMs * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ---- BatchNorm forward ------------------------------------------------------------------------
+// partial: [rows][2][C] per-tile (sum, sumsq) from the conv epilogue.  One thread per channel.
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count, float eps,
+                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, s2 = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    s += (double)partial[(size_t)r * 2 * C + c];
+    s2 += (double)partial[(size_t)r * 2 * C + C + c];
+  }
+  double mean = s / count;
+  double var = s2 / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mean_out[c] = (float)mean;
+  rstd_out[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+}
+
+// out = [relu]( (y - mean) * rstd * gamma + beta [+ residual] ), P pixels x C channels
+__global__ void bn_apply_kernel(const bf16* __restrict__ y, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const bf16* __restrict__ residual, int relu,
+                                bf16* __restrict__ out, long long P, int C, long long res_stride,
+                                long long out_stride) {
+  const int cv = C >> 3;
+  const long long total = P * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / cv;
+    const int c = (int)(i - p * cv) << 3;
+    V8 a = ld8(y + p * C + c);
+    V8 r;
+    if (residual) r = ld8(residual + p * res_stride + c);
+    V8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float sc = __ldg(rstd + c + k) * __ldg(gamma + c + k);
+      float v = (a.v[k] - __ldg(mean + c + k)) * sc + __ldg(beta + c + k);
+      if (residual) v += r.v[k];
+      o.v[k] = relu ? fmaxf(v, 0.f) : v;
+    }
+    st8(out + p * out_stride + c, o);
+  }
+}
+
+// ---- BatchNorm backward -----------------------------------------------------------------------
+// dz = dout * (out > 0 if relu);  partial[block][0][c] = sum dz, partial[block][1][c] = sum dz * xhat
+template <int THREADS>
+__global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out,
+                                     const bf16* __restrict__ y, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd, int relu, float* __restrict__ partial,
+                                     long long P, int C, long long dout_stride, long long out_stride) {
+  // thread layout: tx = channel-vector index (C/8 of them), rows strided by (THREADS / cv)
+  const int cv = C >> 3;
+  const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
+  const int rows_per_block = THREADS / cv;
+  float s[8], t[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s[k] = 0.f; t[k] = 0.f; }
+  const int c = tx << 3;
+  float m[8], rs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { m[k] = mean[c + k]; rs[k] = rstd[c + k]; }
+  if (ty < rows_per_block) {
+    for (long long p = (long long)blockIdx.x * rows_per_block + ty; p < P; p += (long long)gridDim.x * rows_per_block) {
+      V8 d = ld8(dout + p * dout_stride + c);
+      V8 yy = ld8(y + p * C + c);
+      if (relu) {
+        V8 o = ld8(out + p * out_stride + c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (!(o.v[k] > 0.f)) d.v[k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s[k] += d.v[k]; t[k] += d.v[k] * ((yy.v[k] - m[k]) * rs[k]); }
+    }
+  }
+  __shared__ float sm[2][THREADS][8 + 1];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sm[0][threadIdx.x][k] = s[k]; sm[1][threadIdx.x][k] = t[k]; }
+  __syncthreads();
+  // fixed-order reduction over ty for each channel (deterministic)
+  for (int idx = threadIdx.x; idx < 2 * C; idx += THREADS) {
+    const int which = idx / C, ch = idx - which * C;
+    const int vx = ch >> 3, k = ch & 7;
+    float acc = 0.f;
+    for (int r = 0; r < rows_per_block; ++r) acc += sm[which][r * cv + vx][k];
+    partial[((size_t)blockIdx.x * 2 + which) * C + ch] = acc;
+  }
+}
+
+// coef[0][c] = gamma*rstd, coef[1][c] = mean(dz), coef[2][c] = mean(dz*xhat); dgamma/dbeta accumulated (+=)
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, double count,
+                                       const float* __restrict__ gamma, const float* __restrict__ rstd,
+                                       float* __restrict__ coef, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, t = 0.0;
+  for (int b = 0; b < blocks; ++b) {
+    s += (double)partial[((size_t)b * 2 + 0) * C + c];
+    t += (double)partial[((size_t)b * 2 + 1) * C + c];
+  }
+  coef[c] = gamma[c] * rstd[c];
+  coef[C + c] = (float)(s / count);
+  coef[2 * C + c] = (float)(t / count);
+  if (dgamma) dgamma[c] += (float)t;
+  if (dbeta) dbeta[c] += (float)s;
+}
+
+// dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat));  optionally dres = dz
+__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out,
+                                    const bf16* __restrict__ y, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, const float* __restrict__ coef, int relu,
+                                    bf16* __restrict__ dy, bf16* __restrict__ dres, long long P, int C,
+                                    long long dout_stride, long long out_stride, long long dres_stride) {
+  const int cv = C >> 3;
+  const long long total = P * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / cv;
+    const int c = (int)(i - p * cv) << 3;
+    V8 d = ld8(dout + p * dout_stride + c);
+    V8 yy = ld8(y + p * C + c);
+    if (relu) {
+      V8 o = ld8(out + p * out_stride + c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if (!(o.v[k] > 0.f)) d.v[k] = 0.f;
+    }
+    V8 g;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float xh = (yy.v[k] - __ldg(mean + c + k)) * __ldg(rstd + c + k);
+      g.v[k] = __ldg(coef + c + k) * (d.v[k] - __ldg(coef + C + c + k) - xh * __ldg(coef + 2 * C + c + k));
+    }
+    st8(dy + p * C + c, g);
+    if (dres) st8(dres + p * dres_stride + c, d);
+  }
+}
+
+// ---- 2x2 stride-2 max pool (NHWC) -------------------------------------------------------------
+__global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C,
+                                    long long x_stride, long long y_stride) {
+  const int Ho = H >> 1, Wo = W >> 1, cv = C >> 3;
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) << 3;
+    long long p = i / cv;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    const long long base = ((long long)n * H + 2 * ho) * W + 2 * wo;
+    V8 a = ld8(x + base * x_stride + c), b = ld8(x + (base + 1) * x_stride + c);
+    V8 d = ld8(x + (base + W) * x_stride + c), e = ld8(x + (base + W + 1) * x_stride + c);
+    V8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(fmaxf(a.v[k], b.v[k]), fmaxf(d.v[k], e.v[k]));
+    st8(y + (((long long)n * Ho + ho) * Wo + wo) * y_stride + c, o);
+  }
+}
+// dx (N,H,W,C) = dy routed to the first maximal element of each window (row-major window order)
+__global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx,
+                                    int N, int H, int W, int C, long long x_stride, long long dy_stride) {
+  const int Ho = H >> 1, Wo = W >> 1, cv = C >> 3;
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) << 3;
+    long long p = i / cv;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    const long long base = ((long long)n * H + 2 * ho) * W + 2 * wo;
+    const long long off[4] = {base, base + 1, base + W, base + W + 1};
+    V8 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = ld8(x + off[j] * x_stride + c);
+    V8 g = ld8(dy + (((long long)n * Ho + ho) * Wo + wo) * dy_stride + c);
+    V8 o[4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int best = 0; float bv = v[0].v[k];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) if (v[j].v[k] > bv) { bv = v[j].v[k]; best = j; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j].v[k] = (j == best) ? g.v[k] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st8(dx + off[j] * C + c, o[j]);
+  }
+}
+
+// ---- image normalisation: (3,H,W) fp32 BGR -> (Hp,Wp,Cp) bf16 NHWC slot, zero padded --------------
+__global__ void preprocess_kernel(const float* __restrict__ img, int H, int W, bf16* __restrict__ out, int Hp,
+                                  int Wp, int Cp, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const long long total = (long long)Hp * Wp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % Wp), h = (int)(i / Wp);
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (h < H && w < W) {
+      const long long o = (long long)h * W + w;
+      v0 = (img[o] - m0) / s0;
+      v1 = (img[(long long)H * W + o] - m1) / s1;
+      v2 = (img[2LL * H * W + o] - m2) / s2;
+    }
+    bf16* dst = out + i * Cp;
+    for (int c = 0; c < Cp; c += 8) {
+      V8 z;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) z.v[k] = 0.f;
+      if (c == 0) { z.v[0] = v0; z.v[1] = v1; z.v[2] = v2; }
+      st8(dst + c, z);
+    }
+  }
+}
+
+// ---- fused SGD momentum (+weight decay) with finite check ----------------------------------------
+// flags[0] != 0 on entry => skip (another rank or the loss check vetoed the step).  The finite scan is a
+// separate tiny pass (grad_finite_kernel) so that all ranks can agree before anyone updates.
+__global__ void grad_finite_kernel(const float* __restrict__ g, long long n, int* __restrict__ flag) {
+  int bad = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = g[i];
+    if (!(fabsf(v) <= 3.402823466e38f)) bad = 1;     // NaN or Inf
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+__global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom,
+                                    long long n, float lr, float momentum, float wd, float grad_scale,
+                                    const int* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag) return;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float d = g[i] * grad_scale + wd * p[i];
+    float b = momentum * mom[i] + d;        // torch.optim.SGD: buf = momentum*buf + d (dampening 0)
+    mom[i] = b;
+    p[i] = p[i] - lr * b;
+  }
+}
+
+}  // namespace c3d
+
+using namespace c3d;
+#define C3D_REQ(cond, msg) do { if (!(cond)) return set_error(C3D_EINVAL, msg); } while (0)
+
+extern "C" int32_t c3d_bn_finalize(const float* partial, int32_t rows, int32_t C, double count, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* mean_out,
+                                   float* rstd_out, void* stream) {
+  C3D_REQ(partial && mean_out && rstd_out && rows > 0 && C > 0, "bn_finalize: bad args");
+  bn_finalize_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(partial, rows, C, count, eps, momentum,
+                                                                     running_mean, running_var, mean_out, rstd_out);
+  return check_launch("bn_finalize");
+}
+extern "C" int32_t c3d_bn_apply(const void* y, const float* mean, const float* rstd, const float* gamma,
+                                const float* beta, const void* residual, int32_t relu, void* out, int64_t P,
+                                int32_t C, int64_t res_stride, int64_t out_stride, void* stream) {
+  C3D_REQ(y && mean && rstd && gamma && beta && out && C % 8 == 0, "bn_apply: bad args");
+  if (P == 0) return C3D_OK;
+  bn_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)y, mean, rstd, gamma, beta, (const bf16*)residual, relu, (bf16*)out, P, C,
+      res_stride ? res_stride : C, out_stride ? out_stride : C);
+  return check_launch("bn_apply");
+}
+extern "C" int32_t c3d_bn_bwd_blocks(int64_t P, int32_t C) {
+  if (C % 8 != 0 || C > 2048) return 0;
+  int rows = 256 / (C / 8); if (rows < 1) rows = 1;
+  long long b = (P + rows * 8LL - 1) / (rows * 8LL);
+  if (b > kNumSMs * 4) b = kNumSMs * 4;
+  if (b < 1) b = 1;
+  return (int32_t)b;
+}
+extern "C" int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, const float* mean, const float* rstd,
+                              const float* gamma, int32_t relu, float* partial /*[blocks][2][C]*/, float* coef /*[3][C]*/,
+                              float* dgamma, float* dbeta, void* dy, void* dres, int64_t P, int32_t C,
+                              int64_t dout_stride, int64_t out_stride, int64_t dres_stride, void* stream) {
+  C3D_REQ(dout && y && mean && rstd && gamma && partial && coef && dy && C % 8 == 0 && C <= 2048, "bn_bwd: bad args");
+  C3D_REQ(!relu || out, "bn_bwd: relu needs the forward output");
+  if (P == 0) return C3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = c3d_bn_bwd_blocks(P, C);
+  const long long ds = dout_stride ? dout_stride : C, os = out_stride ? out_stride : C;
+  if (C / 8 <= 256)
+    bn_bwd_reduce_kernel<256><<<blocks, 256, 0, st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)y, mean, rstd,
+                                                       relu, partial, P, C, ds, os);
+  else
+    return set_error(C3D_EINVAL, "bn_bwd: C too large");
+  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(partial, blocks, C, (double)P, gamma, rstd, coef, dgamma, dbeta);
+  bn_bwd_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)y,
+                                                                   mean, rstd, coef, relu, (bf16*)dy, (bf16*)dres, P, C,
+                                                                   ds, os, dres_stride ? dres_stride : C);
+  return check_launch("bn_bwd");
+}
+extern "C" int32_t c3d_maxpool2_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
+                                    int64_t x_stride, int64_t y_stride, void* stream) {
+  C3D_REQ(x && y && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2: bad args");
+  long long work = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  if (work == 0) return C3D_OK;
+  maxpool2_fwd_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (bf16*)y, N, H, W, C, x_stride ? x_stride : C, y_stride ? y_stride : C);
+  return check_launch("maxpool2_fwd");
+}
+extern "C" int32_t c3d_maxpool2_bwd(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W,
+                                    int32_t C, int64_t x_stride, int64_t dy_stride, void* stream) {
+  C3D_REQ(x && dy && dx && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_bwd: bad args");
+  long long work = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  if (work == 0) return C3D_OK;
+  maxpool2_bwd_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)dy, (bf16*)dx, N, H, W, C, x_stride ? x_stride : C, dy_stride ? dy_stride : C);
+  return check_launch("maxpool2_bwd");
+}
+extern "C" int32_t c3d_preprocess_image(const float* img, int32_t H, int32_t W, void* out_slot, int32_t Hp,
+                                        int32_t Wp, int32_t Cp, const float* mean3_host, const float* std3_host,
+                                        void* stream) {
+  C3D_REQ(img && out_slot && mean3_host && std3_host && Cp % 8 == 0 && Hp >= H && Wp >= W, "preprocess: bad args");
+  preprocess_kernel<<<grid_for((long long)Hp * Wp, 256), 256, 0, (cudaStream_t)stream>>>(
+      img, H, W, (bf16*)out_slot, Hp, Wp, Cp, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0],
+      std3_host[1], std3_host[2]);
+  return check_launch("preprocess");
+}
+extern "C" int32_t c3d_grad_finite(const float* g, int64_t n, int32_t* flag, void* stream) {
+  C3D_REQ(g && flag, "grad_finite: bad args");
+  if (n == 0) return C3D_OK;
+  grad_finite_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(g, n, flag);
+  return check_launch("grad_finite");
+}
+extern "C" int32_t c3d_sgd_momentum(float* p, const float* g, float* mom, int64_t n, float lr, float momentum,
+                                    float weight_decay, float grad_scale, const int32_t* skip_flag, void* stream) {
+  C3D_REQ(p && g && mom, "sgd: bad args");
+  if (n == 0) return C3D_OK;
+  sgd_momentum_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, mom, n, lr, momentum, weight_decay,
+                                                                           grad_scale, skip_flag);
+  return check_launch("sgd");
+}

@@ -1,0 +1,216 @@
+"""DLA-34 / ResNet-34 bottom-up + FPN on the tcgen05 convolution kernels (NHWC bf16).
+
+Mirrors the module tree, parameter names and initialisation order of
+cubercnn/modeling/backbone/dla.py:40-68,156-321,417-507 and resnet.py:12-96 (+ detectron2 FPN), so a
+reference checkpoint's state_dict loads unchanged and the same seed gives the same initial weights.  The
+nn.Conv2d / nn.BatchNorm2d modules below are PARAMETER HOLDERS (their forward is never called — every
+convolution / BatchNorm / pooling runs through omni3d_b200.nnfunc on libc3d.so).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..nnfunc import ConvBias, ConvBNAct, MaxPool2
+from .registry import BACKBONE_REGISTRY
+
+
+def conv_bn(x, conv, bn, residual=None, relu=True):
+    """x NHWC bf16 -> [relu](BN(conv(x)) [+ residual]) through the fused kernels."""
+    w = conv.weight
+    if w.shape[1] != x.shape[-1]:                       # stem: Cin 3 zero-padded to the 16 the TMA box needs
+        w = F.pad(w, (0, 0, 0, 0, 0, x.shape[-1] - w.shape[1]))
+    return ConvBNAct.apply(x, w, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, conv.stride[0],
+                           conv.padding[0], relu, bn.training, bn.eps, bn.momentum)
+
+
+class BasicBlock(nn.Module):
+    def __init__(self, cin, cout, stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, 3, stride=1, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+
+    def forward(self, x, residual=None):
+        residual = x if residual is None else residual
+        y = conv_bn(x, self.conv1, self.bn1)
+        return conv_bn(y, self.conv2, self.bn2, residual=residual)
+
+
+class Root(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, 1, bias=False)
+        self.bn = nn.BatchNorm2d(cout)
+
+    def forward(self, *xs):
+        return conv_bn(torch.cat(xs, dim=-1), self.conv, self.bn)
+
+
+class Tree(nn.Module):
+    """dla.py:177-230.  For levels == 2 the outer `project` is dead weight in the reference (its output is
+    handed to an inner Tree that recomputes its own residual): parameters kept, never computed."""
+
+    def __init__(self, levels, cin, cout, stride=1, level_root=False, root_dim=0):
+        super().__init__()
+        root_dim = 2 * cout if root_dim == 0 else root_dim
+        if level_root:
+            root_dim += cin
+        if levels == 1:
+            self.tree1 = BasicBlock(cin, cout, stride)
+            self.tree2 = BasicBlock(cout, cout, 1)
+            self.root = Root(root_dim, cout)
+        else:
+            self.tree1 = Tree(levels - 1, cin, cout, stride)
+            self.tree2 = Tree(levels - 1, cout, cout, root_dim=root_dim + cout)
+        self.levels, self.level_root, self.stride = levels, level_root, stride
+        self.project = None
+        if cin != cout:
+            self.project = nn.Sequential(nn.Conv2d(cin, cout, 1, bias=False), nn.BatchNorm2d(cout))
+
+    def forward(self, x, children=None):
+        children = [] if children is None else children
+        bottom = MaxPool2.apply(x) if self.stride > 1 else x
+        if self.level_root:
+            children.append(bottom)
+        if self.levels == 1:
+            residual = conv_bn(bottom, self.project[0], self.project[1], relu=False) if self.project else bottom
+            x1 = self.tree1(x, residual)
+            x2 = self.tree2(x1)
+            return self.root(x2, x1, *children)
+        x1 = self.tree1(x)
+        children.append(x1)
+        return self.tree2(x1, children=children)
+
+
+class DLA34(nn.Module):
+    CH = [16, 32, 64, 128, 256, 512]
+    out_channels = {"p2": 64, "p3": 128, "p4": 256, "p5": 512, "p6": 512}
+    strides = {"p2": 4, "p3": 8, "p4": 16, "p5": 32, "p6": 64}
+
+    def __init__(self):
+        super().__init__()
+        c = self.CH
+
+        def cbr(cin, cout, k, stride=1):
+            return nn.Sequential(nn.Conv2d(cin, cout, k, stride=stride, padding=k // 2, bias=False),
+                                 nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+        self.base_layer = cbr(3, c[0], 7)
+        self.level0 = cbr(c[0], c[0], 3)
+        self.level1 = cbr(c[0], c[1], 3, stride=2)
+        self.level2 = Tree(1, c[1], c[2], 2, level_root=False)
+        self.level3 = Tree(2, c[2], c[3], 2, level_root=True)
+        self.level4 = Tree(2, c[3], c[4], 2, level_root=True)
+        self.level5 = Tree(1, c[4], c[5], 2, level_root=True)
+        for m in self.modules():            # dla.py:262-268
+            if isinstance(m, nn.Conv2d):
+                m.weight.data.normal_(0, math.sqrt(2.0 / (m.kernel_size[0] * m.kernel_size[1] * m.out_channels)))
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+
+    def forward(self, x):
+        for seq in (self.base_layer, self.level0, self.level1):
+            x = conv_bn(x, seq[0], seq[1])
+        out = {}
+        for i, name in zip(range(2, 6), ("p2", "p3", "p4", "p5")):
+            x = getattr(self, "level%d" % i)(x)
+            out[name] = x
+        out["p6"] = x[:, ::2, ::2, :].contiguous()        # F.max_pool2d(k=1, s=2), dla.py:474
+        return out
+
+
+class TVResNet(nn.Module):
+    """torchvision BasicBlock ResNet-18/34 topology (resnet.py:12-63); parameter names of torchvision."""
+    out_channels = DLA34.out_channels
+    strides = DLA34.strides
+
+    def __init__(self, depth):
+        super().__init__()
+        from torchvision import models
+        if depth not in (18, 34):
+            raise ValueError("accelerated path covers the BasicBlock ResNets (BASELINE: ResNet34); got %d" % depth)
+        base = getattr(models, "resnet%d" % depth)(weights=None)
+        for k in ("conv1", "bn1", "layer1", "layer2", "layer3", "layer4"):
+            setattr(self, k, getattr(base, k))
+
+    def forward(self, x):
+        x = conv_bn(x, self.conv1, self.bn1)
+        # 3x3 stride-2 pad-1 max pool of the torchvision stem (channels-last view, no copy of the big tensor)
+        x = F.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
+        out = {}
+        for name, layer in zip(("p2", "p3", "p4", "p5"), (self.layer1, self.layer2, self.layer3, self.layer4)):
+            for blk in layer:
+                idn = x
+                if blk.downsample is not None:
+                    idn = conv_bn(x, blk.downsample[0], blk.downsample[1], relu=False)
+                y = conv_bn(x, blk.conv1, blk.bn1)
+                x = conv_bn(y, blk.conv2, blk.bn2, residual=idn)
+            out[name] = x
+        out["p6"] = x[:, ::2, ::2, :].contiguous()
+        return out
+
+
+class FPN(nn.Module):
+    """detectron2 FPN: fpn_lateral{2..6} 1x1 + fpn_output{2..6} 3x3, both with bias; the
+    nearest-x2 upsample + sum of the top-down path is fused into the lateral conv's epilogue."""
+
+    def __init__(self, bottom_up, in_features, out_channels, make_p7=False):
+        super().__init__()
+        self.bottom_up = bottom_up
+        self.in_features = tuple(in_features)
+        self.stages = [int(math.log2(bottom_up.strides[f])) for f in in_features]
+        for f, s in zip(in_features, self.stages):
+            lat = nn.Conv2d(bottom_up.out_channels[f], out_channels, 1)
+            out = nn.Conv2d(out_channels, out_channels, 3, padding=1)
+            for m in (lat, out):        # c2_xavier_fill
+                nn.init.kaiming_uniform_(m.weight, a=1)
+                nn.init.constant_(m.bias, 0)
+            self.add_module("fpn_lateral%d" % s, lat)
+            self.add_module("fpn_output%d" % s, out)
+        self.size_divisibility = bottom_up.strides[in_features[-1]]
+        self._out_features = ["p%d" % s for s in self.stages]
+        self.out_strides = {"p%d" % s: 2 ** s for s in self.stages}
+        self.out_channels = out_channels
+        # ResNet variant: LastLevelMaxPool emits an unused p7 — never computed here.
+
+    def forward(self, x):
+        feats = self.bottom_up(x)
+        results, prev = {}, None
+        for f, s in reversed(list(zip(self.in_features, self.stages))):
+            lat, outc = getattr(self, "fpn_lateral%d" % s), getattr(self, "fpn_output%d" % s)
+            prev = ConvBias.apply(feats[f], lat.weight, lat.bias, prev, 1, 0, False, False)
+            results["p%d" % s] = ConvBias.apply(prev, outc.weight, outc.bias, None, 1, 1, False, False)
+        return {k: results[k] for k in self._out_features}
+
+
+def _check_weights(cfg):
+    if cfg.MODEL.WEIGHTS_PRETRAIN + cfg.MODEL.WEIGHTS == "":
+        raise RuntimeError("ImageNet download (dla.py:494-496 / resnet.py:76-79) is impossible offline: set "
+                           "MODEL.WEIGHTS_PRETRAIN (or MODEL.WEIGHTS) to a non-empty value for random init")
+
+
+@BACKBONE_REGISTRY.register()
+def build_dla_from_vision_fpn_backbone(cfg, input_shape=None, priors=None):
+    _check_weights(cfg)
+    if cfg.MODEL.DLA.TYPE != "dla34":
+        raise NotImplementedError("accelerated path covers dla34 (BASELINE configs); got " + cfg.MODEL.DLA.TYPE)
+    if cfg.MODEL.FPN.NORM != "" or cfg.MODEL.FPN.FUSE_TYPE != "sum":
+        raise NotImplementedError("FPN NORM/FUSE_TYPE other than ''/'sum'")
+    return FPN(DLA34(), cfg.MODEL.FPN.IN_FEATURES, cfg.MODEL.FPN.OUT_CHANNELS)
+
+
+@BACKBONE_REGISTRY.register()
+def build_resnet_from_vision_fpn_backbone(cfg, input_shape=None, priors=None):
+    _check_weights(cfg)
+    if not cfg.MODEL.RESNETS.TORCHVISION:
+        raise NotImplementedError("MSRA ResNet builder is out of scope (config.py:141 default is torchvision)")
+    return FPN(TVResNet(cfg.MODEL.RESNETS.DEPTH), cfg.MODEL.FPN.IN_FEATURES, cfg.MODEL.FPN.OUT_CHANNELS, make_p7=True)
+
+
+for _n in ("build_densenet_fpn_backbone", "build_mnasnet_fpn_backbone", "build_shufflenet_fpn_backbone"):
+    def _unsupported(cfg, input_shape=None, priors=None, _n=_n):
+        raise NotImplementedError(f"{_n}: registered for config compatibility; not on the accelerated path")
+    BACKBONE_REGISTRY.register(_unsupported, name=_n)

@@ -1,0 +1,395 @@
+"""ROIHeads3D + FastRCNNOutputs + CubeHead on the accelerated path — batched, sync-free restatement of
+cubercnn/modeling/roi_heads/{roi_heads.py:39-941, fast_rcnn.py:16-260, cube_head.py:19-202} over
+detectron2's StandardROIHeads / ROIPooler / FastRCNNConvFCHead / FastRCNNOutputLayers.
+
+Fixed-shape tensors replace per-image Instances lists: every image contributes exactly
+BATCH_SIZE_PER_IMAGE sampled-proposal slots and POSITIVE_FRACTION*BATCH_SIZE foreground slots (masked
+when fewer exist), so the whole head runs without host synchronisation.  ROIAlign runs on libc3d.so, the
+FC stacks are plain bf16 library GEMMs (cuBLAS through torch, as the task allows for plain GEMMs).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..nnfunc import ROIAlign
+from . import geometry as G
+from .registry import ROI_CUBE_HEAD_REGISTRY, ROI_HEADS_REGISTRY
+from .rpn import apply_deltas, get_deltas, gumbel_topk_sample, pairwise_ioa, pairwise_iou
+
+SQRT2 = 1.41421356
+
+
+def assign_levels(boxes, min_level=2, max_level=6):
+    size = torch.sqrt(((boxes[..., 2] - boxes[..., 0]) * (boxes[..., 3] - boxes[..., 1])).clamp(min=0))
+    lvl = torch.floor(4 + torch.log2(size / 224 + 1e-8))
+    return lvl.clamp(min=min_level, max=max_level) - min_level
+
+
+def linear_bf16(x, lin, relu=False, weight=None):
+    w = lin.weight if weight is None else weight
+    y = F.linear(x, w.to(torch.bfloat16), lin.bias.to(torch.bfloat16))
+    return F.relu(y) if relu else y
+
+
+def chw_to_hwc_weight(w, C, P):
+    """fc weight over a (C,P,P)-flattened input -> the same weight over an (P,P,C)-flattened (NHWC) input."""
+    return w.view(w.shape[0], C, P, P).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+
+class FastRCNNConvFCHead(nn.Sequential):
+    def __init__(self, in_dim, fc_dims):
+        super().__init__()
+        self.add_module("flatten", nn.Flatten())
+        d = in_dim
+        for k, fc_dim in enumerate(fc_dims):
+            fc = nn.Linear(d, fc_dim)
+            self.add_module("fc%d" % (k + 1), fc)
+            self.add_module("fc_relu%d" % (k + 1), nn.ReLU())
+            d = fc_dim
+        for k in range(len(fc_dims)):
+            fc = getattr(self, "fc%d" % (k + 1))
+            nn.init.kaiming_uniform_(fc.weight, a=1)
+            nn.init.constant_(fc.bias, 0)
+        self.out_dim = d
+
+
+class FastRCNNOutputs(nn.Module):
+    def __init__(self, in_dim, num_classes):
+        super().__init__()
+        self.cls_score = nn.Linear(in_dim, num_classes + 1)
+        self.bbox_pred = nn.Linear(in_dim, num_classes * 4)
+        nn.init.normal_(self.cls_score.weight, std=0.01)
+        nn.init.normal_(self.bbox_pred.weight, std=0.001)
+        for l in (self.cls_score, self.bbox_pred):
+            nn.init.constant_(l.bias, 0)
+
+
+@ROI_CUBE_HEAD_REGISTRY.register()
+class CubeHead(nn.Module):
+    def __init__(self, cfg, in_dim):
+        super().__init__()
+        H = cfg.MODEL.ROI_CUBE_HEAD
+        if not (H.SHARED_FC and H.POSE_TYPE == "6d" and H.CLUSTER_BINS == 1 and H.NUM_CONV == 0 and H.USE_CONFIDENCE > 0):
+            raise NotImplementedError("accelerated CubeHead covers SHARED_FC / 6d pose / no clusters / confidence on")
+        K = self.num_classes = cfg.MODEL.ROI_HEADS.NUM_CLASSES
+        self.feature_generator = nn.Sequential()
+        d = in_dim
+        for k in range(H.NUM_FC):
+            fc = nn.Linear(d, H.FC_DIM)
+            nn.init.kaiming_uniform_(fc.weight, a=1)
+            nn.init.constant_(fc.bias, 0)
+            self.feature_generator.add_module("fc%d" % (k + 1), fc)
+            self.feature_generator.add_module("fc_relu%d" % (k + 1), nn.ReLU())
+            d = H.FC_DIM
+        for name, mult, bias in (("bbox_3D_dims", 3, 0), ("bbox_3D_center_deltas", 2, 0), ("bbox_3D_pose", 6, 0),
+                                 ("bbox_3D_center_depth", 1, 0), ("bbox_3D_uncertainty", 1, 5)):
+            lin = nn.Linear(d, K * mult)
+            nn.init.normal_(lin.weight, std=0.001)
+            nn.init.constant_(lin.bias, bias)
+            setattr(self, name, lin)
+
+
+@ROI_HEADS_REGISTRY.register()
+class ROIHeads3D(nn.Module):
+    def __init__(self, cfg, in_channels, strides, priors=None):
+        super().__init__()
+        RH, BH, H = cfg.MODEL.ROI_HEADS, cfg.MODEL.ROI_BOX_HEAD, cfg.MODEL.ROI_CUBE_HEAD
+        ok = (H.DISENTANGLED_LOSS and H.CHAMFER_POSE and H.ALLOCENTRIC_POSE and H.VIRTUAL_DEPTH and H.Z_TYPE == "direct"
+              and H.DIMS_PRIORS_ENABLED and H.DIMS_PRIORS_FUNC == "exp" and not H.INVERSE_Z_WEIGHT
+              and H.SCALE_ROI_BOXES == 0.0 and H.LOSS_W_3D > 0 and H.LOSS_W_JOINT > 0 and BH.NUM_CONV == 0
+              and BH.NAME == "FastRCNNConvFCHead" and BH.POOLER_TYPE == "ROIAlignV2" and not BH.CLS_AGNOSTIC_BBOX_REG
+              and list(RH.IOU_LABELS) == [0, 1])
+        if not ok:
+            raise NotImplementedError("accelerated ROIHeads3D covers the BASELINE configuration (Base.yaml:61-86)")
+        self.in_features = list(RH.IN_FEATURES)
+        self.strides = [strides[f] for f in self.in_features]
+        self.num_classes = K = RH.NUM_CLASSES
+        self.batch_size_per_image = RH.BATCH_SIZE_PER_IMAGE
+        self.positive_fraction = RH.POSITIVE_FRACTION
+        self.iou_thresh = RH.IOU_THRESHOLDS[0]
+        self.append_gt = RH.PROPOSAL_APPEND_GT
+        self.pooled = BH.POOLER_RESOLUTION
+        self.box_weights = tuple(BH.BBOX_REG_WEIGHTS)
+        self.test_score_thresh, self.test_nms_thresh = RH.SCORE_THRESH_TEST, RH.NMS_THRESH_TEST
+        self.test_topk = cfg.TEST.DETECTIONS_PER_IMAGE
+        self.ignore_thresh = cfg.MODEL.RPN.IGNORE_THRESHOLD
+        self.virtual_focal = H.VIRTUAL_FOCAL
+        self.w = dict(w3d=H.LOSS_W_3D, xy=H.LOSS_W_XY, z=H.LOSS_W_Z, dims=H.LOSS_W_DIMS, pose=H.LOSS_W_POSE,
+                      joint=H.LOSS_W_JOINT, conf=H.USE_CONFIDENCE)
+        in_dim = in_channels * self.pooled * self.pooled
+        self.in_channels = in_channels
+        # construction order mirrors the reference (same-seed init): box head, predictor, 2nd predictor, cube head
+        self.box_head = FastRCNNConvFCHead(in_dim, [BH.FC_DIM] * BH.NUM_FC)
+        FastRCNNOutputs(self.box_head.out_dim, K)                 # RNG parity with roi_heads.py:151
+        self.box_predictor = FastRCNNOutputs(self.box_head.out_dim, K)
+        assert H.POOLER_RESOLUTION == self.pooled
+        self.cube_head = CubeHead(cfg, in_dim)
+        if priors is not None:
+            self.priors_dims_per_cat = nn.Parameter(torch.FloatTensor(priors["priors_dims_per_cat"]).unsqueeze(0))
+        else:
+            self.priors_dims_per_cat = nn.Parameter(torch.ones(1, K, 2, 3))
+        self.priors_z_scales = nn.Parameter(torch.ones(K, H.CLUSTER_BINS))
+        self.generator = None
+        self.stats = {}
+
+    # -- proposal labelling / sampling (roi_heads.py:826-929) -----------------------------------------
+    @torch.no_grad()
+    def match_proposals(self, boxes, pvalid, gt):
+        """boxes (B,P,4), pvalid (B,P) -> matched gt idx (B,P), iou (B,P), class label (B,P) with K = background,
+        -1 = ignore/invalid."""
+        K = self.num_classes
+        valid = gt["present"] & (gt["classes"] >= 0)
+        ign = gt["present"] & (gt["classes"] < 0)
+        iou = pairwise_iou(gt["boxes"], boxes)
+        iou = torch.where(valid[:, :, None], iou, torch.full_like(iou, -1.0))
+        vals, idx = iou.max(dim=1)
+        fg = vals >= self.iou_thresh
+        ioa = pairwise_ioa(gt["boxes"], boxes)
+        ioa = torch.where(ign[:, :, None], ioa, torch.zeros_like(ioa)).max(dim=1).values
+        bg = ~fg
+        ign_hit = bg & (ioa >= self.ignore_thresh) & (bg.sum(1, keepdim=True) > 1) & ign.any(1, keepdim=True)
+        cls = torch.gather(gt["classes"], 1, idx)
+        cls = torch.where(fg, cls, torch.full_like(cls, K))
+        cls = torch.where(ign_hit | ~pvalid, torch.full_like(cls, -1), cls)
+        return idx, vals.clamp(min=0), cls
+
+    @torch.no_grad()
+    def label_and_sample_proposals(self, prop_boxes, prop_count, gt):
+        """-> dict of fixed-shape (B,S,...) sampled tensors; fg samples occupy the first F slots."""
+        if gt.get("sampled") is not None:                     # parity tests inject the oracle's sampled set
+            return gt["sampled"]
+        B, P, _ = prop_boxes.shape
+        dev = prop_boxes.device
+        pvalid = torch.arange(P, device=dev)[None] < prop_count[:, None]
+        boxes = prop_boxes
+        if self.append_gt:
+            gvalid = gt["present"] & (gt["classes"] >= 0)
+            boxes = torch.cat([prop_boxes, gt["boxes"]], 1)
+            pvalid = torch.cat([pvalid, gvalid], 1)
+        S, K = self.batch_size_per_image, self.num_classes
+        Fcap = int(S * self.positive_fraction)
+        if True:
+            midx, miou, cls = self.match_proposals(boxes, pvalid, gt)
+            fg_c, bg_c = (cls >= 0) & (cls < K), cls == K
+            w = miou + 1e-4
+            num_fg = fg_c.sum(1).clamp(max=Fcap)
+            num_bg = torch.minimum(bg_c.sum(1), S - num_fg)
+            f_idx, f_ok = gumbel_topk_sample(torch.where(fg_c, w, torch.zeros_like(w)), Fcap, self.generator)
+            b_idx, b_ok = gumbel_topk_sample(torch.where(bg_c, w, torch.zeros_like(w)), S, self.generator)
+            f_ok &= torch.arange(f_idx.shape[1], device=dev)[None] < num_fg[:, None]
+            # background picks fill slots Fcap.. (S - Fcap of them, plus unused fg capacity at the tail)
+            b_take = torch.arange(b_idx.shape[1], device=dev)[None] < num_bg[:, None]
+            b_ok &= b_take
+            # [fg picks | bg picks] compacted (stable) to exactly S slots: valid fg first, then valid bg
+            sel = torch.cat([f_idx, b_idx], 1)
+            sel_ok = torch.cat([f_ok, b_ok], 1)
+            pos = torch.arange(sel.shape[1], device=dev)[None] + (~sel_ok).long() * (10 * sel.shape[1])
+            order = pos.argsort(dim=1)[:, :S]
+            sel, sel_ok = torch.gather(sel, 1, order), torch.gather(sel_ok, 1, order)
+            bsel = torch.gather(boxes, 1, sel[:, :, None].expand(-1, -1, 4))
+            cls_sel = torch.where(sel_ok, torch.gather(cls, 1, sel), torch.full_like(sel, -1))
+            midx_sel = torch.gather(midx, 1, sel)
+        g = lambda t: torch.gather(t, 1, midx_sel.reshape(B, -1, *([1] * (t.dim() - 2))).expand(-1, -1, *t.shape[2:]))
+        out = dict(boxes=bsel, valid=sel_ok, classes=cls_sel, gt_boxes=g(gt["boxes"]), gt_boxes3D=g(gt["boxes3D"]),
+                   gt_poses=g(gt["poses"]), fcap=Fcap)
+        with torch.no_grad():
+            fgm = sel_ok & (cls_sel >= 0) & (cls_sel < K)
+            self.stats["roi_head/num_fg_samples"] = fgm.float().sum() / B
+            self.stats["roi_head/num_bg_samples"] = (sel_ok & (cls_sel == K)).float().sum() / B
+        return out
+
+    # -- pooling + heads ------------------------------------------------------------------------------
+    def pool(self, feats, boxes, valid):
+        """boxes (B,S,4) -> (B*S, 7*7*C) bf16 NHWC-flattened RoI features (invalid slots pooled from a dummy box)."""
+        B, S, _ = boxes.shape
+        b = torch.where(valid[:, :, None], boxes, torch.zeros_like(boxes)).reshape(-1, 4)
+        bi = torch.arange(B, device=boxes.device, dtype=torch.float32).repeat_interleave(S)
+        rois = torch.cat([bi[:, None], assign_levels(b)[:, None], b], 1).contiguous()
+        x = ROIAlign.apply(rois, tuple(self.strides), self.pooled, *feats)
+        return x.reshape(B * S, -1)
+
+    def box_branch(self, x):
+        C, P = self.in_channels, self.pooled
+        h = linear_bf16(x, self.box_head.fc1, relu=True, weight=chw_to_hwc_weight(self.box_head.fc1.weight, C, P))
+        k = 2
+        while hasattr(self.box_head, "fc%d" % k):
+            h = linear_bf16(h, getattr(self.box_head, "fc%d" % k), relu=True)
+            k += 1
+        scores = linear_bf16(h, self.box_predictor.cls_score).float()
+        deltas = linear_bf16(h, self.box_predictor.bbox_pred).float()
+        return scores, deltas
+
+    def box_losses(self, scores, deltas, smp):
+        K = self.num_classes
+        cls = smp["classes"].reshape(-1)
+        valid = smp["valid"].reshape(-1)
+        n_valid = valid.float().sum().clamp(min=1.0)
+        ce = F.cross_entropy(scores, cls.clamp(min=0), reduction="none")
+        loss_cls = (ce * valid.float()).sum() / n_valid
+        fg = valid & (cls >= 0) & (cls < K)
+        d = deltas.view(-1, K, 4)
+        pick = torch.gather(d, 1, cls.clamp(0, K - 1)[:, None, None].expand(-1, 1, 4)).squeeze(1)
+        tgt = get_deltas(smp["boxes"].reshape(-1, 4), smp["gt_boxes"].reshape(-1, 4), self.box_weights)
+        l1 = (pick - tgt).abs().sum(-1)
+        loss_box = torch.where(fg, l1, torch.zeros_like(l1)).sum() / n_valid
+        with torch.no_grad():
+            pred = scores.argmax(1)
+            nfg = fg.float().sum().clamp(min=1)
+            self.stats["fast_rcnn/cls_accuracy"] = ((pred == cls) & valid).float().sum() / n_valid
+            self.stats["fast_rcnn/fg_cls_accuracy"] = ((pred == cls) & fg).float().sum() / nfg
+            self.stats["fast_rcnn/false_negative"] = ((pred == K) & fg).float().sum() / nfg
+        return {"BoxHead/loss_cls": loss_cls, "BoxHead/loss_box_reg": loss_box}
+
+    def cube_outputs(self, x, classes):
+        """x (n, 7*7*C) bf16, classes (n,) -> per-class gathered raw head outputs (fp32)."""
+        ch, C, P, K = self.cube_head, self.in_channels, self.pooled, self.num_classes
+        fg = ch.feature_generator
+        h = linear_bf16(x, fg.fc1, relu=True, weight=chw_to_hwc_weight(fg.fc1.weight, C, P))
+        k = 2
+        while hasattr(fg, "fc%d" % k):
+            h = linear_bf16(h, getattr(fg, "fc%d" % k), relu=True)
+            k += 1
+        n = x.shape[0]
+        c = classes.clamp(0, K - 1)
+        pick = lambda lin, m: torch.gather(linear_bf16(h, lin).float().view(n, K, m), 1,
+                                           c[:, None, None].expand(-1, 1, m)).squeeze(1)
+        return dict(deltas=pick(ch.bbox_3D_center_deltas, 2), dims=pick(ch.bbox_3D_dims, 3), pose6=pick(ch.bbox_3D_pose, 6),
+                    z=pick(ch.bbox_3D_center_depth, 1).squeeze(1), uncert=pick(ch.bbox_3D_uncertainty, 1).squeeze(1).clip(0.01))
+
+    def decode(self, raw, boxes, classes, Kb, v2r):
+        """roi_heads.py:409-525: 2D centre, dims (exp * prior), egocentric pose, metric depth."""
+        sw, sh = boxes[:, 2] - boxes[:, 0], boxes[:, 3] - boxes[:, 1]
+        cx = boxes[:, 0] + 0.5 * sw + sw * raw["deltas"][:, 0]
+        cy = boxes[:, 1] + 0.5 * sh + sh * raw["deltas"][:, 1]
+        prior = self.priors_dims_per_cat.detach()[0, classes.clamp(0, self.num_classes - 1), 0, :]
+        dims = torch.exp(raw["dims"].clip(max=5)) * prior
+        pose = G.R_from_allocentric(Kb, G.rotation_6d_to_matrix(raw["pose6"]), cx.detach(), cy.detach())
+        return cx, cy, dims, pose, raw["z"] * v2r
+
+    def cube_losses(self, raw, boxes, classes, valid, gt3, gtR, Kb, v2r):
+        w = self.w
+        cx, cy, dims, pose, z = self.decode(raw, boxes, classes, Kb, v2r)
+        uncert = raw["uncert"]
+        fx, fy, px, py = Kb[:, 0, 0], Kb[:, 1, 1], Kb[:, 0, 2], Kb[:, 1, 2]
+        g2, gz, gdims = gt3[:, :2], gt3[:, 2], gt3[:, 3:6]
+        lift = lambda zz, uu, vv: torch.stack((zz * (uu - px) / fx, zz * (vv - py) / fy, zz), 1)
+        g3 = lift(gz, g2[:, 0], g2[:, 1])
+        gt_c = G.cuboid_corners(g3, gdims, gtR)
+        n = boxes.shape[0]
+        l1 = lambda c: (c - gt_c).abs().reshape(n, -1).mean(1)
+        loss_z = l1(G.cuboid_corners(lift(z, g2[:, 0], g2[:, 1]), gdims, gtR))
+        loss_xy = l1(G.cuboid_corners(lift(gz, cx, cy), gdims, gtR))
+        loss_dims = l1(G.cuboid_corners(g3, dims, gtR))
+        loss_pose = G.chamfer8(G.cuboid_corners(g3, gdims, pose), gt_c)
+        loss_joint = G.chamfer8(G.cuboid_corners(lift(z, cx, cy), dims, pose), gt_c)
+        sf = SQRT2 * torch.exp(-uncert)
+        fm = lambda l, m=valid: G.finite_mean(l, m)
+        losses = {"Cube/uncert": w["conf"] * fm(uncert),
+                  "Cube/loss_dims": fm(loss_dims * sf) * w["dims"] * w["w3d"],
+                  "Cube/loss_xy": fm(loss_xy * sf) * w["xy"] * w["w3d"],
+                  "Cube/loss_z": fm(loss_z * sf) * w["z"] * w["w3d"],
+                  "Cube/loss_pose": fm(loss_pose * sf) * w["pose"] * w["w3d"],
+                  "Cube/loss_joint": fm(loss_joint * sf, valid & (loss_joint < float("inf"))) * w["joint"] * w["w3d"]}
+        with torch.no_grad():
+            vm = valid.float()
+            nv = vm.sum().clamp(min=1)
+            mean = lambda t: (torch.where(valid, t, torch.zeros_like(t))).sum() / nv
+            z_err = (z - gz).abs()
+            total = loss_dims * w["dims"] + loss_pose * w["pose"] + loss_xy * w["xy"] + loss_z * w["z"] + loss_joint * w["joint"]
+            self.stats.update({"Cube/z_error": mean(z_err), "Cube/dims_error": mean((dims - gdims).abs().mean(1)),
+                               "Cube/xy_error": mean((torch.stack((cx, cy), 1) - g2).abs().mean(1)),
+                               "Cube/z_close": mean((z_err < 0.20).float()),
+                               "Cube/total_3D_loss": w["w3d"] * fm(total), "Cube/conf": mean(torch.exp(-uncert))})
+        return losses
+
+    def per_box_camera(self, Ks, ratios, im_h, counts_or_S, B, device):
+        """scaled intrinsics per box and the virtual->real depth factor (roi_heads.py:372-404)."""
+        K = torch.stack([torch.as_tensor(k, dtype=torch.float32) for k in Ks]).to(device)         # (B,3,3)
+        r = torch.as_tensor(ratios, dtype=torch.float32, device=device)
+        Ks_scaled = K / r[:, None, None]
+        Ks_scaled[:, 2, 2] = 1
+        h = torch.as_tensor(im_h, dtype=torch.float32, device=device)
+        v2r = (h * K[:, 1, 1]) / (self.virtual_focal * (h * r))
+        rep = lambda t: t.repeat_interleave(counts_or_S, dim=0)
+        return rep(Ks_scaled), rep(v2r), rep(r)
+
+    # -- forward ----------------------------------------------------------------------------------------
+    def forward(self, features, proposals, image_sizes, Ks, ratios, gt=None):
+        feats = [features[f] for f in self.in_features]
+        prop_boxes, prop_scores, prop_count = proposals
+        B = prop_boxes.shape[0]
+        dev = prop_boxes.device
+        im_h = [s[0] for s in image_sizes]
+        if self.training:
+            smp = self.label_and_sample_proposals(prop_boxes, prop_count, gt)
+            x = self.pool(feats, smp["boxes"], smp["valid"])
+            scores, deltas = self.box_branch(x)
+            losses = self.box_losses(scores, deltas, smp)
+            Fc = smp["fcap"]
+            K = self.num_classes
+            fb, fc_, fv = smp["boxes"][:, :Fc], smp["classes"][:, :Fc], smp["valid"][:, :Fc]
+            fv = fv & (fc_ >= 0) & (fc_ < K)
+            xc = self.pool(feats, fb, fv)
+            Kb, v2r, _ = self.per_box_camera(Ks, ratios, im_h, Fc, B, dev)
+            raw = self.cube_outputs(xc, fc_.reshape(-1))
+            losses.update(self.cube_losses(raw, fb.reshape(-1, 4), fc_.reshape(-1), fv.reshape(-1),
+                                           smp["gt_boxes3D"][:, :Fc].reshape(-1, 9), smp["gt_poses"][:, :Fc].reshape(-1, 3, 3),
+                                           Kb, v2r))
+            return None, losses
+        return self.inference(feats, prop_boxes, prop_count, image_sizes, Ks, ratios), {}
+
+    @torch.no_grad()
+    def inference(self, feats, prop_boxes, prop_count, image_sizes, Ks, ratios):
+        """fast_rcnn.py:57-143 + roi_heads.py:227-246,774-819 (per-image loop: eval is not the bench path)."""
+        from torchvision.ops import batched_nms
+        from .structures import Boxes, Instances
+        B, P, _ = prop_boxes.shape
+        dev = prop_boxes.device
+        K = self.num_classes
+        pvalid = torch.arange(P, device=dev)[None] < prop_count[:, None]
+        x = self.pool(feats, prop_boxes, pvalid)
+        scores, deltas = self.box_branch(x)
+        probs = F.softmax(scores, -1).view(B, P, K + 1)
+        pboxes = apply_deltas(deltas, prop_boxes.reshape(-1, 4), self.box_weights).view(B, P, K, 4)
+        det_boxes, det_cls, det_scores, det_full, counts = [], [], [], [], []
+        for i in range(B):
+            n = int(prop_count[i])
+            h, w = image_sizes[i]
+            b, s = pboxes[i, :n], probs[i, :n]
+            ok = torch.isfinite(b).all(-1).all(-1) & torch.isfinite(s).all(-1)
+            b, s = b[ok], s[ok][:, :-1]
+            lim = torch.tensor([w, h, w, h], dtype=torch.float32, device=dev)
+            b = torch.minimum(b.clamp(min=0), lim)
+            m = s > self.test_score_thresh
+            inds = m.nonzero()
+            bb, ss, sf = b[m], s[m], s[inds[:, 0]]
+            keep = batched_nms(bb, ss, inds[:, 1], self.test_nms_thresh)[: self.test_topk]
+            det_boxes.append(bb[keep]); det_scores.append(ss[keep]); det_full.append(sf[keep]); det_cls.append(inds[keep][:, 1])
+            counts.append(len(keep))
+        results = []
+        D = max(max(counts), 1)
+        padb = torch.zeros((B, D, 4), device=dev)
+        padc = torch.zeros((B, D), dtype=torch.long, device=dev)
+        padv = torch.zeros((B, D), dtype=torch.bool, device=dev)
+        for i in range(B):
+            padb[i, :counts[i]] = det_boxes[i]; padc[i, :counts[i]] = det_cls[i]; padv[i, :counts[i]] = True
+        xc = self.pool(feats, padb, padv)
+        Kb, v2r, rr = self.per_box_camera(Ks, ratios, [s[0] for s in image_sizes], D, B, dev)
+        raw = self.cube_outputs(xc, padc.reshape(-1))
+        cx, cy, dims, pose, z = self.decode(raw, padb.reshape(-1, 4), padc.reshape(-1), Kb, v2r)
+        fx, fy, px, py = Kb[:, 0, 0], Kb[:, 1, 1], Kb[:, 0, 2], Kb[:, 1, 2]
+        cam = torch.stack((z * (cx - px) / fx, z * (cy - py) / fy, z), 1)
+        conf = torch.exp(-raw["uncert"])
+        c2d = torch.stack((cx, cy), 1) * rr[:, None]
+        corners = G.cuboid_corners(cam, dims, pose)
+        for i in range(B):
+            sl = slice(i * D, i * D + counts[i])
+            inst = Instances(tuple(image_sizes[i]))
+            inst.pred_boxes = Boxes(det_boxes[i]); inst.scores = (det_scores[i] * conf[sl]) ** 0.5
+            inst.scores_full = det_full[i]; inst.pred_classes = det_cls[i]
+            inst.pred_bbox3D = corners[sl]; inst.pred_center_cam = cam[sl]; inst.pred_center_2D = c2d[sl]
+            inst.pred_dimensions = dims[sl]; inst.pred_pose = pose[sl]
+            results.append(inst)
+        return results

@@ -1,0 +1,185 @@
+"""ctypes front-ends of the NHWC helper kernels in libc3d.so (BatchNorm, max-pool, preprocess, ROIAlign,
+SGD).  torch tensors are used only as device buffers; pointers + sizes cross the C ABI (include/c3d.h)."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_bound = False
+vp, i32, i64, f32, f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double
+
+
+class RoiLevels(ctypes.Structure):
+    _fields_ = [("feat", vp * 5), ("grad", vp * 5), ("H", i32 * 5), ("W", i32 * 5), ("scale", f32 * 5),
+                ("num_levels", i32)]
+
+
+def _bind():
+    global _bound
+    L = _lib.lib()
+    if _bound:
+        return L
+    sig = {
+        "c3d_bn_finalize": [vp, i32, i32, f64, f32, f32, vp, vp, vp, vp, vp],
+        "c3d_bn_apply": [vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i64, i64, vp],
+        "c3d_bn_bwd_blocks": [i64, i32],
+        "c3d_bn_bwd": [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, vp],
+        "c3d_maxpool2_fwd": [vp, vp, i32, i32, i32, i32, i64, i64, vp],
+        "c3d_maxpool2_bwd": [vp, vp, vp, i32, i32, i32, i32, i64, i64, vp],
+        "c3d_preprocess_image": [vp, i32, i32, vp, i32, i32, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), vp],
+        "c3d_grad_finite": [vp, i64, vp, vp],
+        "c3d_sgd_momentum": [vp, vp, vp, i64, f32, f32, f32, f32, vp, vp],
+        "c3d_roi_align_fwd": [ctypes.POINTER(RoiLevels), vp, i32, i32, i32, i32, vp, vp],
+        "c3d_roi_align_bwd": [ctypes.POINTER(RoiLevels), vp, i32, i32, i32, i32, vp, vp],
+    }
+    L.c3d_nms_workspace_bytes.restype = ctypes.c_size_t
+    L.c3d_nms_workspace_bytes.argtypes = [i32, i32]
+    sig["c3d_nms_batched"] = [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, ctypes.c_size_t, vp]
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.restype = i32
+        fn.argtypes = args
+    _bound = True
+    return L
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _st():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def bn_finalize(stats, count, eps, momentum, running_mean, running_var):
+    L = _bind()
+    rows, _, C = stats.shape
+    mean = torch.empty(C, device=stats.device, dtype=torch.float32)
+    rstd = torch.empty(C, device=stats.device, dtype=torch.float32)
+    _lib.check(L.c3d_bn_finalize(_p(stats), rows, C, float(count), eps, momentum, _p(running_mean), _p(running_var),
+                                 _p(mean), _p(rstd), _st()))
+    return mean, rstd
+
+
+def bn_apply(y, mean, rstd, gamma, beta, residual=None, relu=True, out=None):
+    L = _bind()
+    C = y.shape[-1]
+    P = y.numel() // C
+    if out is None:
+        out = torch.empty_like(y)
+    _lib.check(L.c3d_bn_apply(_p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), int(relu), _p(out), P, C,
+                              0, 0, _st()))
+    return out
+
+
+def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres):
+    """-> dy (bf16, like y), dres (bf16 or None); dgamma/dbeta (fp32 [C]) are accumulated in place."""
+    L = _bind()
+    C = y.shape[-1]
+    P = y.numel() // C
+    blocks = L.c3d_bn_bwd_blocks(P, C)
+    partial = torch.empty((blocks, 2, C), device=y.device, dtype=torch.float32)
+    coef = torch.empty((3, C), device=y.device, dtype=torch.float32)
+    dy = torch.empty_like(y)
+    dres = torch.empty_like(y) if want_dres else None
+    _lib.check(L.c3d_bn_bwd(_p(dout), _p(out), _p(y), _p(mean), _p(rstd), _p(gamma), int(relu), _p(partial), _p(coef),
+                            _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, 0, 0, 0, _st()))
+    return dy, dres
+
+
+def maxpool2_fwd(x):
+    L = _bind()
+    N, H, W, C = x.shape
+    y = torch.empty((N, H // 2, W // 2, C), device=x.device, dtype=x.dtype)
+    _lib.check(L.c3d_maxpool2_fwd(_p(x), _p(y), N, H, W, C, 0, 0, _st()))
+    return y
+
+
+def maxpool2_bwd(x, dy):
+    L = _bind()
+    N, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    _lib.check(L.c3d_maxpool2_bwd(_p(x), _p(dy), _p(dx), N, H, W, C, 0, 0, _st()))
+    return dx
+
+
+def preprocess_images(images, mean, std, size_divisibility=64, cpad=16):
+    """list of (3,H,W) fp32 CUDA tensors -> (N,Hp,Wp,cpad) bf16 NHWC batch (normalised, zero padded)."""
+    L = _bind()
+    Hm = max(im.shape[1] for im in images)
+    Wm = max(im.shape[2] for im in images)
+    d = size_divisibility
+    Hp, Wp = (Hm + d - 1) // d * d, (Wm + d - 1) // d * d
+    out = torch.empty((len(images), Hp, Wp, cpad), device=images[0].device, dtype=torch.bfloat16)
+    m = (f32 * 3)(*[float(v) for v in mean])
+    s = (f32 * 3)(*[float(v) for v in std])
+    for i, im in enumerate(images):
+        assert im.dtype == torch.float32 and im.is_contiguous() and im.is_cuda
+        _lib.check(L.c3d_preprocess_image(_p(im), im.shape[1], im.shape[2], _p(out[i]), Hp, Wp, cpad, m, s, _st()))
+    return out
+
+
+def _levels(feats, strides, grads=None):
+    lv = RoiLevels()
+    lv.num_levels = len(feats)
+    for i, f in enumerate(feats):
+        lv.feat[i] = f.data_ptr()
+        lv.grad[i] = grads[i].data_ptr() if grads is not None else None
+        lv.H[i], lv.W[i] = f.shape[1], f.shape[2]
+        lv.scale[i] = 1.0 / strides[i]
+    return lv
+
+
+def roi_align_fwd(feats, strides, rois, pooled=7):
+    """feats: list of (N,H,W,C) bf16; rois (R,6) fp32 [batch, level, x1,y1,x2,y2] -> (R,pooled,pooled,C) bf16."""
+    L = _bind()
+    C = feats[0].shape[-1]
+    R = rois.shape[0]
+    out = torch.empty((R, pooled, pooled, C), device=feats[0].device, dtype=torch.bfloat16)
+    lv = _levels(feats, strides)
+    _lib.check(L.c3d_roi_align_fwd(ctypes.byref(lv), _p(rois), R, C, pooled, pooled, _p(out), _st()))
+    return out
+
+
+def roi_align_bwd(feats, strides, rois, dout, pooled=7):
+    """-> list of fp32 gradient maps shaped like feats."""
+    L = _bind()
+    C = feats[0].shape[-1]
+    grads = [torch.zeros(f.shape, device=f.device, dtype=torch.float32) for f in feats]
+    lv = _levels(feats, strides, grads)
+    _lib.check(L.c3d_roi_align_bwd(ctypes.byref(lv), _p(rois), rois.shape[0], C, pooled, pooled, _p(dout), _st()))
+    return grads
+
+
+def grad_finite(flat_grad, flag):
+    L = _bind()
+    _lib.check(L.c3d_grad_finite(_p(flat_grad), flat_grad.numel(), _p(flag), _st()))
+
+
+def sgd_momentum(p, g, mom, lr, momentum, weight_decay, grad_scale=1.0, skip_flag=None):
+    L = _bind()
+    _lib.check(L.c3d_sgd_momentum(_p(p), _p(g), _p(mom), p.numel(), lr, momentum, weight_decay, grad_scale,
+                                  _p(skip_flag), _st()))
+
+
+_nms_ws = {}
+
+
+def nms_batched(boxes, nvalid, iou_thresh, max_keep, cats=None, maxc=None, trick_max_numel=20000):
+    """boxes (B,n,4) fp32 sorted by score desc, nvalid (B,) int32, cats (B,n) fp32 categories, maxc (B,) fp32
+    -> keep_idx (B,max_keep) int32 (-1 padded, score order), keep_cnt (B,) int32.  No host sync."""
+    L = _bind()
+    B, n, _ = boxes.shape
+    boxes = boxes.contiguous()
+    need = L.c3d_nms_workspace_bytes(B, n)
+    key = boxes.device.index
+    ws = _nms_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=boxes.device)
+        _nms_ws[key] = ws
+    keep = torch.empty((B, max_keep), dtype=torch.int32, device=boxes.device)
+    cnt = torch.empty((B,), dtype=torch.int32, device=boxes.device)
+    _lib.check(L.c3d_nms_batched(_p(boxes), _p(nvalid), _p(cats), _p(maxc), trick_max_numel, B, n, iou_thresh,
+                                 max_keep, _p(keep), _p(cnt), _p(ws), ws.numel(), _st()))
+    return keep, cnt

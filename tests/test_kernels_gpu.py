@@ -1,0 +1,179 @@
+"""GPU unit tests of the sm_100a helper kernels against plain PyTorch fp32 references of the same op
+(tolerances: bf16 storage => 2^-8 relative on outputs; fp32 accumulations 1e-5)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _r(*shape, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, device="cuda", generator=g)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,s,p", [(2, 32, 32, 64, 64, 3, 1, 1), (1, 20, 20, 256, 128, 3, 1, 1),
+                                                  (2, 32, 32, 64, 128, 3, 2, 1), (2, 16, 16, 128, 256, 1, 1, 0),
+                                                  (1, 64, 64, 16, 32, 3, 2, 1), (2, 24, 40, 32, 64, 1, 1, 0)])
+def test_conv_fwd_dgrad_wgrad_vs_torch(N, H, W, Cin, Cout, k, s, p):
+    from omni3d_b200.nnfunc import ConvBias
+    torch.backends.cudnn.allow_tf32 = False
+    x = _r(N, H, W, Cin).bfloat16().requires_grad_(True)
+    w = (_r(Cout, Cin, k, k, seed=1) / (k * k * Cin) ** 0.5).requires_grad_(True)
+    b = _r(Cout, seed=2).requires_grad_(True)
+    y = ConvBias.apply(x, w, b, None, s, p, True, False)
+    dy = _r(*y.shape, seed=3).bfloat16()
+    y.backward(dy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.detach().bfloat16().float().requires_grad_(True)
+    br = b.detach().clone().requires_grad_(True)
+    yr = F.relu(F.conv2d(xr, wr, br, s, p))
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    tol = lambda ref: 1.2e-2 * ref.abs().max().item() + 1e-3
+    assert (y.float() - yr.permute(0, 2, 3, 1)).abs().max().item() <= tol(yr)
+    assert (x.grad.float() - xr.grad.permute(0, 2, 3, 1)).abs().max().item() <= tol(xr.grad)
+    assert (w.grad - wr.grad).abs().max().item() <= 2e-2 * wr.grad.abs().max().item() + 1e-3
+    assert (b.grad - br.grad).abs().max().item() <= 1e-2 * br.grad.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("C,relu,res", [(64, True, True), (128, True, False), (16, False, False), (512, True, True)])
+def test_conv_bn_act_train_vs_torch(C, relu, res):
+    from omni3d_b200.nnfunc import ConvBNAct
+    N, H, W, Cin = 3, 24, 24, 64
+    x = _r(N, H, W, Cin).bfloat16().requires_grad_(True)
+    w = (_r(C, Cin, 3, 3, seed=1) / (9 * Cin) ** 0.5).requires_grad_(True)
+    gamma = (1 + 0.1 * _r(C, seed=2)).requires_grad_(True)
+    beta = (0.1 * _r(C, seed=3)).requires_grad_(True)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    r = _r(N, H, W, C, seed=4).bfloat16().requires_grad_(True) if res else None
+    out = ConvBNAct.apply(x, w, gamma, beta, rm, rv, r, 1, 1, relu, True, 1e-5, 0.1)
+    dy = _r(*out.shape, seed=5).bfloat16()
+    out.backward(dy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.detach().bfloat16().float().requires_grad_(True)
+    gr, br = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    rmr, rvr = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    yr = F.batch_norm(F.conv2d(xr, wr, None, 1, 1), rmr, rvr, gr, br, True, 0.1, 1e-5)
+    rr = None
+    if res:
+        rr = r.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+        yr = yr + rr
+    if relu:
+        yr = F.relu(yr)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    tol = lambda ref, f=2e-2: f * ref.abs().max().item() + 2e-3
+    assert (out.float() - yr.permute(0, 2, 3, 1)).abs().max().item() <= tol(yr)
+    assert (rm - rmr).abs().max().item() < 1e-3 and (rv - rvr).abs().max().item() < 1e-3
+    assert (gamma.grad - gr.grad).abs().max().item() <= tol(gr.grad, 3e-2)
+    assert (beta.grad - br.grad).abs().max().item() <= tol(br.grad, 3e-2)
+    assert (x.grad.float() - xr.grad.permute(0, 2, 3, 1)).abs().max().item() <= tol(xr.grad, 4e-2)
+    assert (w.grad - wr.grad).abs().max().item() <= tol(wr.grad, 4e-2)
+    if res:
+        assert (r.grad.float() - rr.grad.permute(0, 2, 3, 1)).abs().max().item() <= tol(rr.grad)
+
+
+def test_maxpool2_fwd_bwd():
+    from omni3d_b200.nnfunc import MaxPool2
+    x = _r(2, 16, 24, 64).bfloat16().requires_grad_(True)
+    y = MaxPool2.apply(x)
+    dy = _r(*y.shape, seed=1).bfloat16()
+    y.backward(dy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.max_pool2d(xr, 2, 2)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert torch.equal(y.float(), yr.permute(0, 2, 3, 1))
+    assert torch.equal(x.grad.float(), xr.grad.permute(0, 2, 3, 1))
+
+
+def test_preprocess_matches_reference_formula():
+    from omni3d_b200 import kernels as Kx
+    imgs = [torch.randint(0, 256, (3, 50, 70), device="cuda").float(), torch.randint(0, 256, (3, 64, 40), device="cuda").float()]
+    mean, std = [103.53, 116.28, 123.675], [57.375, 57.12, 58.395]
+    out = Kx.preprocess_images(imgs, mean, std, 64, 16)
+    assert tuple(out.shape) == (2, 64, 128, 16)
+    m, s = torch.tensor(mean, device="cuda").view(3, 1, 1), torch.tensor(std, device="cuda").view(3, 1, 1)
+    for i, im in enumerate(imgs):
+        ref = ((im - m) / s).bfloat16().float()
+        got = out[i, :im.shape[1], :im.shape[2], :3].float().permute(2, 0, 1)
+        assert torch.equal(got, ref)
+        assert out[i, im.shape[1]:].abs().sum() == 0 and out[i, :, im.shape[2]:].abs().sum() == 0
+        assert out[i, ..., 3:].abs().sum() == 0
+
+
+def test_roi_align_fwd_bwd_vs_torchvision():
+    from torchvision.ops import roi_align
+    from omni3d_b200.cubercnn.roi_heads import assign_levels
+    from omni3d_b200.nnfunc import ROIAlign
+    strides = (4, 8, 16, 32, 64)
+    N, C = 2, 256
+    feats = [(_r(N, 128 // (s // 4), 160 // (s // 4), C, seed=s) * 1.0).bfloat16().requires_grad_(True) for s in strides]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    R = 300
+    xy = torch.rand(R, 2, device="cuda", generator=g) * torch.tensor([560.0, 440.0], device="cuda")
+    wh = torch.rand(R, 2, device="cuda", generator=g) ** 2 * 400 + 2
+    boxes = torch.cat([xy, xy + wh], 1)
+    bi = torch.randint(0, N, (R,), device="cuda", generator=g).float()
+    lv = assign_levels(boxes)
+    rois = torch.cat([bi[:, None], lv[:, None], boxes], 1).contiguous()
+    out = ROIAlign.apply(rois, strides, 7, *feats)
+    dy = _r(*out.shape, seed=9).bfloat16()
+    out.backward(dy)
+    fr = [f.detach().float().permute(0, 3, 1, 2).requires_grad_(True) for f in feats]
+    ref = torch.zeros(R, C, 7, 7, device="cuda")
+    for l, s in enumerate(strides):
+        idx = (lv == l).nonzero().squeeze(1)
+        if len(idx):
+            ref[idx] = roi_align(fr[l], torch.cat([bi[idx, None], boxes[idx]], 1), (7, 7), 1.0 / s, 0, aligned=True)
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    assert (out.float() - ref.permute(0, 2, 3, 1)).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    for f, r in zip(feats, fr):
+        if r.grad is None:
+            continue
+        assert (f.grad.float() - r.grad.permute(0, 2, 3, 1)).abs().max().item() <= 2e-2 * r.grad.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("n,trick", [(900, 4000), (6000, 4000), (3000, 20000)])
+def test_nms_batched_exact_vs_torchvision(n, trick):
+    from torchvision.ops import batched_nms
+    from omni3d_b200 import kernels as Kx
+    B = 3
+    g = torch.Generator().manual_seed(n)
+    xy = torch.rand(B, n, 2, generator=g) * 500
+    wh = torch.rand(B, n, 2, generator=g) * 120 + 4
+    boxes = torch.cat([xy, xy + wh], 2)
+    scores = torch.randn(B, n, generator=g)
+    cats = torch.randint(0, 5, (B, n), generator=g).float()
+    nvalid = torch.tensor([n, n - 37, n // 2], dtype=torch.int32)
+    s_sorted, order = scores.sort(1, descending=True)
+    b_sorted = torch.gather(boxes, 1, order[:, :, None].expand(-1, -1, 4))
+    c_sorted = torch.gather(cats, 1, order)
+    maxc = torch.stack([b_sorted[i, :nvalid[i]].max() for i in range(B)])
+    keep, cnt = Kx.nms_batched(b_sorted.cuda(), nvalid.cuda(), 0.7, 1000, cats=c_sorted.cuda().contiguous(),
+                               maxc=maxc.cuda(), trick_max_numel=trick)
+    import torchvision
+    for i in range(B):
+        nv = int(nvalid[i])
+        bb, ss, cc = b_sorted[i, :nv], s_sorted[i, :nv], c_sorted[i, :nv].long()
+        if bb.numel() > trick:      # torchvision's per-category path
+            ref = torchvision.ops.boxes._batched_nms_vanilla(bb, ss, cc, 0.7)
+        else:
+            ref = torchvision.ops.boxes._batched_nms_coordinate_trick(bb, ss, cc, 0.7)
+        ref = ref[:1000]
+        got = keep[i, :int(cnt[i])].cpu().long()
+        assert torch.equal(got, ref), (i, len(got), len(ref))
+
+
+def test_sgd_and_finite_flag():
+    from omni3d_b200 import kernels as Kx
+    n = 100003
+    p, g, m = _r(n, seed=1), _r(n, seed=2), torch.zeros(n, device="cuda")
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.SGD([pr], lr=0.02, momentum=0.9, weight_decay=1e-4)
+    for _ in range(3):
+        pr.grad = g.clone(); opt.step()
+        Kx.sgd_momentum(p, g, m, 0.02, 0.9, 1e-4)
+    assert (p - pr.detach()).abs().max().item() < 1e-6
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    Kx.grad_finite(g, flag); assert int(flag) == 0
+    g[777] = float("inf"); Kx.grad_finite(g, flag); assert int(flag) == 1
+    before = p.clone(); Kx.sgd_momentum(p, g, m, 0.02, 0.9, 1e-4, skip_flag=flag); assert torch.equal(p, before)
