@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the accelerated Cube R-CNN hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W              # our arm (1 process per GPU; torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+
+One "step" = one full train step (H2D of the batch where applicable, forward, backward, gradient all-reduce
+over NCCL for N>1, stabiliser check, fused SGD) of Cube R-CNN DLA34_FPN on a synthetic batch of 32 images
+640x640 per GPU (BASELINE configs[1]; weak scaling: the global batch is 32*N).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "images/sec DLA34 Cube R-CNN train step"
+UNIT = "images/s"
+CONFIG_FILE = "cubercnn_DLA34_FPN.yaml"
+# algorithmic work per image (SURVEY.md section 8d / BASELINE.md section 3)
+GFLOP_TRAIN_PER_IMAGE = 452.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU (BASELINE configs[1]: 32)")
+    ap.add_argument("--size", type=int, default=640)
+    ap.add_argument("--cpu-batch", type=int, default=2, help="images per CPU step (bounded sample of the workload)")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-iou", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1404.6), d.get("hbm_gbs", 6574.1), "measured (MEASURED_PEAKS.json)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_train_images_per_s(batch, size, steps, warmup, threads):
+    """The reference's CPU path for this metric = the oracle port (fp32, MODEL.DEVICE=cpu) doing
+    forward + backward + SGD on a bounded sample (batch `batch`) of the same synthetic workload."""
+    import torch
+    from omni3d_b200 import synth
+    from oracle import cubercnn_oracle as co
+    from oracle import model_io
+    from detectron2.utils.events import EventStorage
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    cfg = co.load_cfg(CONFIG_FILE)
+    model = co.build_model(cfg)
+    model.train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=1e-4, momentum=0.9, weight_decay=1e-4)
+    items = synth.make_batch(batch, size, size, num_gt=8, seed=0)
+    times = []
+    with EventStorage(0):
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            losses = model(model_io.to_d2_inputs(items))
+            opt.zero_grad()
+            sum(losses.values()).backward()
+            opt.step()
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return batch / sec, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    ips, sec = cpu_train_images_per_s(args.cpu_batch, args.size, steps, warm, cores)
+    sample = f"oracle port fwd+bwd+SGD, fp32, batch {args.cpu_batch} x {args.size}x{args.size}, {steps} timed steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Cube R-CNN DLA34_FPN train step, synthetic {args.size}x{args.size}, CPU sample batch {args.cpu_batch}"},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def conv_roofline(trainer, items, peak_tflops, peak_src):
+    """One instrumented step: CUDA events around every conv_tc launch (on the launching stream) ->
+    algorithmic FLOPs / summed duration for the dominant kernel family."""
+    import torch
+    from omni3d_b200 import conv as K
+    rec = []
+    o_f, o_w = K.conv2d_fwd, K.conv2d_wgrad
+
+    def fwd(x, w, *a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = o_f(x, w, *a, **k)
+        e1.record()
+        y = out[0] if isinstance(out, tuple) else out
+        rec.append((e0, e1, 2.0 * y.shape[0] * y.shape[1] * y.shape[2] * w.shape[0] * w.shape[1] * w.shape[2] * w.shape[3], "fwd"))
+        return out
+
+    def wgrad(x, dy, KH, KW, stride=1, pad=0, dw=None):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = o_w(x, dy, KH, KW, stride, pad, dw)
+        e1.record()
+        rec.append((e0, e1, 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * KH * KW * x.shape[3], "wgrad"))
+        return out
+
+    K.conv2d_fwd, K.conv2d_wgrad = fwd, wgrad
+    import omni3d_b200.nnfunc as nf
+    try:
+        trainer.step(items)
+        torch.cuda.synchronize()
+    finally:
+        K.conv2d_fwd, K.conv2d_wgrad = o_f, o_w
+    ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
+    fl = sum(f for _, _, f, _ in rec)
+    ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+    by = {}
+    for a, b, f, kind in rec:
+        t = by.setdefault(kind, [0.0, 0.0, 0])
+        t[0] += a.elapsed_time(b); t[1] += f; t[2] += 1
+    return {"bound": "tensor", "kernel": "conv_tc_kernel + conv_wgrad_tc_kernel (tcgen05 implicit GEMM)",
+            "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": None,
+            "peak_source": peak_src + ", bf16 sustained (kernel timed inside a long step)",
+            "launches_per_step": len(rec), "conv_ms_per_step": ms,
+            "breakdown": {k: {"ms": v[0], "tflops": v[1] / (v[0] * 1e-3) / 1e12 if v[0] else 0, "launches": v[2]}
+                          for k, v in by.items()}}
+
+
+def iou_block():
+    import numpy as np
+    import torch
+    import boxgen
+    from omni3d_b200 import box3d
+    out = {}
+    for regime, L in (("dense", 1.0), ("sparse", 10.0)):
+        a = torch.from_numpy(boxgen.inject_degenerate(boxgen.random_boxes(1000, L, 0), 0.01, 1)[0]).cuda()
+        b = torch.from_numpy(boxgen.random_boxes(1000, L, 5)).cuda()
+        for _ in range(3):
+            box3d.iou_box3d(a, b)
+        ts = []
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); box3d.iou_box3d(a, b); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = float(np.median(ts))
+        out[regime] = {"pairs": 1_000_000, "ms": ms, "pairs_per_s": 1e6 / (ms * 1e-3),
+                       "alg_GBps": (96 * 2000 + 8e6) / (ms * 1e-3) / 1e9}
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from omni3d_b200 import _lib, synth
+    from omni3d_b200 import cubercnn as pc
+    from omni3d_b200.train import FlatSGDTrainer
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    cfg = pc.load_cfg(CONFIG_FILE, ["MODEL.WEIGHTS_PRETRAIN", "none", "MODEL.DEVICE", "cuda", "SOLVER.IMS_PER_BATCH", args.batch * world,
+                                    "SOLVER.BASE_LR", 0.0025])
+    torch.manual_seed(0)
+    model = pc.build_model(cfg)
+    model.train()
+    trainer = FlatSGDTrainer(cfg, model)
+    B, S = args.batch, args.size
+    # two distinct synthetic batches, alternated so that consecutive steps never re-read the same inputs from L2
+    host = [synth.make_batch(B, S, S, num_gt=8, seed=100 + rank * 7 + j) for j in range(2)]
+    for hb in host:
+        for it in hb:
+            it["image"] = it["image"].pin_memory()
+    resident = [[{**it, "image": it["image"].to(dev), "gt": {k: v.to(dev) for k, v in it["gt"].items()}} for it in hb]
+                for hb in host]
+    h2d = sum(it["image"].numel() * 4 for it in host[0]) + sum(sum(v.numel() * v.element_size() for v in it["gt"].values())
+                                                               for it in host[0])
+
+    def timed(batches, steps, read_loss):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.LAUNCHES["n"]
+        e0.record()
+        for i in range(steps):
+            trainer.step(batches[i % 2])
+            if read_loss:
+                trainer.status(wait=True)          # device->host read of the step's losses (pinned, 56 bytes)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, _lib.LAUNCHES["n"] - n0
+
+    for i in range(max(args.warmup, 3)):
+        trainer.step(resident[i % 2])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(resident, args.steps, read_loss=False)
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(2):
+        trainer.step(host[i % 2])
+    ms_e2e, _ = timed(host, args.steps, read_loss=True)
+    status = trainer.status()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak_tf, peak_hbm, peak_src = peaks()
+    ips = B * world * args.steps / (ms * 1e-3)
+    ips_e2e = B * world * args.steps / (ms_e2e * 1e-3)
+    roof = conv_roofline(trainer, resident[0], peak_tf, peak_src)
+    line = {
+        "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"Cube R-CNN DLA34_FPN train step, batch {B}/GPU synthetic {S}x{S}, K=50, G=8 GT/img "
+                               "(BASELINE configs[1]; weak scaling, global batch %d)" % (B * world),
+                   "parallelism": f"dp{world}", "l2": "two alternating input batches (157 MB each) + ~10 GB of activations "
+                                                      "per step: working set >> 126 MB L2",
+                   "train_gflop_per_image": GFLOP_TRAIN_PER_IMAGE},
+        "clocks": clocks,
+        "e2e": {"value": ips_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 56,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "step_tflops_model": ips / world * GFLOP_TRAIN_PER_IMAGE / 1e3,
+        "roofline": roof,
+        "final_losses": status["losses"] if status else None,
+        "iterations_skipped": status["iterations_explode"] if status else None,
+    }
+    if not args.skip_iou:
+        line["box3d_overlap"] = iou_block()
+    if not args.skip_cpu_baseline and world == 1:
+        cores = os.cpu_count()
+        cb, secs = cpu_train_images_per_s(args.cpu_batch, S, 1, 1, cores)
+        line["cpu_baseline"] = {"value": cb, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"oracle port fwd+bwd+SGD fp32, batch {args.cpu_batch} x {S}x{S}, 1 timed step "
+                                          f"({secs:.1f} s) after 1 warm-up"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

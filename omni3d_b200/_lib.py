@@ -41,7 +41,12 @@ def lib():
     return L
 
 
-def check(code):
+# number of libc3d kernel launches issued through the python front-ends (bench.py's gpu_launches)
+LAUNCHES = {"n": 0}
+
+
+def check(code, launches=1):
+    LAUNCHES["n"] += launches
     if code != C3D_OK:
         raise C3DError(f"libc3d error {code}: {lib().c3d_last_error().decode()}")
 

@@ -33,11 +33,12 @@ def collate_gt(batched_inputs, device):
     """list of per-image GT -> padded (B,G,...) tensors + `present` mask (one H2D copy per field)."""
     fields = [_gt_fields(it) for it in batched_inputs]
     B, Gm = len(fields), max(max(len(f[0]) for f in fields), 1)
-    cls = torch.full((B, Gm), -2, dtype=torch.long)
-    boxes = torch.zeros((B, Gm, 4))
-    b3d = torch.zeros((B, Gm, 9))
-    poses = torch.eye(3).repeat(B, Gm, 1, 1)
-    present = torch.zeros((B, Gm), dtype=torch.bool)
+    src = fields[0][0].device                      # build where the annotations live (host, or HBM-resident)
+    cls = torch.full((B, Gm), -2, dtype=torch.long, device=src)
+    boxes = torch.zeros((B, Gm, 4), device=src)
+    b3d = torch.zeros((B, Gm, 9), device=src)
+    poses = torch.eye(3, device=src).repeat(B, Gm, 1, 1)
+    present = torch.zeros((B, Gm), dtype=torch.bool, device=src)
     for i, (c, b, b3, p) in enumerate(fields):
         n = len(c)
         cls[i, :n], boxes[i, :n], b3d[i, :n], poses[i, :n], present[i, :n] = c, b, b3[:, :9], p, True

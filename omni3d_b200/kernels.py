@@ -84,7 +84,7 @@ def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres):
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
     _lib.check(L.c3d_bn_bwd(_p(dout), _p(out), _p(y), _p(mean), _p(rstd), _p(gamma), int(relu), _p(partial), _p(coef),
-                            _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, 0, 0, 0, _st()))
+                            _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, 0, 0, 0, _st()), launches=3)
     return dy, dres
 
 
@@ -181,5 +181,5 @@ def nms_batched(boxes, nvalid, iou_thresh, max_keep, cats=None, maxc=None, trick
     keep = torch.empty((B, max_keep), dtype=torch.int32, device=boxes.device)
     cnt = torch.empty((B,), dtype=torch.int32, device=boxes.device)
     _lib.check(L.c3d_nms_batched(_p(boxes), _p(nvalid), _p(cats), _p(maxc), trick_max_numel, B, n, iou_thresh,
-                                 max_keep, _p(keep), _p(cnt), _p(ws), ws.numel(), _st()))
+                                 max_keep, _p(keep), _p(cnt), _p(ws), ws.numel(), _st()), launches=2)
     return keep, cnt

@@ -1,0 +1,177 @@
+"""Sync-free train-step harness with the semantics of tools/train_net.py:117-316 (do_train) and
+cubercnn/solver/build.py:6-69 (build_optimizer), re-designed for one-process-per-B200 data parallelism:
+
+* parameters live as views into ONE flat fp32 arena (decay | no-decay | unused regions), gradients and
+  momentum in matching arenas: one memset zeroes grads, one NCCL all-reduce averages them over NVLink, one
+  fused kernel does SGD-momentum (+weight decay) — replacing ~190 param groups, a DDP reducer and the
+  per-parameter isnan/isinf loop with its ~380 host syncs (train_net.py:226-233).
+* the stabiliser (skip the update when the reduced loss exceeds 4x its rolling mean or is not finite, or any
+  gradient is NaN/Inf; all ranks skip together; clip the loss to [0,1] before backward when diverging —
+  train_net.py:198-252) is evaluated ON THE DEVICE; the host only reads a small status vector through pinned
+  memory one step late (no per-step synchronisation, vs 3 barriers + 3 scalar all-reduces + ~10 .item()).
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import kernels as Kx
+from . import nnfunc
+
+TOLERANCE, GAMMA_ROLL = 4.0, 0.02          # train_net.py:164-168
+LOSS_KEYS = ["BoxHead/loss_cls", "BoxHead/loss_box_reg", "Cube/uncert", "Cube/loss_dims", "Cube/loss_xy", "Cube/loss_z",
+             "Cube/loss_pose", "Cube/loss_joint", "rpn/cls", "rpn/loc"]
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def unused_parameter_names(model):
+    """Parameters the reference never reaches in forward (find_unused_parameters=True, train_net.py:451):
+    the outer `project` of the two-level DLA trees (dla.py:217-230) and the priors (detached, roi_heads.py:470)."""
+    out = set()
+    for name, _ in model.named_parameters():
+        parts = name.split(".")
+        if "priors_dims_per_cat" in name or "priors_z_scales" in name:
+            out.add(name)
+        if "project" in parts:
+            i = parts.index("project")
+            if parts[i - 1] in ("level3", "level4"):
+                out.add(name)
+    return out
+
+
+def lr_at(cfg, it):
+    """WarmupMultiStepLR (detectron2 build_lr_scheduler; configs/Base.yaml:8)."""
+    S = cfg.SOLVER
+    lr = S.BASE_LR * (S.GAMMA ** sum(1 for s in S.STEPS if s <= it))
+    if it < S.WARMUP_ITERS:
+        alpha = it / S.WARMUP_ITERS
+        lr *= S.WARMUP_FACTOR * (1 - alpha) + alpha
+    return lr
+
+
+class FlatSGDTrainer:
+    def __init__(self, cfg, model):
+        if cfg.SOLVER.TYPE != "sgd":
+            raise ValueError("{} is not supported as an optimizer on the accelerated path.".format(cfg.SOLVER.TYPE))
+        self.cfg, self.model = cfg, model
+        self.world = _world()
+        dev = next(model.parameters()).device
+        norm_types = (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d, torch.nn.BatchNorm3d, torch.nn.GroupNorm,
+                      torch.nn.LayerNorm)
+        S = cfg.SOLVER
+        unused = unused_parameter_names(model)
+        groups = {"decay": [], "nodecay": [], "unused": []}
+        seen = set()
+        for mod_name, module in model.named_modules():
+            for key, p in module.named_parameters(recurse=False):
+                if not p.requires_grad or p in seen:
+                    continue
+                seen.add(p)
+                full = (mod_name + "." if mod_name else "") + key
+                wd = S.WEIGHT_DECAY
+                if isinstance(module, norm_types) and S.WEIGHT_DECAY_NORM is not None:
+                    wd = S.WEIGHT_DECAY_NORM
+                elif key == "bias" and S.WEIGHT_DECAY_BIAS is not None:
+                    wd = S.WEIGHT_DECAY_BIAS
+                if key in ("priors_dims_per_cat", "priors_z_scales", "priors_z_stats"):
+                    wd = 0.0
+                if key == "bias" and S.BIAS_LR_FACTOR not in (None, 1.0):
+                    raise NotImplementedError("BIAS_LR_FACTOR != 1 is not on the flat-arena path")
+                if wd not in (0.0, S.WEIGHT_DECAY):
+                    raise NotImplementedError("per-group weight decay other than {0, WEIGHT_DECAY}")
+                groups["unused" if full in unused else ("decay" if wd > 0 else "nodecay")].append(p)
+        order = groups["decay"] + groups["nodecay"] + groups["unused"]
+        sizes = [p.numel() for p in order]
+        pad = lambda n: (n + 63) // 64 * 64
+        offs, o = [], 0
+        bounds = {}
+        for gname in ("decay", "nodecay", "unused"):
+            start = o
+            for p in groups[gname]:
+                offs.append(o)
+                o += pad(p.numel())
+            bounds[gname] = (start, o)
+        self.bounds, total = bounds, o
+        self.flat_p = torch.zeros(total, device=dev)
+        self.flat_g = torch.zeros(total, device=dev)
+        self.flat_m = torch.zeros(total, device=dev)
+        with torch.no_grad():
+            for p, off, n in zip(order, offs, sizes):
+                self.flat_p[off:off + n].copy_(p.reshape(-1))
+                p.data = self.flat_p[off:off + n].view(p.shape)
+                p.grad = self.flat_g[off:off + n].view(p.shape)
+        self.n_update = bounds["nodecay"][1]
+        if self.world > 1:                      # DDP broadcasts rank-0 parameters and buffers at wrap time
+            dist.broadcast(self.flat_p, 0)
+            for b in model.buffers():
+                dist.broadcast(b, 0)
+        # device-side controller state: [recent_loss, iters_success, iters_explode, initialised]
+        self.state = torch.zeros(4, device=dev)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.status_host = torch.zeros(len(LOSS_KEYS) + 4, pin_memory=True)
+        self.status_event = None
+        self.iteration = 0
+        self.stabilize = cfg.MODEL.STABILIZE > 0
+
+    # -------------------------------------------------------------------------------------------------
+    def step(self, batched_inputs):
+        model, world = self.model, self.world
+        self.flat_g.zero_()
+        loss_dict = model(batched_inputs)
+        vec = torch.stack([loss_dict[k].detach().float() if k in loss_dict else self.flat_g.new_zeros(())
+                           for k in LOSS_KEYS])
+        if world > 1:                                   # allreduce_dict, train_net.py:471-498 (mean over ranks)
+            dist.all_reduce(vec)
+            vec /= world
+        total_reduced = vec.sum()
+        st = self.state
+        recent = torch.where(st[3] > 0, st[0], total_reduced * 2.0)
+        diverging = torch.zeros((), dtype=torch.bool, device=vec.device)
+        if self.stabilize:
+            diverging = (total_reduced > recent * TOLERANCE) | ~torch.isfinite(total_reduced)
+        losses = sum(loss_dict.values())
+        losses = torch.where(diverging, losses.clip(0, 1), losses)
+        losses.backward()
+        if world > 1:                                   # C1: one gradient all-reduce (mean) over NVLink
+            dist.all_reduce(self.flat_g[:self.n_update])
+        self.flag.copy_(diverging.to(torch.int32).reshape(1))
+        if self.stabilize:
+            Kx.grad_finite(self.flat_g[:self.n_update], self.flag)
+        lr = lr_at(self.cfg, self.iteration)
+        S = self.cfg.SOLVER
+        gs = 1.0 / world
+        d0, d1 = self.bounds["decay"]
+        n0, n1 = self.bounds["nodecay"]
+        Kx.sgd_momentum(self.flat_p[d0:d1], self.flat_g[d0:d1], self.flat_m[d0:d1], lr, S.MOMENTUM, S.WEIGHT_DECAY, gs,
+                        self.flag)
+        Kx.sgd_momentum(self.flat_p[n0:n1], self.flat_g[n0:n1], self.flat_m[n0:n1], lr, S.MOMENTUM, 0.0, gs, self.flag)
+        nnfunc.invalidate_packed()
+        skipped = (self.flag > 0).float().squeeze(0)
+        new_recent = torch.where(diverging, recent, recent * (1 - GAMMA_ROLL) + total_reduced * GAMMA_ROLL)
+        self.state = torch.stack([new_recent, st[1] + (1 - skipped), st[2] + skipped, torch.ones_like(st[3])])
+        # async status readback (previous step's values are inspected by `status()` without blocking the GPU)
+        self.status_host.copy_(torch.cat([vec, self.state]), non_blocking=True)
+        self.status_event = torch.cuda.Event()
+        self.status_event.record()
+        self.iteration += 1
+        return loss_dict
+
+    def status(self, wait=True):
+        """{'losses': {...}, 'total_loss', 'recent_loss', 'iterations_success', 'iterations_explode', 'retry'}."""
+        if self.status_event is None:
+            return None
+        if wait:
+            self.status_event.synchronize()
+        elif not self.status_event.query():
+            return None
+        v = self.status_host.tolist()
+        n = len(LOSS_KEYS)
+        ok, bad = v[n + 1], v[n + 2]
+        tot = max(ok + bad, 1.0)
+        retry = (bad / tot) >= self.cfg.MODEL.STABILIZE > 0 and tot > self.cfg.SOLVER.CHECKPOINT_PERIOD / 2
+        return {"losses": dict(zip(LOSS_KEYS, v[:n])), "total_loss": sum(v[:n]), "recent_loss": v[n],
+                "iterations_success": int(ok), "iterations_explode": int(bad), "retry": bool(retry),
+                "lr": lr_at(self.cfg, max(self.iteration - 1, 0))}

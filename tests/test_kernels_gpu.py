@@ -62,14 +62,16 @@ def test_conv_bn_act_train_vs_torch(C, relu, res):
         yr = F.relu(yr)
     yr.backward(dy.float().permute(0, 3, 1, 2))
     tol = lambda ref, f=2e-2: f * ref.abs().max().item() + 2e-3
+    # gradients: relative Frobenius error (a ReLU mask that flips on a near-zero pre-activation moves single
+    # elements by a whole dout, so max-abs is not a meaningful bound for the bf16 path)
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
     assert (out.float() - yr.permute(0, 2, 3, 1)).abs().max().item() <= tol(yr)
     assert (rm - rmr).abs().max().item() < 1e-3 and (rv - rvr).abs().max().item() < 1e-3
-    assert (gamma.grad - gr.grad).abs().max().item() <= tol(gr.grad, 3e-2)
-    assert (beta.grad - br.grad).abs().max().item() <= tol(br.grad, 3e-2)
-    assert (x.grad.float() - xr.grad.permute(0, 2, 3, 1)).abs().max().item() <= tol(xr.grad, 4e-2)
-    assert (w.grad - wr.grad).abs().max().item() <= tol(wr.grad, 4e-2)
+    assert rel(gamma.grad, gr.grad) < 2e-2 and rel(beta.grad, br.grad) < 2e-2
+    assert rel(x.grad.float(), xr.grad.permute(0, 2, 3, 1)) < 2e-2
+    assert rel(w.grad, wr.grad) < 2e-2
     if res:
-        assert (r.grad.float() - rr.grad.permute(0, 2, 3, 1)).abs().max().item() <= tol(rr.grad)
+        assert rel(r.grad.float(), rr.grad.permute(0, 2, 3, 1)) < 1e-2
 
 
 def test_maxpool2_fwd_bwd():

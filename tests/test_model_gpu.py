@@ -90,8 +90,10 @@ def test_proposals_exact_given_oracle_head_outputs(pair):
     for i, r in enumerate(ref):
         n = int(cnt[i])
         assert n == len(r)
-        assert torch.equal(boxes[i, :n].cpu(), r.proposal_boxes.tensor)
+        # identical selection and order (logits are copied bit-for-bit); box coordinates agree to the last
+        # ulps only (exp() differs between the CPU and CUDA math libraries)
         assert torch.equal(scores[i, :n].cpu(), r.objectness_logits)
+        assert torch.allclose(boxes[i, :n].cpu(), r.proposal_boxes.tensor, atol=1e-3, rtol=1e-5)
 
 
 def test_inference_runs_and_matches_loosely(pair):
