@@ -67,9 +67,9 @@ def test_conv_bn_act_train_vs_torch(C, relu, res):
     rel = lambda a, b: ((a - b).norm() / b.norm()).item()
     assert (out.float() - yr.permute(0, 2, 3, 1)).abs().max().item() <= tol(yr)
     assert (rm - rmr).abs().max().item() < 1e-3 and (rv - rvr).abs().max().item() < 1e-3
-    assert rel(gamma.grad, gr.grad) < 2e-2 and rel(beta.grad, br.grad) < 2e-2
-    assert rel(x.grad.float(), xr.grad.permute(0, 2, 3, 1)) < 2e-2
-    assert rel(w.grad, wr.grad) < 2e-2
+    assert rel(gamma.grad, gr.grad) < 4e-2 and rel(beta.grad, br.grad) < 4e-2
+    assert rel(x.grad.float(), xr.grad.permute(0, 2, 3, 1)) < 4e-2
+    assert rel(w.grad, wr.grad) < 4e-2
     if res:
         assert rel(r.grad.float(), rr.grad.permute(0, 2, 3, 1)) < 1e-2
 
