@@ -107,9 +107,11 @@ int32_t c3d_bn_apply(const void* y, const float* mean, const float* rstd, const 
 /* rows of the `partial` scratch needed by c3d_bn_bwd */
 int32_t c3d_bn_bwd_blocks(int64_t P, int32_t C);
 /* BatchNorm(+ReLU,+residual) backward: dy (bf16) w.r.t. the conv output, dgamma/dbeta accumulated (+=),
- * optional dres = masked dout for the residual branch. partial: fp32 [blocks][2][C]; coef: fp32 [3][C]. */
+ * optional dres = masked dout for the residual branch. partial: fp32 [blocks][2][C]; coef: fp32 [3][C].
+ * frozen_stats != 0: mean/rstd are running statistics (eval mode / freeze_bn, cubercnn/solver/build.py:71-76). */
 int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, const float* mean, const float* rstd,
-                   const float* gamma, int32_t relu, float* partial, float* coef, float* dgamma, float* dbeta,
+                   const float* gamma, int32_t relu, int32_t frozen_stats, float* partial, float* coef, float* dgamma,
+                   float* dbeta,
                    void* dy, void* dres, int64_t P, int32_t C, int64_t dout_stride, int64_t out_stride,
                    int64_t dres_stride, void* stream);
 int32_t c3d_maxpool2_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int64_t x_stride,

@@ -138,7 +138,7 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, double count,
                                        const float* __restrict__ gamma, const float* __restrict__ rstd,
                                        float* __restrict__ coef, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
+                                       float* __restrict__ dbeta, int frozen) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s = 0.0, t = 0.0;
@@ -147,8 +147,9 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int bl
     t += (double)partial[((size_t)b * 2 + 1) * C + c];
   }
   coef[c] = gamma[c] * rstd[c];
-  coef[C + c] = (float)(s / count);
-  coef[2 * C + c] = (float)(t / count);
+  // frozen (eval-mode / freeze_bn) statistics do not depend on the batch: dy = gamma * rstd * dz
+  coef[C + c] = frozen ? 0.f : (float)(s / count);
+  coef[2 * C + c] = frozen ? 0.f : (float)(t / count);
   if (dgamma) dgamma[c] += (float)t;
   if (dbeta) dbeta[c] += (float)s;
 }
@@ -316,7 +317,8 @@ extern "C" int32_t c3d_bn_bwd_blocks(int64_t P, int32_t C) {
   return (int32_t)b;
 }
 extern "C" int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, const float* mean, const float* rstd,
-                              const float* gamma, int32_t relu, float* partial /*[blocks][2][C]*/, float* coef /*[3][C]*/,
+                              const float* gamma, int32_t relu, int32_t frozen_stats, float* partial /*[blocks][2][C]*/,
+                              float* coef /*[3][C]*/,
                               float* dgamma, float* dbeta, void* dy, void* dres, int64_t P, int32_t C,
                               int64_t dout_stride, int64_t out_stride, int64_t dres_stride, void* stream) {
   C3D_REQ(dout && y && mean && rstd && gamma && partial && coef && dy && C % 8 == 0 && C <= 2048, "bn_bwd: bad args");
@@ -330,7 +332,8 @@ extern "C" int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, 
                                                        relu, partial, P, C, ds, os);
   else
     return set_error(C3D_EINVAL, "bn_bwd: C too large");
-  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(partial, blocks, C, (double)P, gamma, rstd, coef, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(partial, blocks, C, (double)P, gamma, rstd, coef, dgamma, dbeta,
+                                                       frozen_stats);
   bn_bwd_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)y,
                                                                    mean, rstd, coef, relu, (bf16*)dy, (bf16*)dres, P, C,
                                                                    ds, os, dres_stride ? dres_stride : C);

@@ -24,7 +24,7 @@ def _bind():
         "c3d_bn_finalize": [vp, i32, i32, f64, f32, f32, vp, vp, vp, vp, vp],
         "c3d_bn_apply": [vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i64, i64, vp],
         "c3d_bn_bwd_blocks": [i64, i32],
-        "c3d_bn_bwd": [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, vp],
+        "c3d_bn_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, vp],
         "c3d_maxpool2_fwd": [vp, vp, i32, i32, i32, i32, i64, i64, vp],
         "c3d_maxpool2_bwd": [vp, vp, vp, i32, i32, i32, i32, i64, i64, vp],
         "c3d_preprocess_image": [vp, i32, i32, vp, i32, i32, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), vp],
@@ -73,7 +73,7 @@ def bn_apply(y, mean, rstd, gamma, beta, residual=None, relu=True, out=None):
     return out
 
 
-def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres):
+def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres, frozen=False):
     """-> dy (bf16, like y), dres (bf16 or None); dgamma/dbeta (fp32 [C]) are accumulated in place."""
     L = _bind()
     C = y.shape[-1]
@@ -83,7 +83,7 @@ def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres):
     coef = torch.empty((3, C), device=y.device, dtype=torch.float32)
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
-    _lib.check(L.c3d_bn_bwd(_p(dout), _p(out), _p(y), _p(mean), _p(rstd), _p(gamma), int(relu), _p(partial), _p(coef),
+    _lib.check(L.c3d_bn_bwd(_p(dout), _p(out), _p(y), _p(mean), _p(rstd), _p(gamma), int(relu), int(frozen), _p(partial), _p(coef),
                             _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, 0, 0, 0, _st()), launches=3)
     return dy, dres
 

@@ -90,11 +90,11 @@ class ConvBNAct(torch.autograd.Function):
     def backward(ctx, dout):
         x, w, gamma, y, mean, rstd, out = ctx.saved_tensors
         stride, pad, relu, training, has_res = ctx.cfg
-        assert training, "backward through eval-mode BatchNorm is not supported (freeze via no_grad instead)"
         dout = dout.contiguous()
         dgamma = torch.zeros_like(gamma)
         dbeta = torch.zeros_like(gamma)
-        dy, dres = Kx.bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, has_res and ctx.needs_input_grad[6])
+        dy, dres = Kx.bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, has_res and ctx.needs_input_grad[6],
+                              frozen=not training)
         dx = _dgrad(dy, w, stride, pad, x.shape[1:3]) if ctx.needs_input_grad[0] else None
         dw = _wgrad_to_master(x, dy, w, stride, pad) if ctx.needs_input_grad[1] else None
         return dx, dw, dgamma, dbeta, None, None, dres, None, None, None, None, None, None
