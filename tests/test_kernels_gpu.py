@@ -71,7 +71,7 @@ def test_conv_bn_act_train_vs_torch(C, relu, res):
     assert rel(x.grad.float(), xr.grad.permute(0, 2, 3, 1)) < 4e-2
     assert rel(w.grad, wr.grad) < 4e-2
     if res:
-        assert rel(r.grad.float(), rr.grad.permute(0, 2, 3, 1)) < 1e-2
+        assert rel(r.grad.float(), rr.grad.permute(0, 2, 3, 1)) < 4e-2
 
 
 def test_maxpool2_fwd_bwd():
