@@ -98,8 +98,11 @@ int32_t c3d_conv2d_wgrad(const c3d_conv_desc* d, const void* x, const void* dy, 
  * SGD step + per-parameter finite check (tools/train_net.py:226-252, cubercnn/solver/build.py:47-56).
  * ------------------------------------------------------------------------------------------ */
 /* per-channel batch statistics from the conv epilogue partials [rows][2][C] -> mean, rstd (+ running stats) */
+/* scratch (fp64 slab sums) needed by c3d_bn_finalize / c3d_bn_bwd */
+size_t c3d_bn_scratch_bytes(int32_t C);
 int32_t c3d_bn_finalize(const float* partial, int32_t rows, int32_t C, double count, float eps, float momentum,
-                        float* running_mean, float* running_var, float* mean_out, float* rstd_out, void* stream);
+                        float* running_mean, float* running_var, float* mean_out, float* rstd_out, void* scratch,
+                        void* stream);
 /* out = [relu]((y-mean)*rstd*gamma+beta [+ residual]); y,out,residual bf16 (P pixels x C) */
 int32_t c3d_bn_apply(const void* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
                      const void* residual, int32_t relu, void* out, int64_t P, int32_t C, int64_t res_stride,
@@ -113,7 +116,17 @@ int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, const float
                    const float* gamma, int32_t relu, int32_t frozen_stats, float* partial, float* coef, float* dgamma,
                    float* dbeta,
                    void* dy, void* dres, int64_t P, int32_t C, int64_t dout_stride, int64_t out_stride,
-                   int64_t dres_stride, void* stream);
+                   int64_t dres_stride, void* scratch, void* stream);
+/* backward of the bias(+ReLU) epilogue of the bias convs (FPN / RPN head): dz (bf16) = dout * (out > 0 if relu),
+ * dbias (fp32 [C]) += sum over pixels.  dout/out are bf16, or fp32 when dout_fp32 != 0.
+ * partial: fp32 [c3d_bn_bwd_blocks(P,C)][C]; scratch: c3d_bn_scratch_bytes(C). */
+int32_t c3d_bias_act_bwd(const void* dout, const void* out, int32_t relu, int32_t dout_fp32, void* dz, float* partial,
+                         float* dbias, int64_t P, int32_t C, void* scratch, void* stream);
+/* y (N,H/2,W/2,C) = 2x2 block sums of x: gradient of the FPN nearest-x2 upsampling */
+int32_t c3d_sumpool2(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+/* z (N,H,W,C) = dy (N,Ho,Wo,C) at even positions, zero elsewhere: input of a stride-2 conv's data gradient */
+int32_t c3d_zero_stuff2(const void* dy, void* z, int32_t N, int32_t Ho, int32_t Wo, int32_t H, int32_t W, int32_t C,
+                        void* stream);
 int32_t c3d_maxpool2_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int64_t x_stride,
                          int64_t y_stride, void* stream);
 int32_t c3d_maxpool2_bwd(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C,

@@ -293,33 +293,36 @@ static int32_t launch_conv(const CUtensorMap& mx, const CUtensorMap& mw, const C
 
 // ------------------------------------------------------------------------------------------------
 // Weight gradient: dW[co][kh][kw][ci] += sum_pixels dY[p][co] * X[p*stride + tap - pad][ci].
-// GEMM view per tap: M = Cout (128 per CTA), N = Cin tile, K = pixels.  Both operands are
-// "MN-major" for the tensor core (the contiguous NHWC channel axis is M resp. N, pixels are K):
-// the very same 4-D TMA boxes as the forward pass ([RH][RW][64 channels], 128B swizzle) are
-// consumed through MN-major shared-memory descriptors.  Grid = (pixel-range split, tap, co/ci
-// tile); split-K partials are reduced with fp32 atomics straight into the gradient arena.
+// GEMM view: M = Cout (128 per CTA), N = (tap, ci) columns — up to 256 per CTA, made of whole TMA boxes
+// [pixels][cw channels] (cw = 64/32/16), so small-Cin layers put SEVERAL TAPS side by side in N and dY is
+// re-read ceil(taps*Cin/256) times instead of `taps` times — K = pixels.  Both operands are "MN-major"
+// for the tensor core (the contiguous NHWC channel axis is M resp. N, pixels are K): the same 4-D TMA
+// boxes as the forward pass are consumed through MN-major shared-memory descriptors.  Grid = (pixel-range
+// split, column group, co tile); split-K partials are reduced with fp32 atomics into the gradient buffer.
 struct WgradKParams {
   int N, Ho, Wo, Cout, Cin;
   int KH, KW, stride, pad;
   int RH, RW, tiles_h, tiles_w;
   int num_tiles, tiles_per_split;
-  int ci_tiles;
-  float* dw;                  // [Cout][KH][KW][Cin] fp32, accumulated with atomics
+  int cw, nci, boxes_per_cta, total_boxes;   // B boxes: width cw channels, nci = Cin / cw per tap
+  int ca, a_chunks_max;                      // A boxes: width ca channels
+  float* dw;                                 // [Cout][KH][KW][Cin] fp32, accumulated with atomics
 };
 
-template <int BLOCK_N, int STAGES>
+template <int STAGES>
 struct WgradSmem {
-  static constexpr int kChunk = 128 * 128;                    // one [<=128 px][64 ch] sub-tile slot
-  static constexpr int kStageBytes = kChunk * (2 + BLOCK_N / 64);
+  static constexpr int kABytes = 2 * 128 * 128;            // up to two [128 px][64 ch] chunks (or narrower)
+  static constexpr int kBBytes = 128 * 256 * 2;            // 256 columns x 128 pixels
+  static constexpr int kStageBytes = kABytes + kBBytes;    // 96 KB
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;
 };
 
-template <int BLOCK_N, int STAGES>
+template <int STAGES>
 __global__ void __launch_bounds__(192)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                      const WgradKParams P) {
-  using S = WgradSmem<BLOCK_N, STAGES>;
+  using S = WgradSmem<STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
@@ -328,15 +331,17 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int split = blockIdx.x, tap = blockIdx.y;
-  const int co_tile = blockIdx.z / P.ci_tiles, ci_tile = blockIdx.z - co_tile * P.ci_tiles;
-  const int co0 = co_tile * 128, ci0 = ci_tile * BLOCK_N;
-  const int kh = tap / P.KW, kw = tap - kh * P.KW;
+  const int split = blockIdx.x, group = blockIdx.y, co_tile = blockIdx.z;
+  const int co0 = co_tile * 128;
+  const int box0 = group * P.boxes_per_cta;
+  const int nb = min(P.boxes_per_cta, P.total_boxes - box0);       // boxes (taps x ci chunks) of this CTA
+  const int ncols = nb * P.cw;                                     // UMMA N (multiple of 16, <= 256)
   const int t_begin = split * P.tiles_per_split;
   const int t_end = min(P.num_tiles, t_begin + P.tiles_per_split);
   const int R = P.RH * P.RW;
-  const int a_chunks = (P.Cout - co0) > 64 ? 2 : 1;
-  int b_chunks = (P.Cin - ci0 + 63) / 64; if (b_chunks > BLOCK_N / 64) b_chunks = BLOCK_N / 64;
+  int a_chunks = (P.Cout - co0 + P.ca - 1) / P.ca;
+  if (a_chunks > P.a_chunks_max) a_chunks = P.a_chunks_max;
+  const uint32_t a_box_bytes = (uint32_t)(128 * P.ca * 2), b_box_bytes = (uint32_t)(128 * P.cw * 2);
 
   if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&tmap_dy); ptx::prefetch_tensormap(&tmap_x); }
   if (warp == 1 && lane == 0) {
@@ -344,7 +349,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc<BLOCK_N>(tmem_ptr);
+  if (warp == 2) ptx::tmem_alloc<256>(tmem_ptr);
   ptx::tcgen05_fence_before();
   __syncthreads();
   ptx::tcgen05_fence_after();
@@ -354,39 +359,45 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
     if (warp == 0) {
       if (ptx::elect_one()) {
         int stage = 0; uint32_t phase = 0;
-        const uint32_t bytes = (uint32_t)(R * 128 * (a_chunks + b_chunks));
+        const uint32_t bytes = (uint32_t)(R * 2 * (a_chunks * P.ca + nb * P.cw));
         for (int t = t_begin; t < t_end; ++t) {
           const int tw_i = t % P.tiles_w, th_i = (t / P.tiles_w) % P.tiles_h, img = t / (P.tiles_w * P.tiles_h);
           const int ho0 = th_i * P.RH, wo0 = tw_i * P.RW;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
           ptx::mbar_expect_tx(&full_bar[stage], bytes);
           for (int c = 0; c < a_chunks; ++c)
-            ptx::tma_load_4d(sa + c * S::kChunk, &tmap_dy, &full_bar[stage], co0 + 64 * c, wo0, ho0, img);
-          for (int c = 0; c < b_chunks; ++c)
-            ptx::tma_load_4d(sa + (2 + c) * S::kChunk, &tmap_x, &full_bar[stage], ci0 + 64 * c,
+            ptx::tma_load_4d(sa + c * a_box_bytes, &tmap_dy, &full_bar[stage], co0 + P.ca * c, wo0, ho0, img);
+          for (int b = 0; b < nb; ++b) {
+            const int box = box0 + b;
+            const int tap = box / P.nci, chunk = box - tap * P.nci;
+            const int kh = tap / P.KW, kw = tap - kh * P.KW;
+            ptx::tma_load_4d(sb + b * b_box_bytes, &tmap_x, &full_bar[stage], chunk * P.cw,
                              wo0 * P.stride + kw - P.pad, ho0 * P.stride + kh - P.pad, img);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     } else if (warp == 1) {
       if (ptx::elect_one()) {
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N, 1, 1);
+        const uint32_t idesc = ptx::make_idesc_bf16(128, ncols, 1, 1);
+        const uint32_t lt_a = ptx::swizzle_layout_type(P.ca * 2), lt_b = ptx::swizzle_layout_type(P.cw * 2);
         int stage = 0; uint32_t phase = 0;
         const int ksteps = R / 16;
+        // MN-major descriptors: LBO = distance between channel chunks, SBO = 8 pixel rows
+        const uint32_t a_sbo = 8 * P.ca * 2, b_sbo = 8 * P.cw * 2;
+        const uint32_t a_kstep = (16 * P.ca * 2) >> 4, b_kstep = (16 * P.cw * 2) >> 4;
         for (int t = t_begin; t < t_end; ++t) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tcgen05_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * S::kStageBytes);
-          const uint32_t sb = sa + 2 * S::kChunk;
-          // MN-major, 128B swizzle: LBO = distance between 64-channel chunks, SBO = 8 pixel rows
-          const uint64_t da = ptx::make_smem_desc(sa, S::kChunk, 1024, 2);
-          const uint64_t db = ptx::make_smem_desc(sb, S::kChunk, 1024, 2);
-          for (int k = 0; k < ksteps; ++k) {
-            // 16 pixel rows = 2048 bytes per K step: +128 in the (addr>>4) field
-            ptx::umma_bf16(tmem_base, da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc,
+          const uint32_t sb = sa + S::kABytes;
+          const uint64_t da = ptx::make_smem_desc(sa, a_box_bytes, a_sbo, lt_a);
+          const uint64_t db = ptx::make_smem_desc(sb, b_box_bytes, b_sbo, lt_b);
+          for (int k = 0; k < ksteps; ++k)
+            ptx::umma_bf16(tmem_base, da + (uint64_t)(a_kstep * k), db + (uint64_t)(b_kstep * k), idesc,
                            (t != t_begin || k != 0) ? 1u : 0u);
-          }
           ptx::umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -397,17 +408,20 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
       const int co = co0 + q * 32 + lane;
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tcgen05_fence_after();
-      const int n_valid = min(BLOCK_N, P.Cin - ci0);
+      const int taps = P.KH * P.KW;
 #pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 16; ++ch) {
-        if (ch * 16 >= n_valid) break;                    // warp-uniform
+      for (int ch = 0; ch * 16 < ncols; ++ch) {
         uint32_t v[16];
         ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), v);
         ptx::tmem_ld_wait();
-        if (co < P.Cout) {
-          float* dst = P.dw + ((size_t)co * (P.KH * P.KW) + tap) * P.Cin + ci0 + ch * 16;
+        const int n = ch * 16;
+        const int box = box0 + n / P.cw;
+        const int tap = box / P.nci, ci = (box - tap * P.nci) * P.cw + (n % P.cw);
+        if (co < P.Cout && ci < P.Cin) {
+          float* dst = P.dw + ((size_t)co * taps + tap) * P.Cin + ci;
+          const int lim = min(16, P.Cin - ci);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+          for (int i = 0; i < 16; ++i) if (i < lim) atomicAdd(dst + i, __uint_as_float(v[i]));
         }
       }
     }
@@ -416,7 +430,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
   __syncthreads();
   if (warp == 2) {
     ptx::tcgen05_fence_after();
-    ptx::tmem_dealloc<BLOCK_N>(tmem_base);
+    ptx::tmem_dealloc<256>(tmem_base);
   }
 }
 
@@ -434,21 +448,6 @@ static void pick_tile_k(int Ho, int Wo, int stride, int* RH, int* RW) {
     }
   }
   *RH = bth; *RW = btw;
-}
-
-template <int BN, int ST>
-static int32_t launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgradKParams& P, dim3 grid,
-                            cudaStream_t st) {
-  using S = WgradSmem<BN, ST>;
-  auto kern = conv_wgrad_tc_kernel<BN, ST>;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
-    if (e != cudaSuccess) return set_error(C3D_ECUDA, "wgrad smem attr: %s", cudaGetErrorString(e));
-    attr = true;
-  }
-  kern<<<grid, 192, S::kTotal, st>>>(mdy, mx, P);
-  return check_launch("conv_wgrad_tc_kernel");
 }
 
 }  // namespace c3d
@@ -541,7 +540,7 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
 extern "C" int32_t c3d_conv2d_wgrad(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
   if (!d || !x || !dy || !dw) return set_error(C3D_EINVAL, "wgrad: null pointer");
   const int Cin = d->Cin, Cout = d->Cout;
-  if (Cin % 8 != 0 || Cout % 8 != 0) return set_error(C3D_EINVAL, "wgrad: channels must be multiples of 8");
+  if (Cin % 16 != 0 || Cout % 16 != 0) return set_error(C3D_EINVAL, "wgrad: channels must be multiples of 16");
   if (d->stride < 1 || d->stride > 2) return set_error(C3D_EINVAL, "wgrad: stride %d unsupported", d->stride);
   const int Ho = (d->H + 2 * d->pad - d->KH) / d->stride + 1;
   const int Wo = (d->W + 2 * d->pad - d->KW) / d->stride + 1;
@@ -553,12 +552,16 @@ extern "C" int32_t c3d_conv2d_wgrad(const c3d_conv_desc* d, const void* x, const
   pick_tile_k(Ho, Wo, d->stride, &P.RH, &P.RW);
   P.tiles_h = (Ho + P.RH - 1) / P.RH; P.tiles_w = (Wo + P.RW - 1) / P.RW;
   P.num_tiles = d->N * P.tiles_h * P.tiles_w;
-  const int BN = Cin > 128 ? 256 : (Cin > 64 ? 128 : 64);
-  P.ci_tiles = (Cin + BN - 1) / BN;
-  const int co_tiles = (Cout + 127) / 128;
   const int taps = d->KH * d->KW;
-  // split the pixel range so the grid is ~4 waves of 148 SMs
-  long long base = (long long)taps * co_tiles * P.ci_tiles;
+  P.cw = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
+  P.nci = Cin / P.cw;
+  P.boxes_per_cta = 256 / P.cw;
+  P.total_boxes = taps * P.nci;
+  P.ca = (Cout % 64 == 0) ? 64 : (Cout % 32 == 0 ? 32 : 16);
+  P.a_chunks_max = 128 / P.ca;                  // chunks beyond Cout are not loaded (those D rows are never stored)
+  const int groups = (P.total_boxes + P.boxes_per_cta - 1) / P.boxes_per_cta;
+  const int co_tiles = (Cout + 127) / 128;
+  long long base = (long long)groups * co_tiles;
   int splits = (int)((4LL * kNumSMs + base - 1) / base);
   if (splits > P.num_tiles) splits = P.num_tiles;
   if (splits < 1) splits = 1;
@@ -571,26 +574,33 @@ extern "C" int32_t c3d_conv2d_wgrad(const c3d_conv_desc* d, const void* x, const
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)d->N};
     cuuint64_t strides[3] = {(cuuint64_t)yps * 2, (cuuint64_t)yps * 2 * Wo, (cuuint64_t)yps * 2 * Wo * Ho};
-    cuuint32_t box[4] = {64, (cuuint32_t)P.RW, (cuuint32_t)P.RH, 1};
+    cuuint32_t box[4] = {(cuuint32_t)P.ca, (cuuint32_t)P.RW, (cuuint32_t)P.RH, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&mdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz(P.ca * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(C3D_ECUDA, "encode dy tensormap failed: %d", (int)r);
   }
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     cuuint64_t strides[3] = {(cuuint64_t)xps * 2, (cuuint64_t)xps * 2 * d->W, (cuuint64_t)xps * 2 * d->W * d->H};
-    cuuint32_t box[4] = {64, (cuuint32_t)(P.RW * d->stride), (cuuint32_t)(P.RH * d->stride), 1};
+    cuuint32_t box[4] = {(cuuint32_t)P.cw, (cuuint32_t)(P.RW * d->stride), (cuuint32_t)(P.RH * d->stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
     CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz(P.cw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(C3D_ECUDA, "encode x tensormap failed: %d", (int)r);
   }
-  dim3 grid((unsigned)splits, (unsigned)taps, (unsigned)(co_tiles * P.ci_tiles));
+  dim3 grid((unsigned)splits, (unsigned)groups, (unsigned)co_tiles);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (BN == 256) return launch_wgrad<256, 2>(mdy, mx, P, grid, st);
-  if (BN == 128) return launch_wgrad<128, 3>(mdy, mx, P, grid, st);
-  return launch_wgrad<64, 4>(mdy, mx, P, grid, st);
+  using S = WgradSmem<2>;
+  auto kern = conv_wgrad_tc_kernel<2>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) return set_error(C3D_ECUDA, "wgrad smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  kern<<<grid, 192, S::kTotal, st>>>(mdy, mx, P);
+  return check_launch("conv_wgrad_tc_kernel");
 }

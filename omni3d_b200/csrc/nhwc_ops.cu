@@ -39,16 +39,43 @@ static inline int grid_for(long long work_items, int threads) {
 }
 
 // ---- BatchNorm forward ------------------------------------------------------------------------
-// partial: [rows][2][C] per-tile (sum, sumsq) from the conv epilogue.  One thread per channel.
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count, float eps,
+// Column sums of a [rows][cols] fp32 matrix in fixed order (deterministic): stage 1 = slabs of rows per
+// block (64 columns x 4 row lanes), doubles out; the consumers below finish over <= kSlabs slabs.
+constexpr int kSlabs = 128;
+__global__ void colsum_stage1_kernel(const float* __restrict__ m, int rows, int cols, int rows_per_slab,
+                                     double* __restrict__ out /*[gridDim.y][cols]*/) {
+  const int col = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int lane = threadIdx.x >> 6;                       // 0..3
+  const int r0 = blockIdx.y * rows_per_slab;
+  const int r1 = min(rows, r0 + rows_per_slab);
+  double acc = 0.0;
+  if (col < cols)
+    for (int r = r0 + lane; r < r1; r += 4) acc += (double)m[(size_t)r * cols + col];
+  __shared__ double sm[4][64];
+  sm[lane][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (lane == 0 && col < cols)
+    out[(size_t)blockIdx.y * cols + col] = ((sm[0][threadIdx.x] + sm[1][threadIdx.x]) + sm[2][threadIdx.x]) + sm[3][threadIdx.x];
+}
+static inline void launch_colsum(const float* m, int rows, int cols, double* scratch, int* slabs_out, cudaStream_t st) {
+  int slabs = rows < kSlabs ? rows : kSlabs;
+  int rps = (rows + slabs - 1) / slabs;
+  slabs = (rows + rps - 1) / rps;
+  dim3 grid((cols + 63) / 64, slabs);
+  colsum_stage1_kernel<<<grid, 256, 0, st>>>(m, rows, cols, rps, scratch);
+  *slabs_out = slabs;
+}
+
+// partial: [rows][2][C] per-tile (sum, sumsq) from the conv epilogue -> slab sums -> statistics.
+__global__ void bn_finalize_kernel(const double* __restrict__ slab, int slabs, int C, double count, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean_out, float* __restrict__ rstd_out) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s = 0.0, s2 = 0.0;
-  for (int r = 0; r < rows; ++r) {
-    s += (double)partial[(size_t)r * 2 * C + c];
-    s2 += (double)partial[(size_t)r * 2 * C + C + c];
+  for (int r = 0; r < slabs; ++r) {
+    s += slab[(size_t)r * 2 * C + c];
+    s2 += slab[(size_t)r * 2 * C + C + c];
   }
   double mean = s / count;
   double var = s2 / count - mean * mean;
@@ -135,7 +162,7 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* 
 }
 
 // coef[0][c] = gamma*rstd, coef[1][c] = mean(dz), coef[2][c] = mean(dz*xhat); dgamma/dbeta accumulated (+=)
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, double count,
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int blocks, int C, double count,
                                        const float* __restrict__ gamma, const float* __restrict__ rstd,
                                        float* __restrict__ coef, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, int frozen) {
@@ -143,8 +170,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int bl
   if (c >= C) return;
   double s = 0.0, t = 0.0;
   for (int b = 0; b < blocks; ++b) {
-    s += (double)partial[((size_t)b * 2 + 0) * C + c];
-    t += (double)partial[((size_t)b * 2 + 1) * C + c];
+    s += partial[((size_t)b * 2 + 0) * C + c];
+    t += partial[((size_t)b * 2 + 1) * C + c];
   }
   coef[c] = gamma[c] * rstd[c];
   // frozen (eval-mode / freeze_bn) statistics do not depend on the batch: dy = gamma * rstd * dz
@@ -181,6 +208,102 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* _
     }
     st8(dy + p * C + c, g);
     if (dres) st8(dres + p * dres_stride + c, d);
+  }
+}
+
+// ---- bias / ReLU backward for the bias convs (FPN, RPN head) -----------------------------------------
+// dz = dout * (out > 0 if relu) written as bf16; partial[block][c] = sum over the block's pixels of dz (dbias)
+template <int THREADS, typename TIN>
+__global__ void bias_act_bwd_kernel(const TIN* __restrict__ dout, const TIN* __restrict__ out, int relu,
+                                    bf16* __restrict__ dz, float* __restrict__ partial, long long P, int C) {
+  const int cv = C >> 3;
+  const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
+  const int rows_per_block = THREADS / cv;
+  const int c = tx << 3;
+  float s[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = 0.f;
+  auto load = [&](const TIN* p) {
+    V8 r;
+    if constexpr (sizeof(TIN) == 2) { r = ld8(reinterpret_cast<const bf16*>(p)); }
+    else {
+      const float4* q = reinterpret_cast<const float4*>(p);
+      float4 a = q[0], b = q[1];
+      r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    }
+    return r;
+  };
+  if (ty < rows_per_block) {
+    for (long long p = (long long)blockIdx.x * rows_per_block + ty; p < P; p += (long long)gridDim.x * rows_per_block) {
+      V8 d = load(dout + p * C + c);
+      if (relu) {
+        V8 o = load(out + p * C + c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (!(o.v[k] > 0.f)) d.v[k] = 0.f;
+      }
+      st8(dz + p * C + c, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] += d.v[k];
+    }
+  }
+  __shared__ float sm[THREADS][8 + 1];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sm[threadIdx.x][k] = s[k];
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += THREADS) {
+    const int vx = ch >> 3, k = ch & 7;
+    float acc = 0.f;
+    for (int r = 0; r < rows_per_block; ++r) acc += sm[r * cv + vx][k];
+    partial[(size_t)blockIdx.x * C + ch] = acc;
+  }
+}
+__global__ void bias_bwd_finalize_kernel(const double* __restrict__ slab, int slabs, int C, float* __restrict__ dbias) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int b = 0; b < slabs; ++b) s += slab[(size_t)b * C + c];
+  dbias[c] += (float)s;
+}
+
+// dsmall[n,h,w,c] = sum of the 2x2 block of dbig (gradient of nearest x2 upsampling), bf16 in/out
+__global__ void sumpool2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C) {
+  const int Ho = H >> 1, Wo = W >> 1, cv = C >> 3;
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) << 3;
+    long long p = i / cv;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    const long long base = ((long long)n * H + 2 * ho) * W + 2 * wo;
+    V8 a = ld8(x + base * C + c), b = ld8(x + (base + 1) * C + c);
+    V8 d = ld8(x + (base + W) * C + c), e = ld8(x + (base + W + 1) * C + c);
+    V8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = (a.v[k] + b.v[k]) + (d.v[k] + e.v[k]);
+    st8(y + (((long long)n * Ho + ho) * Wo + wo) * C + c, o);
+  }
+}
+
+// z (N,2Ho,2Wo,C) = dy scattered to the even positions, zeros elsewhere (input of the stride-2 data gradient)
+__global__ void zero_stuff2_kernel(const bf16* __restrict__ dy, bf16* __restrict__ z, int N, int Ho, int Wo, int H,
+                                   int W, int C) {
+  const int cv = C >> 3;
+  const long long total = (long long)N * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) << 3;
+    long long p = i / cv;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H);
+    const int n = (int)(p / H);
+    V8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
+    if (!(h & 1) && !(w & 1) && (h >> 1) < Ho && (w >> 1) < Wo)
+      o = ld8(dy + (((long long)n * Ho + (h >> 1)) * Wo + (w >> 1)) * C + c);
+    st8(z + i * 8, o);
   }
 }
 
@@ -290,12 +413,16 @@ __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restri
 using namespace c3d;
 #define C3D_REQ(cond, msg) do { if (!(cond)) return set_error(C3D_EINVAL, msg); } while (0)
 
+extern "C" size_t c3d_bn_scratch_bytes(int32_t C) { return (size_t)kSlabs * 2 * (size_t)(C > 0 ? C : 0) * sizeof(double); }
 extern "C" int32_t c3d_bn_finalize(const float* partial, int32_t rows, int32_t C, double count, float eps,
                                    float momentum, float* running_mean, float* running_var, float* mean_out,
-                                   float* rstd_out, void* stream) {
-  C3D_REQ(partial && mean_out && rstd_out && rows > 0 && C > 0, "bn_finalize: bad args");
-  bn_finalize_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(partial, rows, C, count, eps, momentum,
-                                                                     running_mean, running_var, mean_out, rstd_out);
+                                   float* rstd_out, void* scratch, void* stream) {
+  C3D_REQ(partial && mean_out && rstd_out && scratch && rows > 0 && C > 0, "bn_finalize: bad args");
+  int slabs;
+  launch_colsum(partial, rows, 2 * C, (double*)scratch, &slabs, (cudaStream_t)stream);
+  bn_finalize_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>((const double*)scratch, slabs, C, count, eps,
+                                                                     momentum, running_mean, running_var, mean_out,
+                                                                     rstd_out);
   return check_launch("bn_finalize");
 }
 extern "C" int32_t c3d_bn_apply(const void* y, const float* mean, const float* rstd, const float* gamma,
@@ -320,8 +447,10 @@ extern "C" int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, 
                               const float* gamma, int32_t relu, int32_t frozen_stats, float* partial /*[blocks][2][C]*/,
                               float* coef /*[3][C]*/,
                               float* dgamma, float* dbeta, void* dy, void* dres, int64_t P, int32_t C,
-                              int64_t dout_stride, int64_t out_stride, int64_t dres_stride, void* stream) {
-  C3D_REQ(dout && y && mean && rstd && gamma && partial && coef && dy && C % 8 == 0 && C <= 2048, "bn_bwd: bad args");
+                              int64_t dout_stride, int64_t out_stride, int64_t dres_stride, void* scratch,
+                              void* stream) {
+  C3D_REQ(dout && y && mean && rstd && gamma && partial && coef && dy && scratch && C % 8 == 0 && C <= 2048,
+          "bn_bwd: bad args");
   C3D_REQ(!relu || out, "bn_bwd: relu needs the forward output");
   if (P == 0) return C3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -332,8 +461,10 @@ extern "C" int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, 
                                                        relu, partial, P, C, ds, os);
   else
     return set_error(C3D_EINVAL, "bn_bwd: C too large");
-  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(partial, blocks, C, (double)P, gamma, rstd, coef, dgamma, dbeta,
-                                                       frozen_stats);
+  int slabs;
+  launch_colsum(partial, blocks, 2 * C, (double*)scratch, &slabs, st);
+  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>((const double*)scratch, slabs, C, (double)P, gamma, rstd, coef,
+                                                       dgamma, dbeta, frozen_stats);
   bn_bwd_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)y,
                                                                    mean, rstd, coef, relu, (bf16*)dy, (bf16*)dres, P, C,
                                                                    ds, os, dres_stride ? dres_stride : C);
@@ -379,4 +510,41 @@ extern "C" int32_t c3d_sgd_momentum(float* p, const float* g, float* mom, int64_
   sgd_momentum_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, mom, n, lr, momentum, weight_decay,
                                                                            grad_scale, skip_flag);
   return check_launch("sgd");
+}
+
+extern "C" int32_t c3d_bias_act_bwd(const void* dout, const void* out, int32_t relu, int32_t dout_fp32, void* dz,
+                                    float* partial /*[c3d_bn_bwd_blocks(P,C)][C]*/, float* dbias, int64_t P, int32_t C,
+                                    void* scratch, void* stream) {
+  C3D_REQ(dout && dz && partial && scratch && C % 8 == 0 && C <= 2048, "bias_act_bwd: bad args");
+  C3D_REQ(!relu || out, "bias_act_bwd: relu needs the forward output");
+  if (P == 0) return C3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = c3d_bn_bwd_blocks(P, C);
+  if (dout_fp32)
+    bias_act_bwd_kernel<256, float><<<blocks, 256, 0, st>>>((const float*)dout, (const float*)out, relu, (bf16*)dz,
+                                                           partial, P, C);
+  else
+    bias_act_bwd_kernel<256, bf16><<<blocks, 256, 0, st>>>((const bf16*)dout, (const bf16*)out, relu, (bf16*)dz,
+                                                          partial, P, C);
+  if (dbias) {
+    int slabs;
+    launch_colsum(partial, blocks, C, (double*)scratch, &slabs, st);
+    bias_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>((const double*)scratch, slabs, C, dbias);
+  }
+  return check_launch("bias_act_bwd");
+}
+extern "C" int32_t c3d_sumpool2(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+  C3D_REQ(x && y && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "sumpool2: bad args");
+  long long work = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  if (work == 0) return C3D_OK;
+  sumpool2_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, N, H, W, C);
+  return check_launch("sumpool2");
+}
+extern "C" int32_t c3d_zero_stuff2(const void* dy, void* z, int32_t N, int32_t Ho, int32_t Wo, int32_t H, int32_t W,
+                                   int32_t C, void* stream) {
+  C3D_REQ(dy && z && C % 8 == 0, "zero_stuff2: bad args");
+  long long work = (long long)N * H * W * (C / 8);
+  if (work == 0) return C3D_OK;
+  zero_stuff2_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (bf16*)z, N, Ho, Wo, H, W, C);
+  return check_launch("zero_stuff2");
 }

@@ -21,10 +21,10 @@ def _bind():
     if _bound:
         return L
     sig = {
-        "c3d_bn_finalize": [vp, i32, i32, f64, f32, f32, vp, vp, vp, vp, vp],
+        "c3d_bn_finalize": [vp, i32, i32, f64, f32, f32, vp, vp, vp, vp, vp, vp],
         "c3d_bn_apply": [vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i64, i64, vp],
         "c3d_bn_bwd_blocks": [i64, i32],
-        "c3d_bn_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, vp],
+        "c3d_bn_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, vp, vp],
         "c3d_maxpool2_fwd": [vp, vp, i32, i32, i32, i32, i64, i64, vp],
         "c3d_maxpool2_bwd": [vp, vp, vp, i32, i32, i32, i32, i64, i64, vp],
         "c3d_preprocess_image": [vp, i32, i32, vp, i32, i32, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), vp],
@@ -33,6 +33,11 @@ def _bind():
         "c3d_roi_align_fwd": [ctypes.POINTER(RoiLevels), vp, i32, i32, i32, i32, vp, vp],
         "c3d_roi_align_bwd": [ctypes.POINTER(RoiLevels), vp, i32, i32, i32, i32, vp, vp],
     }
+    sig["c3d_bias_act_bwd"] = [vp, vp, i32, i32, vp, vp, vp, i64, i32, vp, vp]
+    sig["c3d_sumpool2"] = [vp, vp, i32, i32, i32, i32, vp]
+    sig["c3d_zero_stuff2"] = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    L.c3d_bn_scratch_bytes.restype = ctypes.c_size_t
+    L.c3d_bn_scratch_bytes.argtypes = [i32]
     L.c3d_nms_workspace_bytes.restype = ctypes.c_size_t
     L.c3d_nms_workspace_bytes.argtypes = [i32, i32]
     sig["c3d_nms_batched"] = [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, ctypes.c_size_t, vp]
@@ -57,8 +62,9 @@ def bn_finalize(stats, count, eps, momentum, running_mean, running_var):
     rows, _, C = stats.shape
     mean = torch.empty(C, device=stats.device, dtype=torch.float32)
     rstd = torch.empty(C, device=stats.device, dtype=torch.float32)
+    scratch = torch.empty(128 * 2 * C, device=stats.device, dtype=torch.float64)
     _lib.check(L.c3d_bn_finalize(_p(stats), rows, C, float(count), eps, momentum, _p(running_mean), _p(running_var),
-                                 _p(mean), _p(rstd), _st()))
+                                 _p(mean), _p(rstd), _p(scratch), _st()), launches=2)
     return mean, rstd
 
 
@@ -83,8 +89,9 @@ def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres, froz
     coef = torch.empty((3, C), device=y.device, dtype=torch.float32)
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
+    scratch = torch.empty(128 * 2 * C, device=y.device, dtype=torch.float64)
     _lib.check(L.c3d_bn_bwd(_p(dout), _p(out), _p(y), _p(mean), _p(rstd), _p(gamma), int(relu), int(frozen), _p(partial), _p(coef),
-                            _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, 0, 0, 0, _st()), launches=3)
+                            _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, 0, 0, 0, _p(scratch), _st()), launches=4)
     return dy, dres
 
 
@@ -183,3 +190,35 @@ def nms_batched(boxes, nvalid, iou_thresh, max_keep, cats=None, maxc=None, trick
     _lib.check(L.c3d_nms_batched(_p(boxes), _p(nvalid), _p(cats), _p(maxc), trick_max_numel, B, n, iou_thresh,
                                  max_keep, _p(keep), _p(cnt), _p(ws), ws.numel(), _st()), launches=2)
     return keep, cnt
+
+
+def bias_act_bwd(dout, out, relu, want_dbias):
+    """dz (bf16) = dout * (out > 0 if relu); dbias (fp32 [C]) = sum over pixels (or None)."""
+    L = _bind()
+    C = dout.shape[-1]
+    P = dout.numel() // C
+    dout = dout.contiguous()
+    blocks = L.c3d_bn_bwd_blocks(P, C)
+    partial = torch.empty((blocks, C), device=dout.device, dtype=torch.float32)
+    scratch = torch.empty(128 * 2 * C, device=dout.device, dtype=torch.float64)
+    dz = torch.empty(dout.shape, device=dout.device, dtype=torch.bfloat16)
+    dbias = torch.zeros(C, device=dout.device, dtype=torch.float32) if want_dbias else None
+    _lib.check(L.c3d_bias_act_bwd(_p(dout), _p(out), int(relu), int(dout.dtype == torch.float32), _p(dz), _p(partial),
+                                  _p(dbias), P, C, _p(scratch), _st()), launches=3 if want_dbias else 1)
+    return dz, dbias
+
+
+def sumpool2(x):
+    L = _bind()
+    N, H, W, C = x.shape
+    y = torch.empty((N, H // 2, W // 2, C), device=x.device, dtype=x.dtype)
+    _lib.check(L.c3d_sumpool2(_p(x), _p(y), N, H, W, C, _st()))
+    return y
+
+
+def zero_stuff2(dy, H, W):
+    L = _bind()
+    N, Ho, Wo, C = dy.shape
+    z = torch.empty((N, H, W, C), device=dy.device, dtype=dy.dtype)
+    _lib.check(L.c3d_zero_stuff2(_p(dy), _p(z), N, Ho, Wo, H, W, C, _st()))
+    return z

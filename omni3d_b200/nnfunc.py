@@ -51,10 +51,8 @@ def _dgrad(dy, w, stride, pad, in_hw):
     if stride == 1:
         return K.conv2d_fwd(dy, wp, stride=1, pad=KH - 1 - pad)
     assert stride == 2
-    N, Ho, Wo, C = dy.shape
     H, W = in_hw
-    z = torch.zeros((N, H, W, C), device=dy.device, dtype=dy.dtype)
-    z[:, (0 if KH == 1 else 0):2 * Ho:2, 0:2 * Wo:2, :] = dy
+    z = Kx.zero_stuff2(dy, H, W)
     if KH == 1:                      # 1x1 stride 2: pure scatter + 1x1 conv
         return K.conv2d_fwd(z, wp, stride=1, pad=0)
     return K.conv2d_fwd(z, wp, stride=1, pad=KH - 1 - pad)
@@ -117,16 +115,8 @@ class ConvBias(torch.autograd.Function):
     def backward(ctx, dout):
         x, w, out = ctx.saved_tensors
         stride, pad, relu, has_add, has_bias = ctx.cfg
-        dz = dout
-        if relu:
-            dz = dz * (out > 0)
-        dzf = dz.float() if dz.dtype != torch.float32 else dz
-        dbias = dzf.sum((0, 1, 2)) if has_bias else None
-        dzb = dz.to(torch.bfloat16).contiguous()
-        dadd = None
-        if has_add and ctx.needs_input_grad[3]:
-            N, H, W, C = dzb.shape
-            dadd = dzf.view(N, H // 2, 2, W // 2, 2, C).sum((2, 4)).to(torch.bfloat16)
+        dzb, dbias = Kx.bias_act_bwd(dout, out, relu, has_bias)
+        dadd = Kx.sumpool2(dzb) if has_add and ctx.needs_input_grad[3] else None
         dx = _dgrad(dzb, w, stride, pad, x.shape[1:3]) if ctx.needs_input_grad[0] else None
         dw = _wgrad_to_master(x, dzb, w, stride, pad) if ctx.needs_input_grad[1] else None
         return dx, dw, dbias, dadd, None, None, None, None
