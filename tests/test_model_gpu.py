@@ -26,6 +26,12 @@ def pair():
     return prod, orc
 
 
+def _sync_state(prod, orc):
+    """start every test from the oracle's exact parameters AND BatchNorm running statistics (earlier
+    train-mode tests moved each model's running stats along its own fp32 / bf16 trajectory)."""
+    prod.load_state_dict(orc.state_dict())
+
+
 def _freeze_bn(m, frozen=True):
     """cubercnn/solver/build.py:71-76 freeze_bn: BatchNorm layers use their running statistics."""
     m.train()
@@ -44,6 +50,7 @@ def test_backbone_fpn_features_frozen_bn(pair):
     prod, orc = pair
     from oracle import model_io
     items = synth.make_batch(2, H, W, with_gt=False, seed=7)
+    _sync_state(prod, orc)
     _freeze_bn(prod); _freeze_bn(orc)
     with torch.no_grad():
         x, _ = prod.preprocess_image(items)
@@ -119,6 +126,7 @@ def test_train_losses_and_grads_frozen_bn(pair):
     prod, orc = pair
     from oracle_capture import run_oracle_train, to_injection
     items = synth.make_batch(2, H, W, num_gt=4, seed=2)
+    _sync_state(prod, orc)
     _freeze_bn(orc)
     orc_train = orc.train
     orc.train = lambda *a, **k: orc            # keep BN frozen inside run_oracle_train
