@@ -29,6 +29,9 @@ def pair():
 def _sync_state(prod, orc):
     """start every test from the oracle's exact parameters AND BatchNorm running statistics (earlier
     train-mode tests moved each model's running stats along its own fp32 / bf16 trajectory)."""
+    for m in orc.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.reset_running_stats()
     prod.load_state_dict(orc.state_dict())
 
 
