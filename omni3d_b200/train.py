@@ -111,7 +111,8 @@ class FlatSGDTrainer:
         # device-side controller state: [recent_loss, iters_success, iters_explode, initialised]
         self.state = torch.zeros(4, device=dev)
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.status_host = torch.zeros(len(LOSS_KEYS) + 4, pin_memory=True)
+        self.on_cuda = dev.type == "cuda"
+        self.status_host = torch.zeros(len(LOSS_KEYS) + 4, pin_memory=self.on_cuda)
         self.status_event = None
         self.iteration = 0
         self.stabilize = cfg.MODEL.STABILIZE > 0
@@ -154,8 +155,11 @@ class FlatSGDTrainer:
         self.state = torch.stack([new_recent, st[1] + (1 - skipped), st[2] + skipped, torch.ones_like(st[3])])
         # async status readback (previous step's values are inspected by `status()` without blocking the GPU)
         self.status_host.copy_(torch.cat([vec, self.state]), non_blocking=True)
-        self.status_event = torch.cuda.Event()
-        self.status_event.record()
+        if self.on_cuda:
+            self.status_event = torch.cuda.Event()
+            self.status_event.record()
+        else:
+            self.status_event = True
         self.iteration += 1
         return loss_dict
 
@@ -163,10 +167,11 @@ class FlatSGDTrainer:
         """{'losses': {...}, 'total_loss', 'recent_loss', 'iterations_success', 'iterations_explode', 'retry'}."""
         if self.status_event is None:
             return None
-        if wait:
-            self.status_event.synchronize()
-        elif not self.status_event.query():
-            return None
+        if self.on_cuda:
+            if wait:
+                self.status_event.synchronize()
+            elif not self.status_event.query():
+                return None
         v = self.status_host.tolist()
         n = len(LOSS_KEYS)
         ok, bad = v[n + 1], v[n + 2]
