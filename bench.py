@@ -266,14 +266,17 @@ def run_ours(args):
         trainer.step(host[i % 2])
     ms_e2e, _ = timed(host, args.steps, read_loss=True)
     status = trainer.status()
+    peak_tf, peak_hbm, peak_src = peaks()
+    # the instrumented step runs on EVERY rank (it contains the same collectives as any other step)
+    roof = conv_roofline(trainer, resident[0], peak_tf, peak_src)
+    if world > 1:
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peak_tf, peak_hbm, peak_src = peaks()
     ips = B * world * args.steps / (ms * 1e-3)
     ips_e2e = B * world * args.steps / (ms_e2e * 1e-3)
-    roof = conv_roofline(trainer, resident[0], peak_tf, peak_src)
     line = {
         "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
