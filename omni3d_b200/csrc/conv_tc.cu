@@ -16,6 +16,7 @@
 // ReLU / BatchNorm partial statistics -> bf16|fp32 NHWC stores).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "c3d_common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -241,6 +242,203 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM slot loops over (m-tile, n-tile) work items; the fp32 accumulator is
+// DOUBLE-BUFFERED in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the TMA/MMA main loop of
+// tile i+1, and barrier init / TMEM allocation are paid once per CTA instead of once per 128-pixel tile.
+template <int BLOCK_N, int BLOCK_K, int STAGES>
+__global__ void __launch_bounds__(192)
+conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                          const ConvKParams P, const int tiles_m, const int n_tiles) {
+  using S = ConvSmem<BLOCK_N, BLOCK_K, STAGES>;
+  constexpr int kSwizzle = BLOCK_K * 2;
+  constexpr uint32_t kAccCols = BLOCK_N < 16 ? 16 : BLOCK_N;
+  constexpr uint32_t kTmemCols = (2 * kAccCols) < 32 ? 32 : (2 * kAccCols);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;          // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;              // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* red = reinterpret_cast<float*>(smem + S::kBarOffset + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = P.KH * P.KW * P.kc_blocks;
+  const int total = tiles_m * n_tiles;
+
+  if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&tmap_x); ptx::prefetch_tensormap(&tmap_w); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<kTmemCols>(tmem_ptr);
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      const uint32_t a_bytes = (uint32_t)(P.TH * P.TW * BLOCK_K * 2);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int tile_m = tile / n_tiles, n0 = (tile - tile_m * n_tiles) * BLOCK_N;
+        const int tw_i = tile_m % P.tiles_w, th_i = (tile_m / P.tiles_w) % P.tiles_h;
+        const int img = tile_m / (P.tiles_w * P.tiles_h);
+        const int hi0 = th_i * P.TH * P.stride - P.pad, wi0 = tw_i * P.TW * P.stride - P.pad;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / P.kc_blocks, kc = kb - tap * P.kc_blocks;
+          const int kh = tap / P.KW, kw = tap - kh * P.KW;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kTileBytes;
+          ptx::mbar_expect_tx(&full_bar[stage], a_bytes + (uint32_t)S::kBBytes);
+          ptx::tma_load_4d(sa, &tmap_x, &full_bar[stage], kc * BLOCK_K, wi0 + kw, hi0 + kh, img);
+          ptx::tma_load_2d(sa + S::kABytes, &tmap_w, &full_bar[stage], tap * P.Cin + kc * BLOCK_K, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, kAccCols, 0, 0);
+      constexpr uint32_t lt = ptx::swizzle_layout_type(kSwizzle);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue drained this accumulator
+        ptx::tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)acc * kAccCols;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tcgen05_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * S::kTileBytes);
+          const uint64_t da = ptx::make_smem_desc(sa, 16, 8 * kSwizzle, lt);
+          const uint64_t db = ptx::make_smem_desc(sa + S::kABytes, 16, 8 * kSwizzle, lt);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            ptx::umma_bf16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int tile_m = tile / n_tiles, n0 = (tile - tile_m * n_tiles) * BLOCK_N;
+      const int tw_i = tile_m % P.tiles_w, th_i = (tile_m / P.tiles_w) % P.tiles_h;
+      const int img = tile_m / (P.tiles_w * P.tiles_h);
+      const int r = q * 32 + lane;
+      const int ty = r / P.TW, tx = r - ty * P.TW;
+      const int ho = th_i * P.TH + ty, wo = tw_i * P.TW + tx;
+      const bool valid = (r < P.TH * P.TW) && (ho < P.Ho) && (wo < P.Wo);
+      const long long pix = ((long long)img * P.Ho + ho) * P.Wo + wo;
+      long long apix = 0;
+      if (P.add_mode == 1) apix = pix;
+      else if (P.add_mode == 2) apix = ((long long)img * (P.Ho >> 1) + (ho >> 1)) * (P.Wo >> 1) + (wo >> 1);
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccCols;
+      constexpr int kChunks = (BLOCK_N + 15) / 16;
+#pragma unroll 1
+      for (int ch = 0; ch < kChunks; ++ch) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x32b_x16(tacc + (uint32_t)(ch * 16), v);
+        ptx::tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        const int c0 = n0 + ch * 16;
+        if (P.stats) {
+          float s[16], s2[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { float x = valid ? f[i] : 0.f; s[i] = x; s2[i] = x * x; }
+#pragma unroll
+          for (int step = 0; step < 4; ++step) {
+            const int half = 8 >> step;
+            const int mask = 1 << step;
+            const bool upper = (lane & mask) != 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i < half) {
+                float send = upper ? s[i] : s[i + half];
+                float keep = upper ? s[i + half] : s[i];
+                float send2 = upper ? s2[i] : s2[i + half];
+                float keep2 = upper ? s2[i + half] : s2[i];
+                s[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+                s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, mask);
+              }
+            }
+          }
+          s[0] += __shfl_xor_sync(0xffffffffu, s[0], 16);
+          s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 16);
+          const int cidx = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
+          if (lane < 16) { red[(q * 2 + 0) * 16 + cidx] = s[0]; red[(q * 2 + 1) * 16 + cidx] = s2[0]; }
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+          if (q == 0 && lane < 16 && (c0 + lane) < P.Cout) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { a += red[(w * 2 + 0) * 16 + lane]; b += red[(w * 2 + 1) * 16 + lane]; }
+            float* dst = P.stats + (size_t)tile_m * 2 * P.Cout;
+            dst[c0 + lane] = a;
+            dst[P.Cout + c0 + lane] = b;
+          }
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        }
+        if (valid && c0 < P.Cout) {
+          if (P.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += __ldg(P.bias + c0 + i);
+          }
+          if (P.add_mode) {
+            const uint4* ap = reinterpret_cast<const uint4*>(P.addend + apix * P.add_pix_stride + c0);
+            uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+            const bf16* h0 = reinterpret_cast<const bf16*>(&a0);
+            const bf16* h1 = reinterpret_cast<const bf16*>(&a1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { f[i] += __bfloat162float(h0[i]); f[8 + i] += __bfloat162float(h1[i]); }
+          }
+          if (P.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (P.out_fp32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix * P.out_pix_stride + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          } else {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + pix * P.out_pix_stride + c0);
+            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      // this warp is done reading the accumulator: hand it back to the MMA issuer
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
 // ---- host side --------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -450,6 +648,24 @@ static void pick_tile_k(int Ho, int Wo, int stride, int* RH, int* RW) {
   *RH = bth; *RW = btw;
 }
 
+template <int BN, int BK, int ST>
+static int32_t launch_conv_p(const CUtensorMap& mx, const CUtensorMap& mw, const ConvKParams& P, int tiles_m, int n_tiles,
+                             int ctas_per_sm, cudaStream_t st) {
+  using S = ConvSmem<BN, BK, ST>;
+  auto kern = conv_tc_persistent_kernel<BN, BK, ST>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) return set_error(C3D_ECUDA, "conv smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  long long total = (long long)tiles_m * n_tiles;
+  long long grid = (long long)kNumSMs * ctas_per_sm;
+  if (grid > total) grid = total;
+  kern<<<(unsigned)grid, 192, S::kTotal, st>>>(mx, mw, P, tiles_m, n_tiles);
+  return check_launch("conv_tc_persistent_kernel");
+}
+
 }  // namespace c3d
 
 using namespace c3d;
@@ -474,8 +690,11 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   if (Cout % 16 != 0 || Cout <= 0) return set_error(C3D_EINVAL, "conv2d: Cout=%d must be a multiple of 16", Cout);
   if (d->stride < 1 || d->stride > 2) return set_error(C3D_EINVAL, "conv2d: stride %d unsupported", d->stride);
   const int BK = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
+  static const bool non_persistent = getenv("C3D_CONV_NONPERSISTENT") != nullptr;
+  static const bool allow_n256 = getenv("C3D_CONV_NO_N256") == nullptr;
   int BN = 128;
   if (Cout % 128 != 0) BN = (Cout % 64 == 0) ? 64 : (Cout % 32 == 0 ? 32 : 16);
+  if (!non_persistent && allow_n256 && BK == 64 && Cout % 256 == 0) BN = 256;
   const int Ho = (d->H + 2 * d->pad - d->KH) / d->stride + 1;
   const int Wo = (d->W + 2 * d->pad - d->KW) / d->stride + 1;
   if (d->add_mode == 2 && ((Ho & 1) || (Wo & 1))) return set_error(C3D_EINVAL, "conv2d: up2 addend needs even output");
@@ -519,6 +738,25 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   }
   dim3 grid((unsigned)(d->N * P.tiles_h * P.tiles_w), (unsigned)(Cout / BN));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!non_persistent) {
+    const int tiles_m = d->N * P.tiles_h * P.tiles_w, n_tiles = Cout / BN;
+#define C3D_CONV_P(bn, bk, stg, cps) \
+    if (BN == bn && BK == bk) return launch_conv_p<bn, bk, stg>(mx, mw, P, tiles_m, n_tiles, cps, st);
+    C3D_CONV_P(256, 64, 4, 1)
+    C3D_CONV_P(128, 64, 6, 1)
+    C3D_CONV_P(64, 64, 8, 1)
+    C3D_CONV_P(32, 64, 8, 1)
+    C3D_CONV_P(16, 64, 8, 1)
+    C3D_CONV_P(128, 32, 8, 1)
+    C3D_CONV_P(64, 32, 8, 2)
+    C3D_CONV_P(32, 32, 8, 2)
+    C3D_CONV_P(16, 32, 8, 2)
+    C3D_CONV_P(128, 16, 8, 2)
+    C3D_CONV_P(64, 16, 8, 2)
+    C3D_CONV_P(32, 16, 8, 4)
+    C3D_CONV_P(16, 16, 8, 4)
+#undef C3D_CONV_P
+  }
 #define C3D_CONV_CASE(bn, bk, stg) \
   if (BN == bn && BK == bk) return launch_conv<bn, bk, stg>(mx, mw, P, grid, st);
   C3D_CONV_CASE(128, 64, 3)
