@@ -90,6 +90,14 @@ int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const void* w, con
  * forward input x (N,H,W,Cin) and the output gradient dy (N,Ho,Wo,Cout), both bf16 NHWC.
  * Split-K over pixels with fp32 atomics: the caller zeroes (or pre-loads) dw. */
 int32_t c3d_conv2d_wgrad(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);
+/* same, oihw != 0: dw is the fp32 master-layout gradient [Cout][Cin][KH][KW] (accumulate straight into the
+ * optimizer's gradient arena, no layout conversion pass) */
+int32_t c3d_conv2d_wgrad_ex(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, int32_t oihw,
+                            void* stream);
+/* fp32 OIHW master weight -> bf16 (Cout,KH,KW,Cin) forward pack and/or bf16 (Cin,KH,KW,Cout) 180-degree-rotated
+ * data-gradient pack (either output may be NULL) */
+int32_t c3d_pack_conv_weight(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t KH, int32_t KW, void* fwd_ohwi,
+                             void* dgrad_ihwo, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * HBM-bound NHWC bf16 kernels around the convolutions.

@@ -34,6 +34,10 @@ def _bind():
         L.c3d_conv2d_fwd.argtypes = [P, vp, vp, vp, vp, vp, vp, vp]
         L.c3d_conv2d_wgrad.restype = i32
         L.c3d_conv2d_wgrad.argtypes = [P, vp, vp, vp, vp]
+        L.c3d_conv2d_wgrad_ex.restype = i32
+        L.c3d_conv2d_wgrad_ex.argtypes = [P, vp, vp, vp, i32, vp]
+        L.c3d_pack_conv_weight.restype = i32
+        L.c3d_pack_conv_weight.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
         _bound = True
     return L
 
@@ -88,14 +92,25 @@ def conv2d_fwd(x, w, bias=None, stride=1, pad=0, relu=False, addend=None, up2=Fa
     return (out, stats) if want_stats else out
 
 
-def conv2d_wgrad(x, dy, KH, KW, stride=1, pad=0, dw=None):
-    """dW (Cout,KH,KW,Cin) fp32 (+)= wgrad(x (N,H,W,Cin) bf16, dy (N,Ho,Wo,Cout) bf16)."""
+def pack_conv_weight(w, want_fwd=True, want_dgrad=True):
+    """fp32 (Cout,Cin,KH,KW) -> bf16 (Cout,KH,KW,Cin) and bf16 (Cin,KH,KW,Cout) rotated, in ONE launch."""
+    L = _bind()
+    Cout, Cin, KH, KW = w.shape
+    w = w.detach().contiguous()
+    f = torch.empty((Cout, KH, KW, Cin), device=w.device, dtype=torch.bfloat16) if want_fwd else None
+    g = torch.empty((Cin, KH, KW, Cout), device=w.device, dtype=torch.bfloat16) if want_dgrad else None
+    _lib.check(L.c3d_pack_conv_weight(_ptr(w), Cout, Cin, KH, KW, _ptr(f), _ptr(g), _stream()))
+    return f, g
+
+
+def conv2d_wgrad(x, dy, KH, KW, stride=1, pad=0, dw=None, oihw=False):
+    """dW (Cout,KH,KW,Cin) [or (Cout,Cin,KH,KW) when oihw] fp32 (+)= wgrad(x (N,H,W,Cin) bf16, dy bf16)."""
     L = _bind()
     N, H, W, Cin = x.shape
     Cout = dy.shape[3]
     assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
     if dw is None:
-        dw = torch.zeros((Cout, KH, KW, Cin), device=x.device, dtype=torch.float32)
+        dw = torch.zeros((Cout, Cin, KH, KW) if oihw else (Cout, KH, KW, Cin), device=x.device, dtype=torch.float32)
     d = ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, 0, 0, 0, 0, 0, 0)
-    _lib.check(L.c3d_conv2d_wgrad(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _stream()))
+    _lib.check(L.c3d_conv2d_wgrad_ex(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), int(oihw), _stream()))
     return dw

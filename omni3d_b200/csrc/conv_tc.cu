@@ -504,7 +504,8 @@ struct WgradKParams {
   int num_tiles, tiles_per_split;
   int cw, nci, boxes_per_cta, total_boxes;   // B boxes: width cw channels, nci = Cin / cw per tap
   int ca, a_chunks_max;                      // A boxes: width ca channels
-  float* dw;                                 // [Cout][KH][KW][Cin] fp32, accumulated with atomics
+  float* dw;                                 // fp32, accumulated with atomics
+  int oihw;                                  // 0: dw is [Cout][KH][KW][Cin]; 1: [Cout][Cin][KH][KW] (master layout)
 };
 
 template <int STAGES>
@@ -616,10 +617,16 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
         const int box = box0 + n / P.cw;
         const int tap = box / P.nci, ci = (box - tap * P.nci) * P.cw + (n % P.cw);
         if (co < P.Cout && ci < P.Cin) {
-          float* dst = P.dw + ((size_t)co * taps + tap) * P.Cin + ci;
           const int lim = min(16, P.Cin - ci);
+          if (P.oihw) {
+            float* dst = P.dw + ((size_t)co * P.Cin + ci) * taps + tap;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) if (i < lim) atomicAdd(dst + i, __uint_as_float(v[i]));
+            for (int i = 0; i < 16; ++i) if (i < lim) atomicAdd(dst + (size_t)i * taps, __uint_as_float(v[i]));
+          } else {
+            float* dst = P.dw + ((size_t)co * taps + tap) * P.Cin + ci;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (i < lim) atomicAdd(dst + i, __uint_as_float(v[i]));
+          }
         }
       }
     }
@@ -738,7 +745,9 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   }
   dim3 grid((unsigned)(d->N * P.tiles_h * P.tiles_w), (unsigned)(Cout / BN));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!non_persistent) {
+  // persistent + double-buffered TMEM pays off for the tensor-bound shapes; the tiny-K / memory-bound ones
+  // (Cin < 64, or 1x1 with few output tiles per SM) run better as many short CTAs (measured, profiles/)
+  if (!non_persistent && BK == 64 && BN >= 64 && !(d->KH == 1 && Cin <= 64)) {
     const int tiles_m = d->N * P.tiles_h * P.tiles_w, n_tiles = Cout / BN;
 #define C3D_CONV_P(bn, bk, stg, cps) \
     if (BN == bn && BK == bk) return launch_conv_p<bn, bk, stg>(mx, mw, P, tiles_m, n_tiles, cps, st);
@@ -775,7 +784,13 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   return set_error(C3D_EINVAL, "conv2d: no kernel for BN=%d BK=%d", BN, BK);
 }
 
+extern "C" int32_t c3d_conv2d_wgrad_ex(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, int32_t oihw,
+                                       void* stream);
 extern "C" int32_t c3d_conv2d_wgrad(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
+  return c3d_conv2d_wgrad_ex(d, x, dy, dw, 0, stream);
+}
+extern "C" int32_t c3d_conv2d_wgrad_ex(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, int32_t oihw,
+                                       void* stream) {
   if (!d || !x || !dy || !dw) return set_error(C3D_EINVAL, "wgrad: null pointer");
   const int Cin = d->Cin, Cout = d->Cout;
   if (Cin % 16 != 0 || Cout % 16 != 0) return set_error(C3D_EINVAL, "wgrad: channels must be multiples of 16");
@@ -806,6 +821,7 @@ extern "C" int32_t c3d_conv2d_wgrad(const c3d_conv_desc* d, const void* x, const
   P.tiles_per_split = (P.num_tiles + splits - 1) / splits;
   splits = (P.num_tiles + P.tiles_per_split - 1) / P.tiles_per_split;
   P.dw = dw;
+  P.oihw = oihw;
   const long long xps = d->x_pix_stride ? d->x_pix_stride : Cin;
   const long long yps = d->y_pix_stride ? d->y_pix_stride : Cout;
   CUtensorMap mdy, mx;

@@ -360,6 +360,22 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
   }
 }
 
+// ---- weight re-pack: fp32 OIHW master -> bf16 OHWI (forward) and bf16 rotated/transposed (data gradient) ----
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW,
+                                        bf16* __restrict__ fwd, bf16* __restrict__ dgrad) {
+  const long long total = (long long)Cout * Cin * KH * KW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kw = (int)(i % KW);
+    long long t = i / KW;
+    const int kh = (int)(t % KH); t /= KH;
+    const int ci = (int)(t % Cin);
+    const int co = (int)(t / Cin);
+    const bf16 v = __float2bfloat16(w[i]);
+    if (fwd) fwd[(((long long)co * KH + kh) * KW + kw) * Cin + ci] = v;
+    if (dgrad) dgrad[(((long long)ci * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)) * Cout + co] = v;
+  }
+}
+
 // ---- image normalisation: (3,H,W) fp32 BGR -> (Hp,Wp,Cp) bf16 NHWC slot, zero padded --------------
 __global__ void preprocess_kernel(const float* __restrict__ img, int H, int W, bf16* __restrict__ out, int Hp,
                                   int Wp, int Cp, float m0, float m1, float m2, float s0, float s1, float s2) {
@@ -547,4 +563,14 @@ extern "C" int32_t c3d_zero_stuff2(const void* dy, void* z, int32_t N, int32_t H
   if (work == 0) return C3D_OK;
   zero_stuff2_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (bf16*)z, N, Ho, Wo, H, W, C);
   return check_launch("zero_stuff2");
+}
+
+extern "C" int32_t c3d_pack_conv_weight(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t KH, int32_t KW,
+                                        void* fwd_ohwi, void* dgrad_ihwo, void* stream) {
+  C3D_REQ(w_oihw && (fwd_ohwi || dgrad_ihwo), "pack_conv_weight: bad args");
+  long long total = (long long)Cout * Cin * KH * KW;
+  if (total == 0) return C3D_OK;
+  pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, KH, KW,
+                                                                                  (bf16*)fwd_ohwi, (bf16*)dgrad_ihwo);
+  return check_launch("pack_conv_weight");
 }

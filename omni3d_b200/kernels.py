@@ -192,8 +192,8 @@ def nms_batched(boxes, nvalid, iou_thresh, max_keep, cats=None, maxc=None, trick
     return keep, cnt
 
 
-def bias_act_bwd(dout, out, relu, want_dbias):
-    """dz (bf16) = dout * (out > 0 if relu); dbias (fp32 [C]) = sum over pixels (or None)."""
+def bias_act_bwd(dout, out, relu, dbias):
+    """dz (bf16) = dout * (out > 0 if relu); dbias (fp32 [C] or None) += sum over pixels."""
     L = _bind()
     C = dout.shape[-1]
     P = dout.numel() // C
@@ -202,10 +202,9 @@ def bias_act_bwd(dout, out, relu, want_dbias):
     partial = torch.empty((blocks, C), device=dout.device, dtype=torch.float32)
     scratch = torch.empty(128 * 2 * C, device=dout.device, dtype=torch.float64)
     dz = torch.empty(dout.shape, device=dout.device, dtype=torch.bfloat16)
-    dbias = torch.zeros(C, device=dout.device, dtype=torch.float32) if want_dbias else None
     _lib.check(L.c3d_bias_act_bwd(_p(dout), _p(out), int(relu), int(dout.dtype == torch.float32), _p(dz), _p(partial),
-                                  _p(dbias), P, C, _p(scratch), _st()), launches=3 if want_dbias else 1)
-    return dz, dbias
+                                  _p(dbias), P, C, _p(scratch), _st()), launches=3 if dbias is not None else 1)
+    return dz
 
 
 def sumpool2(x):

@@ -24,24 +24,18 @@ def invalidate_packed():
 
 
 def _packed(w, kind):
-    """bf16 kernel-layout copies of an fp32 OIHW master; cached for nn.Parameters only (per storage/version/
-    epoch) — temporaries (padded stem weight, fused RPN predictor weight) are packed on the fly."""
-    cacheable = isinstance(w, torch.nn.Parameter)
-    key = (w.data_ptr(), kind)
-    ver = (w._version, _epoch)
-    hit = _pack_cache.get(key) if cacheable else None
-    if hit is not None and hit[0] == ver and hit[2] == tuple(w.shape):
-        return hit[1]
-    with torch.no_grad():
-        if kind == "fwd":        # (Cout,Cin,KH,KW) -> (Cout,KH,KW,Cin)
-            p = w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
-        elif kind == "dgrad":    # -> (Cin,KH,KW,Cout), taps rotated by 180 degrees
-            p = w.flip(2, 3).permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)
-        else:
-            raise ValueError(kind)
-    if cacheable:
-        _pack_cache[key] = (ver, p, tuple(w.shape))
-    return p
+    """bf16 kernel-layout copies of an fp32 OIHW master — (Cout,KH,KW,Cin) for the forward pass and
+    (Cin,KH,KW,Cout) with the taps rotated by 180 degrees for the data gradient — produced by ONE
+    c3d_pack_conv_weight launch and cached per (storage, version, optimizer epoch)."""
+    key = w.data_ptr()
+    ver = (w._version, _epoch, tuple(w.shape))
+    hit = _pack_cache.get(key)
+    if hit is None or hit[0] != ver:
+        f, g = K.pack_conv_weight(w)
+        hit = (ver, f, g)
+        if isinstance(w, torch.nn.Parameter) or w.is_leaf:
+            _pack_cache[key] = hit
+    return hit[1] if kind == "fwd" else hit[2]
 
 
 def _dgrad(dy, w, stride, pad, in_hw):
@@ -59,8 +53,21 @@ def _dgrad(dy, w, stride, pad, in_hw):
 
 
 def _wgrad_to_master(x, dy, w, stride, pad):
-    dw = K.conv2d_wgrad(x, dy, w.shape[2], w.shape[3], stride, pad)      # (Cout,KH,KW,Cin) fp32
-    return dw.permute(0, 3, 1, 2)
+    """weight gradient in the master (Cout,Cin,KH,KW) layout.  When the parameter already owns a contiguous
+    fp32 .grad (the trainer's flat arena) the kernel accumulates straight into it and autograd gets None."""
+    g = w.grad if w.is_leaf else None
+    if g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == w.shape:
+        K.conv2d_wgrad(x, dy, w.shape[2], w.shape[3], stride, pad, dw=g, oihw=True)
+        return None
+    return K.conv2d_wgrad(x, dy, w.shape[2], w.shape[3], stride, pad, oihw=True)
+
+
+def _grad_slot(p):
+    """(.grad to accumulate into in place, or a fresh zero buffer; True if autograd must be given the buffer)"""
+    g = p.grad if p.is_leaf else None
+    if g is not None and g.dtype == torch.float32 and g.is_contiguous():
+        return g, False
+    return torch.zeros_like(p, dtype=torch.float32), True
 
 
 class ConvBNAct(torch.autograd.Function):
@@ -89,13 +96,14 @@ class ConvBNAct(torch.autograd.Function):
         x, w, gamma, y, mean, rstd, out = ctx.saved_tensors
         stride, pad, relu, training, has_res = ctx.cfg
         dout = dout.contiguous()
-        dgamma = torch.zeros_like(gamma)
-        dbeta = torch.zeros_like(gamma)
+        dgamma, ret_g = _grad_slot(gamma)
+        dbeta, ret_b = _grad_slot(beta)
         dy, dres = Kx.bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, has_res and ctx.needs_input_grad[6],
                               frozen=not training)
         dx = _dgrad(dy, w, stride, pad, x.shape[1:3]) if ctx.needs_input_grad[0] else None
         dw = _wgrad_to_master(x, dy, w, stride, pad) if ctx.needs_input_grad[1] else None
-        return dx, dw, dgamma, dbeta, None, None, dres, None, None, None, None, None, None
+        return (dx, dw, dgamma if ret_g else None, dbeta if ret_b else None, None, None, dres, None, None, None, None,
+                None, None)
 
 
 class ConvBias(torch.autograd.Function):
@@ -107,19 +115,20 @@ class ConvBias(torch.autograd.Function):
         add = addend.contiguous() if addend is not None else None
         out = K.conv2d_fwd(x, _packed(w, "fwd"), bias, stride, pad, relu=relu, addend=add, up2=add is not None,
                            out_fp32=out_fp32)
-        ctx.save_for_backward(x, w, out if relu else None)
+        ctx.save_for_backward(x, w, out if relu else None, bias)
         ctx.cfg = (stride, pad, relu, addend is not None, bias is not None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, w, out = ctx.saved_tensors
+        x, w, out, bias = ctx.saved_tensors
         stride, pad, relu, has_add, has_bias = ctx.cfg
-        dzb, dbias = Kx.bias_act_bwd(dout, out, relu, has_bias)
+        dbias, ret_b = _grad_slot(bias) if has_bias else (None, False)
+        dzb = Kx.bias_act_bwd(dout, out, relu, dbias)
         dadd = Kx.sumpool2(dzb) if has_add and ctx.needs_input_grad[3] else None
         dx = _dgrad(dzb, w, stride, pad, x.shape[1:3]) if ctx.needs_input_grad[0] else None
         dw = _wgrad_to_master(x, dzb, w, stride, pad) if ctx.needs_input_grad[1] else None
-        return dx, dw, dbias, dadd, None, None, None, None
+        return dx, dw, dbias if ret_b else None, dadd, None, None, None, None
 
 
 class MaxPool2(torch.autograd.Function):
