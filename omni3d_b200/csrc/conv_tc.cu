@@ -701,7 +701,10 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   static const bool allow_n256 = getenv("C3D_CONV_NO_N256") == nullptr;
   int BN = 128;
   if (Cout % 128 != 0) BN = (Cout % 64 == 0) ? 64 : (Cout % 32 == 0 ? 32 : 16);
-  if (!non_persistent && allow_n256 && BK == 64 && Cout % 256 == 0) BN = 256;
+  // persistent + double-buffered TMEM pays off for the tensor-bound shapes; the tiny-K / memory-bound ones
+  // (Cin < 64, or 1x1 with Cin <= 64) run better as many short CTAs (measured, profiles/)
+  const bool persistent = !non_persistent && BK == 64 && BN >= 64 && !(d->KH == 1 && Cin <= 64);
+  if (persistent && allow_n256 && Cout % 256 == 0) BN = 256;
   const int Ho = (d->H + 2 * d->pad - d->KH) / d->stride + 1;
   const int Wo = (d->W + 2 * d->pad - d->KW) / d->stride + 1;
   if (d->add_mode == 2 && ((Ho & 1) || (Wo & 1))) return set_error(C3D_EINVAL, "conv2d: up2 addend needs even output");
@@ -745,9 +748,7 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   }
   dim3 grid((unsigned)(d->N * P.tiles_h * P.tiles_w), (unsigned)(Cout / BN));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // persistent + double-buffered TMEM pays off for the tensor-bound shapes; the tiny-K / memory-bound ones
-  // (Cin < 64, or 1x1 with few output tiles per SM) run better as many short CTAs (measured, profiles/)
-  if (!non_persistent && BK == 64 && BN >= 64 && !(d->KH == 1 && Cin <= 64)) {
+  if (persistent) {
     const int tiles_m = d->N * P.tiles_h * P.tiles_w, n_tiles = Cout / BN;
 #define C3D_CONV_P(bn, bk, stg, cps) \
     if (BN == bn && BK == bk) return launch_conv_p<bn, bk, stg>(mx, mw, P, tiles_m, n_tiles, cps, st);

@@ -87,13 +87,13 @@ class ConvBNAct(torch.autograd.Function):
             mean, rstd = running_mean, torch.rsqrt(running_var + eps)
         res = residual.contiguous() if residual is not None else None
         out = Kx.bn_apply(y, mean, rstd, gamma, beta, res, relu)
-        ctx.save_for_backward(x, w, gamma, y, mean, rstd, out)
+        ctx.save_for_backward(x, w, gamma, y, mean, rstd, out, beta)
         ctx.cfg = (stride, pad, relu, training, residual is not None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, w, gamma, y, mean, rstd, out = ctx.saved_tensors
+        x, w, gamma, y, mean, rstd, out, beta = ctx.saved_tensors
         stride, pad, relu, training, has_res = ctx.cfg
         dout = dout.contiguous()
         dgamma, ret_g = _grad_slot(gamma)
