@@ -151,10 +151,10 @@ def conv_roofline(trainer, items, peak_tflops, peak_src):
         rec.append((e0, e1, 2.0 * y.shape[0] * y.shape[1] * y.shape[2] * w.shape[0] * w.shape[1] * w.shape[2] * w.shape[3], "fwd"))
         return out
 
-    def wgrad(x, dy, KH, KW, stride=1, pad=0, dw=None):
+    def wgrad(x, dy, KH, KW, stride=1, pad=0, dw=None, oihw=False):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = o_w(x, dy, KH, KW, stride, pad, dw)
+        out = o_w(x, dy, KH, KW, stride, pad, dw, oihw)
         e1.record()
         rec.append((e0, e1, 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * KH * KW * x.shape[3], "wgrad"))
         return out
