@@ -181,6 +181,19 @@ int32_t c3d_nms_batched(const float* boxes, const int32_t* nvalid, const float* 
                         int32_t max_keep, int32_t* keep_idx, int32_t* keep_cnt, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * CubeHead decode + disentangled 3D corner losses, fused forward / backward (one thread per RoI).
+ * Replaces the ATen micro-kernels of cubercnn/modeling/roi_heads/roi_heads.py:409-525 (decode) and :527-740
+ * (xy / z / dims L1 corner losses, chamfer pose + joint losses, sqrt(2)*exp(-u) weighting), with
+ * math_util.py:116-219,651-679 and pytorch3d rotation_6d_to_matrix inlined.
+ *   raw  fp32 [n][13]: delta x,y | z | dims W,H,L | pose6 | uncertainty   (per-class-gathered head outputs)
+ *   aux  fp32 [n][28]: box x1,y1,x2,y2 | fx,fy,px,py | virtual->real | prior W,H,L | gt u,v,z,W,H,L | gt R (9) | pad
+ *   out  fp32 [n][10]: u, l_dims*sf, l_xy*sf, l_z*sf, l_pose*sf, l_joint*sf, |z-gz|, mean|dims-gt|, mean|xy-gt|, exp(-u)
+ *   dout fp32 [n][6] : upstream gradient of out[:, 0:6];  draw fp32 [n][13]
+ * ------------------------------------------------------------------------------------------ */
+int32_t c3d_cube_loss_fwd(const float* raw, const float* aux, int32_t n, float* out, void* stream);
+int32_t c3d_cube_loss_bwd(const float* raw, const float* aux, const float* dout, int32_t n, float* draw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

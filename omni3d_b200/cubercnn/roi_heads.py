@@ -133,6 +133,7 @@ class ROIHeads3D(nn.Module):
         self.priors_z_scales = nn.Parameter(torch.ones(K, H.CLUSTER_BINS))
         self.generator = None
         self.stats = {}
+        self.fused_cube = True        # c3d_cube_loss_fwd/bwd; False = the batched torch fp32 formulation below
 
     # -- proposal labelling / sampling (roi_heads.py:826-929) -----------------------------------------
     @torch.no_grad()
@@ -255,8 +256,9 @@ class ROIHeads3D(nn.Module):
         c = classes.clamp(0, K - 1)
         pick = lambda lin, m: torch.gather(linear_bf16(h, lin).float().view(n, K, m), 1,
                                            c[:, None, None].expand(-1, 1, m)).squeeze(1)
+        ur = pick(ch.bbox_3D_uncertainty, 1).squeeze(1)
         return dict(deltas=pick(ch.bbox_3D_center_deltas, 2), dims=pick(ch.bbox_3D_dims, 3), pose6=pick(ch.bbox_3D_pose, 6),
-                    z=pick(ch.bbox_3D_center_depth, 1).squeeze(1), uncert=pick(ch.bbox_3D_uncertainty, 1).squeeze(1).clip(0.01))
+                    z=pick(ch.bbox_3D_center_depth, 1).squeeze(1), uncert=ur.clip(0.01), uncert_raw=ur)
 
     def decode(self, raw, boxes, classes, Kb, v2r):
         """roi_heads.py:409-525: 2D centre, dims (exp * prior), egocentric pose, metric depth."""
@@ -267,6 +269,28 @@ class ROIHeads3D(nn.Module):
         dims = torch.exp(raw["dims"].clip(max=5)) * prior
         pose = G.R_from_allocentric(Kb, G.rotation_6d_to_matrix(raw["pose6"]), cx.detach(), cy.detach())
         return cx, cy, dims, pose, raw["z"] * v2r
+
+    def cube_losses_fused(self, raw, boxes, classes, valid, gt3, gtR, Kb, v2r):
+        """same quantities as cube_losses(), computed by the fused sm_100a kernel (c3d_cube_loss_fwd/bwd)."""
+        from ..nnfunc import CubeLossRows
+        w = self.w
+        n = boxes.shape[0]
+        prior = self.priors_dims_per_cat.detach()[0, classes.clamp(0, self.num_classes - 1), 0, :]
+        aux = torch.cat([boxes, Kb[:, 0, 0:1], Kb[:, 1, 1:2], Kb[:, 0, 2:3], Kb[:, 1, 2:3], v2r[:, None], prior, gt3[:, :6],
+                         gtR.reshape(n, 9), boxes.new_zeros(n, 1)], 1)
+        raw13 = torch.cat([raw["deltas"], raw["z"][:, None], raw["dims"], raw["pose6"], raw["uncert_raw"][:, None]], 1)
+        rows = CubeLossRows.apply(raw13, aux)
+        fm = lambda col, m=valid: G.finite_mean(rows[:, col], m)
+        losses = {"Cube/uncert": w["conf"] * fm(0), "Cube/loss_dims": fm(1) * w["dims"] * w["w3d"],
+                  "Cube/loss_xy": fm(2) * w["xy"] * w["w3d"], "Cube/loss_z": fm(3) * w["z"] * w["w3d"],
+                  "Cube/loss_pose": fm(4) * w["pose"] * w["w3d"], "Cube/loss_joint": fm(5) * w["joint"] * w["w3d"]}
+        with torch.no_grad():
+            r = rows.detach()
+            nv = valid.float().sum().clamp(min=1)
+            mean = lambda t: torch.where(valid, t, torch.zeros_like(t)).sum() / nv
+            self.stats.update({"Cube/z_error": mean(r[:, 6]), "Cube/dims_error": mean(r[:, 7]), "Cube/xy_error": mean(r[:, 8]),
+                               "Cube/z_close": mean((r[:, 6] < 0.20).float()), "Cube/conf": mean(r[:, 9])})
+        return losses
 
     def cube_losses(self, raw, boxes, classes, valid, gt3, gtR, Kb, v2r):
         w = self.w
@@ -334,7 +358,8 @@ class ROIHeads3D(nn.Module):
             xc = self.pool(feats, fb, fv)
             Kb, v2r, _ = self.per_box_camera(Ks, ratios, im_h, Fc, B, dev)
             raw = self.cube_outputs(xc, fc_.reshape(-1))
-            losses.update(self.cube_losses(raw, fb.reshape(-1, 4), fc_.reshape(-1), fv.reshape(-1),
+            cube_fn = self.cube_losses_fused if self.fused_cube else self.cube_losses
+            losses.update(cube_fn(raw, fb.reshape(-1, 4), fc_.reshape(-1), fv.reshape(-1),
                                            smp["gt_boxes3D"][:, :Fc].reshape(-1, 9), smp["gt_poses"][:, :Fc].reshape(-1, 3, 3),
                                            Kb, v2r))
             return None, losses

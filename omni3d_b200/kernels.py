@@ -35,6 +35,8 @@ def _bind():
     }
     sig["c3d_bias_act_bwd"] = [vp, vp, i32, i32, vp, vp, vp, i64, i32, vp, vp]
     sig["c3d_sumpool2"] = [vp, vp, i32, i32, i32, i32, vp]
+    sig["c3d_cube_loss_fwd"] = [vp, vp, i32, vp, vp]
+    sig["c3d_cube_loss_bwd"] = [vp, vp, vp, i32, vp, vp]
     sig["c3d_zero_stuff2"] = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.c3d_bn_scratch_bytes.restype = ctypes.c_size_t
     L.c3d_bn_scratch_bytes.argtypes = [i32]
@@ -221,3 +223,19 @@ def zero_stuff2(dy, H, W):
     z = torch.empty((N, H, W, C), device=dy.device, dtype=dy.dtype)
     _lib.check(L.c3d_zero_stuff2(_p(dy), _p(z), N, Ho, Wo, H, W, C, _st()))
     return z
+
+
+def cube_loss_fwd(raw, aux):
+    L = _bind()
+    n = raw.shape[0]
+    out = torch.empty((n, 10), device=raw.device, dtype=torch.float32)
+    _lib.check(L.c3d_cube_loss_fwd(_p(raw), _p(aux), n, _p(out), _st()))
+    return out
+
+
+def cube_loss_bwd(raw, aux, dout):
+    L = _bind()
+    n = raw.shape[0]
+    draw = torch.empty((n, 13), device=raw.device, dtype=torch.float32)
+    _lib.check(L.c3d_cube_loss_bwd(_p(raw), _p(aux), _p(dout), n, _p(draw), _st()))
+    return draw

@@ -160,3 +160,21 @@ class ROIAlign(torch.autograd.Function):
         strides, pooled = ctx.cfg
         grads = Kx.roi_align_bwd(feats, strides, rois, dout.contiguous(), pooled)
         return (None, None, None) + tuple(g.to(torch.bfloat16) for g in grads)
+
+
+class CubeLossRows(torch.autograd.Function):
+    """raw (n,13) head outputs + aux (n,28) constants -> (n,10): [u, l_dims, l_xy, l_z, l_pose, l_joint (each x
+    sqrt2*exp(-u)), |z-gz|, dims err, xy err, conf] — roi_heads.py:409-740 in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, raw, aux):
+        raw, aux = raw.contiguous().float(), aux.contiguous().float()
+        ctx.save_for_backward(raw, aux)
+        out = Kx.cube_loss_fwd(raw, aux)
+        ctx.mark_non_differentiable()
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        raw, aux = ctx.saved_tensors
+        return Kx.cube_loss_bwd(raw, aux, dout[:, :6].contiguous().float()), None

@@ -179,3 +179,44 @@ def test_sgd_and_finite_flag():
     Kx.grad_finite(g, flag); assert int(flag) == 0
     g[777] = float("inf"); Kx.grad_finite(g, flag); assert int(flag) == 1
     before = p.clone(); Kx.sgd_momentum(p, g, m, 0.02, 0.9, 1e-4, skip_flag=flag); assert torch.equal(p, before)
+
+
+def test_fused_cube_loss_matches_torch_formulation():
+    """c3d_cube_loss_fwd/bwd vs the batched torch fp32 formulation (ROIHeads3D.cube_losses + autograd)."""
+    from omni3d_b200 import cubercnn as pc
+    from omni3d_b200.cubercnn import geometry as G
+    cfg = pc.load_cfg("cubercnn_DLA34_FPN.yaml", ["MODEL.WEIGHTS_PRETRAIN", "none", "MODEL.DEVICE", "cuda"])
+    torch.manual_seed(0)
+    heads = pc.ROI_HEADS_REGISTRY.get("ROIHeads3D")(cfg, 256, {"p2": 4, "p3": 8, "p4": 16, "p5": 32, "p6": 64}).cuda()
+    heads.priors_dims_per_cat.data.uniform_(0.5, 2.0)
+    n = 600
+    g = torch.Generator(device="cuda").manual_seed(3)
+    R = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    U = lambda lo, hi, *s: torch.rand(*s, device="cuda", generator=g) * (hi - lo) + lo
+    xy = U(0, 400, n, 2); wh = U(20, 200, n, 2)
+    boxes = torch.cat([xy, xy + wh], 1)
+    classes = torch.randint(0, 50, (n,), device="cuda", generator=g)
+    valid = torch.rand(n, device="cuda", generator=g) > 0.2
+    f = U(400, 800, n)
+    Kb = torch.zeros(n, 3, 3, device="cuda"); Kb[:, 0, 0] = f; Kb[:, 1, 1] = f; Kb[:, 0, 2] = 320; Kb[:, 1, 2] = 240; Kb[:, 2, 2] = 1
+    v2r = U(0.5, 2.0, n)
+    gt3 = torch.cat([xy + 0.5 * wh + R(n, 2) * 5, U(2, 40, n, 1), U(0.3, 3, n, 3), R(n, 3)], 1)
+    q, _ = torch.linalg.qr(R(n, 3, 3)); gtR = q
+    base = dict(deltas=R(n, 2) * 0.1, dims=R(n, 3) * 0.3, pose6=R(n, 6) * 0.5, z=U(1, 30, n), ur=U(-0.2, 5.0, n))
+    out = {}
+    for mode in ("torch", "fused"):
+        leaves = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+        raw = dict(deltas=leaves["deltas"], dims=leaves["dims"], pose6=leaves["pose6"], z=leaves["z"],
+                   uncert=leaves["ur"].clip(0.01), uncert_raw=leaves["ur"])
+        fn = heads.cube_losses if mode == "torch" else heads.cube_losses_fused
+        losses = fn(raw, boxes, classes, valid, gt3, gtR, Kb, v2r)
+        sum(v * (i + 1) for i, v in enumerate(losses.values())).backward()
+        out[mode] = ({k: float(v) for k, v in losses.items()}, {k: v.grad.clone() for k, v in leaves.items()},
+                     {k: float(v) for k, v in heads.stats.items() if k.startswith("Cube/")})
+    for k, v in out["torch"][0].items():
+        assert abs(out["fused"][0][k] - v) <= 1e-4 * abs(v) + 1e-6, (k, out["fused"][0][k], v)
+    for k, gref in out["torch"][1].items():
+        gf = out["fused"][1][k]
+        assert ((gf - gref).norm() / (gref.norm() + 1e-12)).item() < 2e-3, k    # chamfer argmin ties aside
+    for k in ("Cube/z_error", "Cube/dims_error", "Cube/xy_error", "Cube/conf"):
+        assert abs(out["fused"][2][k] - out["torch"][2][k]) <= 1e-4 * abs(out["torch"][2][k]) + 1e-6, k
