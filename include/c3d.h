@@ -76,6 +76,12 @@ typedef struct {
   int32_t out_fp32;          /* output fp32 instead of bf16 */
   int32_t add_mode;          /* 0 none; 1 addend (N,Ho,Wo,Cout); 2 addend (N,Ho/2,Wo/2,Cout) nearest-up x2 (FPN) */
   int64_t x_pix_stride, y_pix_stride, add_pix_stride;   /* elements; 0 => dense */
+  /* optional strided output placement (in pixels): y pixel index = n*y_img_stride + ho*y_h_stride + wo*y_w_stride +
+   * y_offset; all 0 => dense (N,Ho,Wo).  Used by the phase-decomposed stride-2 data gradient. */
+  int64_t y_img_stride, y_h_stride, y_w_stride, y_offset;
+  /* optional explicit output size (0 => (H + 2*pad - KH)/stride + 1): lets a conv pad only on the high side
+   * (taps that run past H/W read TMA zero fill) */
+  int32_t out_h, out_w;
 } c3d_conv_desc;
 
 /* number of 128-pixel output tiles (= rows of the BatchNorm partial-statistics buffer) and tile shape */

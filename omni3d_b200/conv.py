@@ -16,7 +16,9 @@ class ConvDesc(ctypes.Structure):
                 ("stride", ctypes.c_int32), ("pad", ctypes.c_int32), ("relu", ctypes.c_int32),
                 ("out_fp32", ctypes.c_int32), ("add_mode", ctypes.c_int32),
                 ("x_pix_stride", ctypes.c_int64), ("y_pix_stride", ctypes.c_int64),
-                ("add_pix_stride", ctypes.c_int64)]
+                ("add_pix_stride", ctypes.c_int64), ("y_img_stride", ctypes.c_int64), ("y_h_stride", ctypes.c_int64),
+                ("y_w_stride", ctypes.c_int64), ("y_offset", ctypes.c_int64), ("out_h", ctypes.c_int32),
+                ("out_w", ctypes.c_int32)]
 
 
 _bound = False
@@ -58,7 +60,7 @@ def make_desc(x, w, stride=1, pad=0, relu=False, out_fp32=False, add_mode=0):
     N, H, W, Cin = x.shape
     Cout, KH, KW, Cin2 = w.shape
     assert Cin == Cin2, (x.shape, w.shape)
-    return ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, int(relu), int(out_fp32), add_mode, 0, 0, 0)
+    return ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, int(relu), int(out_fp32), add_mode, 0, 0, 0, 0, 0, 0, 0, 0, 0)
 
 
 def num_tiles(desc):
@@ -69,7 +71,7 @@ def num_tiles(desc):
 
 
 def conv2d_fwd(x, w, bias=None, stride=1, pad=0, relu=False, addend=None, up2=False, out_fp32=False,
-               want_stats=False, out=None):
+               want_stats=False, out=None, out_place=None, out_hw_override=None):
     """x (N,H,W,Cin) bf16, w (Cout,KH,KW,Cin) bf16 -> y (N,Ho,Wo,Cout) bf16|fp32 [, stats (tiles,2,Cout)]."""
     L = _bind()
     assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()
@@ -77,6 +79,11 @@ def conv2d_fwd(x, w, bias=None, stride=1, pad=0, relu=False, addend=None, up2=Fa
     add_mode = 0 if addend is None else (2 if up2 else 1)
     d = make_desc(x, w, stride, pad, relu, out_fp32, add_mode)
     Ho, Wo = out_hw(d.H, d.W, d.KH, d.KW, stride, pad)
+    if out_hw_override is not None:
+        Ho, Wo = out_hw_override
+        d.out_h, d.out_w = Ho, Wo
+    if out_place is not None:        # (img_stride, h_stride, w_stride, offset) in pixels of `out`
+        d.y_img_stride, d.y_h_stride, d.y_w_stride, d.y_offset = out_place
     if out is None:
         out = torch.empty((d.N, Ho, Wo, d.Cout), device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
     stats = None
@@ -111,6 +118,6 @@ def conv2d_wgrad(x, dy, KH, KW, stride=1, pad=0, dw=None, oihw=False):
     assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
     if dw is None:
         dw = torch.zeros((Cout, Cin, KH, KW) if oihw else (Cout, KH, KW, Cin), device=x.device, dtype=torch.float32)
-    d = ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, 0, 0, 0, 0, 0, 0)
+    d = ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
     _lib.check(L.c3d_conv2d_wgrad_ex(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), int(oihw), _stream()))
     return dw

@@ -38,6 +38,7 @@ struct ConvKParams {
   long long add_pix_stride;
   void* out;
   long long out_pix_stride;  // elements
+  long long out_img_stride, out_h_stride, out_w_stride, out_off;   // output pixel index = img*is + ho*hs + wo*ws + off
   float* stats;              // [tiles_m][2][Cout] partial (sum, sum of squares) or null
 };
 
@@ -140,9 +141,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int ty = r / P.TW, tx = r - ty * P.TW;
     const int ho = ho0 + ty, wo = wo0 + tx;
     const bool valid = (r < P.TH * P.TW) && (ho < P.Ho) && (wo < P.Wo);
-    const long long pix = ((long long)img * P.Ho + ho) * P.Wo + wo;
+    const long long lpix = ((long long)img * P.Ho + ho) * P.Wo + wo;   // dense pixel index (addend / stats)
+    const long long pix = (long long)img * P.out_img_stride + (long long)ho * P.out_h_stride + (long long)wo * P.out_w_stride + P.out_off;
     long long apix = 0;
-    if (P.add_mode == 1) apix = pix;
+    if (P.add_mode == 1) apix = lpix;
     else if (P.add_mode == 2) apix = ((long long)img * (P.Ho >> 1) + (ho >> 1)) * (P.Wo >> 1) + (wo >> 1);
 
     ptx::mbar_wait(tmem_full_bar, 0);
@@ -337,9 +339,10 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
       const int ty = r / P.TW, tx = r - ty * P.TW;
       const int ho = th_i * P.TH + ty, wo = tw_i * P.TW + tx;
       const bool valid = (r < P.TH * P.TW) && (ho < P.Ho) && (wo < P.Wo);
-      const long long pix = ((long long)img * P.Ho + ho) * P.Wo + wo;
+      const long long lpix = ((long long)img * P.Ho + ho) * P.Wo + wo;   // dense pixel index (addend / stats)
+    const long long pix = (long long)img * P.out_img_stride + (long long)ho * P.out_h_stride + (long long)wo * P.out_w_stride + P.out_off;
       long long apix = 0;
-      if (P.add_mode == 1) apix = pix;
+      if (P.add_mode == 1) apix = lpix;
       else if (P.add_mode == 2) apix = ((long long)img * (P.Ho >> 1) + (ho >> 1)) * (P.Wo >> 1) + (wo >> 1);
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tcgen05_fence_after();
@@ -679,8 +682,8 @@ using namespace c3d;
 
 extern "C" int32_t c3d_conv2d_tiles(const c3d_conv_desc* d, int32_t* tiles_m, int32_t* TH, int32_t* TW) {
   if (!d) return set_error(C3D_EINVAL, "null desc");
-  int Ho = (d->H + 2 * d->pad - d->KH) / d->stride + 1;
-  int Wo = (d->W + 2 * d->pad - d->KW) / d->stride + 1;
+  int Ho = d->out_h > 0 ? d->out_h : (d->H + 2 * d->pad - d->KH) / d->stride + 1;
+  int Wo = d->out_w > 0 ? d->out_w : (d->W + 2 * d->pad - d->KW) / d->stride + 1;
   int th, tw;
   pick_tile(Ho, Wo, d->stride, &th, &tw);
   if (TH) *TH = th;
@@ -705,8 +708,8 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   // (Cin < 64, or 1x1 with Cin <= 64) run better as many short CTAs (measured, profiles/)
   const bool persistent = !non_persistent && BK == 64 && BN >= 64 && !(d->KH == 1 && Cin <= 64);
   if (persistent && allow_n256 && Cout % 256 == 0) BN = 256;
-  const int Ho = (d->H + 2 * d->pad - d->KH) / d->stride + 1;
-  const int Wo = (d->W + 2 * d->pad - d->KW) / d->stride + 1;
+  const int Ho = d->out_h > 0 ? d->out_h : (d->H + 2 * d->pad - d->KH) / d->stride + 1;
+  const int Wo = d->out_w > 0 ? d->out_w : (d->W + 2 * d->pad - d->KW) / d->stride + 1;
   if (d->add_mode == 2 && ((Ho & 1) || (Wo & 1))) return set_error(C3D_EINVAL, "conv2d: up2 addend needs even output");
   if (d->add_mode && !addend) return set_error(C3D_EINVAL, "conv2d: addend missing");
   PFN_encodeTiled enc = get_encode();
@@ -721,6 +724,11 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   P.addend = static_cast<const bf16*>(addend);
   P.add_pix_stride = d->add_pix_stride ? d->add_pix_stride : Cout;
   P.out = y; P.out_pix_stride = d->y_pix_stride ? d->y_pix_stride : Cout;
+  if (d->y_img_stride) {
+    P.out_img_stride = d->y_img_stride; P.out_h_stride = d->y_h_stride; P.out_w_stride = d->y_w_stride; P.out_off = d->y_offset;
+  } else {
+    P.out_img_stride = (long long)Ho * Wo; P.out_h_stride = Wo; P.out_w_stride = 1; P.out_off = 0;
+  }
   P.stats = stats;
   const long long xps = d->x_pix_stride ? d->x_pix_stride : Cin;
 

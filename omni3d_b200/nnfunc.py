@@ -21,6 +21,7 @@ def invalidate_packed():
     global _epoch
     _epoch += 1
     _pack_cache.clear()
+    _phase_cache.clear()
 
 
 def _packed(w, kind):
@@ -38,9 +39,42 @@ def _packed(w, kind):
     return hit[1] if kind == "fwd" else hit[2]
 
 
+_phase_cache = {}
+
+
+def _phase_packs(w):
+    """sub-kernels of a 3x3 / stride-2 / pad-1 conv's data gradient, one per output parity (a,b):
+    dx[2i+a, 2j+b] = sum_{k'} dy[i+k'h, j+k'w] * W[.., kh(a,k'h), kw(b,k'w)] with kh(0,.) = [1], kh(1,.) = [2,0].
+    -> {(a,b): bf16 (Cin, KH', KW', Cout)}, cached per parameter version / optimizer epoch."""
+    key = w.data_ptr()
+    ver = (w._version, _epoch, tuple(w.shape))
+    hit = _phase_cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    taps = {0: [1], 1: [2, 0]}
+    packs = {}
+    with torch.no_grad():
+        for a in (0, 1):
+            for b in (0, 1):
+                sub = w[:, :, taps[a]][:, :, :, taps[b]]                   # (Cout,Cin,KH',KW')
+                packs[(a, b)] = sub.permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)
+    if w.is_leaf:
+        _phase_cache[key] = (ver, packs)
+    return packs
+
+
 def _dgrad(dy, w, stride, pad, in_hw):
-    """dx for y = conv(x, w, stride, pad): stride-1 conv of (zero-stuffed) dy with the rotated weights."""
+    """dx for y = conv(x, w, stride, pad).  stride 1: conv of dy with the 180-degree-rotated, transposed weights.
+    3x3/s2/p1: four phase convs (one per output parity) written straight into the strided positions of dx —
+    exactly the algorithmic FLOPs, no zero-stuffed intermediate."""
     KH = w.shape[2]
+    if stride == 2 and KH == 3 and pad == 1 and in_hw[0] == 2 * dy.shape[1] and in_hw[1] == 2 * dy.shape[2]:
+        N, Ho, Wo, _ = dy.shape
+        H, W = in_hw
+        dx = torch.empty((N, H, W, w.shape[1]), device=dy.device, dtype=dy.dtype)
+        for (a, b), wp in _phase_packs(w).items():
+            K.conv2d_fwd(dy, wp, stride=1, pad=0, out=dx, out_place=(H * W, 2 * W, 2, a * W + b), out_hw_override=(Ho, Wo))
+        return dx
     wp = _packed(w, "dgrad")
     if stride == 1:
         return K.conv2d_fwd(dy, wp, stride=1, pad=KH - 1 - pad)
