@@ -100,10 +100,10 @@ int32_t c3d_conv2d_wgrad(const c3d_conv_desc* d, const void* x, const void* dy, 
  * optimizer's gradient arena, no layout conversion pass) */
 int32_t c3d_conv2d_wgrad_ex(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, int32_t oihw,
                             void* stream);
-/* fp32 OIHW master weight -> bf16 (Cout,KH,KW,Cin) forward pack and/or bf16 (Cin,KH,KW,Cout) 180-degree-rotated
- * data-gradient pack (either output may be NULL) */
-int32_t c3d_pack_conv_weight(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t KH, int32_t KW, void* fwd_ohwi,
-                             void* dgrad_ihwo, void* stream);
+/* fp32 master weight (OIHW, or OHWI = torch channels_last storage when src_is_ohwi != 0) -> bf16 (Cout,KH,KW,Cin)
+ * forward pack and/or bf16 (Cin,KH,KW,Cout) 180-degree-rotated data-gradient pack (either output may be NULL) */
+int32_t c3d_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin, int32_t KH, int32_t KW, int32_t src_is_ohwi,
+                             void* fwd_ohwi, void* dgrad_ihwo, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * HBM-bound NHWC bf16 kernels around the convolutions.

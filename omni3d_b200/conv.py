@@ -39,7 +39,7 @@ def _bind():
         L.c3d_conv2d_wgrad_ex.restype = i32
         L.c3d_conv2d_wgrad_ex.argtypes = [P, vp, vp, vp, i32, vp]
         L.c3d_pack_conv_weight.restype = i32
-        L.c3d_pack_conv_weight.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
+        L.c3d_pack_conv_weight.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp]
         _bound = True
     return L
 
@@ -103,10 +103,13 @@ def pack_conv_weight(w, want_fwd=True, want_dgrad=True):
     """fp32 (Cout,Cin,KH,KW) -> bf16 (Cout,KH,KW,Cin) and bf16 (Cin,KH,KW,Cout) rotated, in ONE launch."""
     L = _bind()
     Cout, Cin, KH, KW = w.shape
-    w = w.detach().contiguous()
+    w = w.detach()
+    ohwi = (not w.is_contiguous()) and w.permute(0, 2, 3, 1).is_contiguous()     # channels_last master storage
+    if not ohwi:
+        w = w.contiguous()
     f = torch.empty((Cout, KH, KW, Cin), device=w.device, dtype=torch.bfloat16) if want_fwd else None
     g = torch.empty((Cin, KH, KW, Cout), device=w.device, dtype=torch.bfloat16) if want_dgrad else None
-    _lib.check(L.c3d_pack_conv_weight(_ptr(w), Cout, Cin, KH, KW, _ptr(f), _ptr(g), _stream()))
+    _lib.check(L.c3d_pack_conv_weight(_ptr(w), Cout, Cin, KH, KW, int(ohwi), _ptr(f), _ptr(g), _stream()))
     return f, g
 
 

@@ -626,9 +626,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
 #pragma unroll
             for (int i = 0; i < 16; ++i) if (i < lim) atomicAdd(dst + (size_t)i * taps, __uint_as_float(v[i]));
           } else {
-            float* dst = P.dw + ((size_t)co * taps + tap) * P.Cin + ci;
+            float4* dst = reinterpret_cast<float4*>(P.dw + ((size_t)co * taps + tap) * P.Cin + ci);   // 64-B aligned
 #pragma unroll
-            for (int i = 0; i < 16; ++i) if (i < lim) atomicAdd(dst + i, __uint_as_float(v[i]));
+            for (int i = 0; i < 4; ++i)
+              atomicAdd(dst + i, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                             __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
           }
         }
       }
@@ -823,8 +825,9 @@ extern "C" int32_t c3d_conv2d_wgrad_ex(const c3d_conv_desc* d, const void* x, co
   P.a_chunks_max = 128 / P.ca;                  // chunks beyond Cout are not loaded (those D rows are never stored)
   const int groups = (P.total_boxes + P.boxes_per_cta - 1) / P.boxes_per_cta;
   const int co_tiles = (Cout + 127) / 128;
+  // split the pixel range for ~1.3 waves of CTAs (1 CTA/SM): every extra split costs 128 x N fp32 atomics
   long long base = (long long)groups * co_tiles;
-  int splits = (int)((4LL * kNumSMs + base - 1) / base);
+  int splits = (int)((13LL * kNumSMs / 10 + base - 1) / base);
   if (splits > P.num_tiles) splits = P.num_tiles;
   if (splits < 1) splits = 1;
   P.tiles_per_split = (P.num_tiles + splits - 1) / splits;

@@ -361,15 +361,24 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
 }
 
 // ---- weight re-pack: fp32 OIHW master -> bf16 OHWI (forward) and bf16 rotated/transposed (data gradient) ----
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW,
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, int src_ohwi,
                                         bf16* __restrict__ fwd, bf16* __restrict__ dgrad) {
   const long long total = (long long)Cout * Cin * KH * KW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int kw = (int)(i % KW);
-    long long t = i / KW;
-    const int kh = (int)(t % KH); t /= KH;
-    const int ci = (int)(t % Cin);
-    const int co = (int)(t / Cin);
+    int kw, kh, ci, co;
+    if (src_ohwi) {                      // master stored (Cout,KH,KW,Cin): the forward pack is a plain cast
+      ci = (int)(i % Cin);
+      long long t = i / Cin;
+      kw = (int)(t % KW); t /= KW;
+      kh = (int)(t % KH);
+      co = (int)(t / KH);
+    } else {
+      kw = (int)(i % KW);
+      long long t = i / KW;
+      kh = (int)(t % KH); t /= KH;
+      ci = (int)(t % Cin);
+      co = (int)(t / Cin);
+    }
     const bf16 v = __float2bfloat16(w[i]);
     if (fwd) fwd[(((long long)co * KH + kh) * KW + kw) * Cin + ci] = v;
     if (dgrad) dgrad[(((long long)ci * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)) * Cout + co] = v;
@@ -566,11 +575,11 @@ extern "C" int32_t c3d_zero_stuff2(const void* dy, void* z, int32_t N, int32_t H
 }
 
 extern "C" int32_t c3d_pack_conv_weight(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t KH, int32_t KW,
-                                        void* fwd_ohwi, void* dgrad_ihwo, void* stream) {
+                                        int32_t src_is_ohwi, void* fwd_ohwi, void* dgrad_ihwo, void* stream) {
   C3D_REQ(w_oihw && (fwd_ohwi || dgrad_ihwo), "pack_conv_weight: bad args");
   long long total = (long long)Cout * Cin * KH * KW;
   if (total == 0) return C3D_OK;
-  pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, KH, KW,
+  pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, KH, KW, src_is_ohwi,
                                                                                   (bf16*)fwd_ohwi, (bf16*)dgrad_ihwo);
   return check_launch("pack_conv_weight");
 }

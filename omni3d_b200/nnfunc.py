@@ -90,9 +90,13 @@ def _wgrad_to_master(x, dy, w, stride, pad):
     """weight gradient in the master (Cout,Cin,KH,KW) layout.  When the parameter already owns a contiguous
     fp32 .grad (the trainer's flat arena) the kernel accumulates straight into it and autograd gets None."""
     g = w.grad if w.is_leaf else None
-    if g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == w.shape:
-        K.conv2d_wgrad(x, dy, w.shape[2], w.shape[3], stride, pad, dw=g, oihw=True)
-        return None
+    if g is not None and g.dtype == torch.float32 and g.shape == w.shape:
+        if g.is_contiguous():
+            K.conv2d_wgrad(x, dy, w.shape[2], w.shape[3], stride, pad, dw=g, oihw=True)
+            return None
+        if g.permute(0, 2, 3, 1).is_contiguous():      # channels_last arena: the kernel's native (O,H,W,I) layout
+            K.conv2d_wgrad(x, dy, w.shape[2], w.shape[3], stride, pad, dw=g, oihw=False)
+            return None
     return K.conv2d_wgrad(x, dy, w.shape[2], w.shape[3], stride, pad, oihw=True)
 
 

@@ -53,7 +53,7 @@ def lr_at(cfg, it):
 
 
 class FlatSGDTrainer:
-    def __init__(self, cfg, model):
+    def __init__(self, cfg, model, channels_last_weights=True):
         if cfg.SOLVER.TYPE != "sgd":
             raise ValueError("{} is not supported as an optimizer on the accelerated path.".format(cfg.SOLVER.TYPE))
         self.cfg, self.model = cfg, model
@@ -100,6 +100,15 @@ class FlatSGDTrainer:
         self.flat_m = torch.zeros(total, device=dev)
         with torch.no_grad():
             for p, off, n in zip(order, offs, sizes):
+                if p.dim() == 4 and channels_last_weights:
+                    # conv weights are STORED (Cout,KH,KW,Cin) — the layout the tcgen05 kernels consume and the
+                    # weight-gradient kernel produces — and exposed to torch as (Cout,Cin,KH,KW) strided views
+                    # (= torch.channels_last); checkpoints and optimizer semantics are unchanged
+                    O, I, KH, KW = p.shape
+                    self.flat_p[off:off + n].view(O, KH, KW, I).copy_(p.permute(0, 2, 3, 1))
+                    p.data = self.flat_p[off:off + n].view(O, KH, KW, I).permute(0, 3, 1, 2)
+                    p.grad = self.flat_g[off:off + n].view(O, KH, KW, I).permute(0, 3, 1, 2)
+                    continue
                 self.flat_p[off:off + n].copy_(p.reshape(-1))
                 p.data = self.flat_p[off:off + n].view(p.shape)
                 p.grad = self.flat_g[off:off + n].view(p.shape)
