@@ -825,9 +825,11 @@ extern "C" int32_t c3d_conv2d_wgrad_ex(const c3d_conv_desc* d, const void* x, co
   P.a_chunks_max = 128 / P.ca;                  // chunks beyond Cout are not loaded (those D rows are never stored)
   const int groups = (P.total_boxes + P.boxes_per_cta - 1) / P.boxes_per_cta;
   const int co_tiles = (Cout + 127) / 128;
-  // split the pixel range for ~1.3 waves of CTAs (1 CTA/SM): every extra split costs 128 x N fp32 atomics
+  // split-K over pixels (1 CTA/SM): every split costs 128 x N fp32 atomics, so big weight tensors get exactly one
+  // wave of CTAs (<= 148) while small ones (<= 64K elements: the pixel-heavy early layers) get ~4 waves for balance
   long long base = (long long)groups * co_tiles;
-  int splits = (int)((13LL * kNumSMs / 10 + base - 1) / base);
+  const long long welems = (long long)Cout * taps * Cin;
+  int splits = welems <= 65536 ? (int)((4LL * kNumSMs + base - 1) / base) : (int)(kNumSMs / base);
   if (splits > P.num_tiles) splits = P.num_tiles;
   if (splits < 1) splits = 1;
   P.tiles_per_split = (P.num_tiles + splits - 1) / splits;
