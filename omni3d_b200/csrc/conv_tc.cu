@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
+#include <string.h>
 #include "c3d_common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -680,12 +681,20 @@ static int32_t launch_conv_p(const CUtensorMap& mx, const CUtensorMap& mw, const
 
 }  // namespace c3d
 
+#include "conv_halo.cuh"
+
 using namespace c3d;
 
 extern "C" int32_t c3d_conv2d_tiles(const c3d_conv_desc* d, int32_t* tiles_m, int32_t* TH, int32_t* TW) {
   if (!d) return set_error(C3D_EINVAL, "null desc");
   int Ho = d->out_h > 0 ? d->out_h : (d->H + 2 * d->pad - d->KH) / d->stride + 1;
   int Wo = d->out_w > 0 ? d->out_w : (d->W + 2 * d->pad - d->KW) / d->stride + 1;
+  if (halo_fwd_eligible(d)) {          // one partial-statistics row per persistent CTA
+    if (TH) *TH = 1;
+    if (TW) *TW = 128;
+    if (tiles_m) *tiles_m = halo_fwd_grid(d);
+    return C3D_OK;
+  }
   int th, tw;
   pick_tile(Ho, Wo, d->stride, &th, &tw);
   if (TH) *TH = th;
@@ -698,6 +707,7 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
                                   const void* addend, void* y, float* stats, void* stream) {
   if (!d || !x || !w || !y) return set_error(C3D_EINVAL, "conv2d: null pointer");
   const int Cin = d->Cin, Cout = d->Cout;
+  if (halo_fwd_eligible(d)) return launch_halo_fwd(d, x, w, bias, y, stats, static_cast<cudaStream_t>(stream));
   if (Cin % 16 != 0 || Cin <= 0) return set_error(C3D_EINVAL, "conv2d: Cin=%d must be a multiple of 16", Cin);
   if (Cout % 16 != 0 || Cout <= 0) return set_error(C3D_EINVAL, "conv2d: Cout=%d must be a multiple of 16", Cout);
   if (d->stride < 1 || d->stride > 2) return set_error(C3D_EINVAL, "conv2d: stride %d unsupported", d->stride);
@@ -804,6 +814,7 @@ extern "C" int32_t c3d_conv2d_wgrad_ex(const c3d_conv_desc* d, const void* x, co
                                        void* stream) {
   if (!d || !x || !dy || !dw) return set_error(C3D_EINVAL, "wgrad: null pointer");
   const int Cin = d->Cin, Cout = d->Cout;
+  if (halo_wgrad_eligible(d)) return launch_halo_wgrad(d, x, dy, dw, oihw, static_cast<cudaStream_t>(stream));
   if (Cin % 16 != 0 || Cout % 16 != 0) return set_error(C3D_EINVAL, "wgrad: channels must be multiples of 16");
   if (d->stride < 1 || d->stride > 2) return set_error(C3D_EINVAL, "wgrad: stride %d unsupported", d->stride);
   const int Ho = (d->H + 2 * d->pad - d->KH) / d->stride + 1;

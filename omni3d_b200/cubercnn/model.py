@@ -70,7 +70,8 @@ class RCNN3D(nn.Module):
     def preprocess_image(self, batched_inputs):
         imgs = [x["image"].to(self.device, non_blocking=True).float().contiguous() for x in batched_inputs]
         sizes = [(int(im.shape[1]), int(im.shape[2])) for im in imgs]
-        x = Kx.preprocess_images(imgs, self._mean, self._std, self.backbone.size_divisibility, cpad=16)
+        x = Kx.preprocess_images(imgs, self._mean, self._std, self.backbone.size_divisibility,
+                                 cpad=getattr(self.backbone.bottom_up, "stem_cpad", 16))
         return x, sizes
 
     def forward(self, batched_inputs, _inject=None):

@@ -36,6 +36,42 @@ def test_conv_fwd_dgrad_wgrad_vs_torch(N, H, W, Cin, Cout, k, s, p):
     assert (b.grad - br.grad).abs().max().item() <= 1e-2 * br.grad.abs().max().item() + 1e-3
 
 
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k", [(2, 40, 256, 16, 16, 3), (1, 33, 200, 8, 16, 7), (2, 70, 128, 32, 32, 3),
+                                             (1, 9, 384, 16, 32, 5), (3, 35, 130, 32, 16, 3)])
+def test_halo_conv_fwd_dgrad_wgrad_vs_torch(N, H, W, Cin, Cout, k):
+    """thin-channel stride-1 layers (DLA stem / level0) run on conv_halo_* (rolling input rows in smem, no-swizzle
+    UMMA descriptors): ragged strips (W % 128 != 0), chunk boundaries (H > 32) and both K-chunk modes."""
+    from omni3d_b200 import conv as K
+    from omni3d_b200.nnfunc import ConvBias
+    p = k // 2
+    x = _r(N, H, W, Cin).bfloat16().requires_grad_(Cin != 8)
+    w = (_r(Cout, Cin, k, k, seed=1) / (k * k * Cin) ** 0.5).requires_grad_(True)
+    b = _r(Cout, seed=2).requires_grad_(True)
+    y = ConvBias.apply(x, w, b, None, 1, p, True, False)
+    dy = _r(*y.shape, seed=3).bfloat16()
+    y.backward(dy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.detach().bfloat16().float().requires_grad_(True)
+    br = b.detach().clone().requires_grad_(True)
+    yr = F.relu(F.conv2d(xr, wr, br, 1, p))
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    tol = lambda ref: 1.2e-2 * ref.abs().max().item() + 1e-3
+    assert (y.float() - yr.permute(0, 2, 3, 1)).abs().max().item() <= tol(yr)
+    if Cin != 8:                      # the 8-channel stem has no data gradient in the model (dgrad needs Cout in {16,32})
+        assert (x.grad.float() - xr.grad.permute(0, 2, 3, 1)).abs().max().item() <= tol(xr.grad)
+    assert (w.grad - wr.grad).abs().max().item() <= 2e-2 * wr.grad.abs().max().item() + 1e-3
+    # per-CTA BatchNorm partial statistics and the OHWI gradient layout
+    wp = w.detach().permute(0, 2, 3, 1).contiguous().bfloat16()
+    y2, stats = K.conv2d_fwd(x.detach(), wp, stride=1, pad=p, want_stats=True)
+    ref = F.conv2d(xr.detach(), wr.detach(), None, 1, p).permute(0, 2, 3, 1)
+    tot = stats.double().sum(0)
+    assert (tot[0] - ref.double().sum((0, 1, 2))).abs().max().item() <= 2e-3 * ref.abs().sum((0, 1, 2)).max().item() + 1e-2
+    assert (tot[1] - (ref.double() ** 2).sum((0, 1, 2))).abs().max().item() <= 2e-3 * (ref.double() ** 2).sum((0, 1, 2)).max().item()
+    dz = dy.float() * (yr.permute(0, 2, 3, 1) > 0)
+    g2 = K.conv2d_wgrad(x.detach(), dz.bfloat16().contiguous(), k, k, 1, p, oihw=False)
+    assert (g2.permute(0, 3, 1, 2) - wr.grad).abs().max().item() <= 2e-2 * wr.grad.abs().max().item() + 1e-3
+
+
 @pytest.mark.parametrize("C,relu,res", [(64, True, True), (128, True, False), (16, False, False), (512, True, True)])
 def test_conv_bn_act_train_vs_torch(C, relu, res):
     from omni3d_b200.nnfunc import ConvBNAct

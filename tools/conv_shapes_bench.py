@@ -7,8 +7,9 @@ sys.path.insert(0, ROOT)
 import torch
 from omni3d_b200 import conv as K
 
+STEM_C = 16 if os.environ.get("C3D_CONV_NO_HALO") else 8     # NHWC8 image for the rolling-halo stem kernel
 SHAPES = [  # name, H, W, Cin, Cout, k, stride, pad, real_cin
-    ("stem7x7_3(16)->16@640", 640, 640, 16, 16, 7, 1, 3, 3),
+    ("stem7x7_3(%d)->16@640" % STEM_C, 640, 640, STEM_C, 16, 7, 1, 3, 3),
     ("level0_16->16@640", 640, 640, 16, 16, 3, 1, 1, 16),
     ("level1_16->32s2@640", 640, 640, 16, 32, 3, 2, 1, 16),
     ("l2_64->64@160", 160, 160, 64, 64, 3, 1, 1, 64),
