@@ -44,29 +44,41 @@ struct HaloParams {
 // ------------------------------------------------------------------------------------------------------------
 // forward / data-gradient: y[n,y,x,:] = sum_taps W[:,kh,kw,:] . x[n, y+kh-pad, x+kw-pad, :]
 // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue.  CH = Cout / 16 (1 or 2).
-template <int CH>
-__global__ void __launch_bounds__(192)
+// descriptor halves: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version 1 (bit 46) | layout none
+__device__ __forceinline__ uint64_t halo_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+__host__ __device__ constexpr uint32_t halo_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+
+// KS / CIN > 0 fix the filter size and input channels at compile time: the MMA-issuing thread is a single lane whose
+// instruction latency bounds the kernel (measured: ~6 cycles per dependent instruction), so its per-MMA address
+// arithmetic must fold to immediates.  KS = CIN = 0 is the generic (slow) fallback.
+template <int CH, int KS, int CIN>
+__global__ void __launch_bounds__(192, CH == 1 ? 3 : 2)
 conv_halo_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams P) {
   constexpr int kCout = CH * 16;
-  constexpr uint32_t kTmemCols = 64;
+  constexpr int kAcc = 4;                                         // TMEM accumulator ring (rows in flight MMA -> epilogue)
+  constexpr uint32_t kTmemCols = 128;
+  const int KH = KS > 0 ? KS : P.KH, KW = KH;
+  const int Cin = CIN > 0 ? CIN : P.Cin;
+  const int BW = KS > 1 ? 136 : P.BW;
+  const int NP = Cin >> 3;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  const int plane_bytes = P.BW * 16;
-  const int slot_bytes = P.P * plane_bytes;
+  const int plane_bytes = BW * 16;
+  const int slot_bytes = NP * plane_bytes;
   const int wimg_bytes = P.ksteps * kCout * 32;
   uint8_t* wimg = smem;
   uint8_t* ring = smem + ((wimg_bytes + 127) & ~127);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)P.R * slot_bytes);
   uint64_t* empty_bar = full_bar + P.R;
   uint64_t* tfull_bar = empty_bar + P.R;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tempty_bar = tfull_bar + kAcc;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + kAcc);
   float* red = reinterpret_cast<float*>(tmem_ptr + 4);            // [4 warps][2][kCout]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KWP = (P.KW + 1) >> 1;                                // tap pairs per filter row (Cin == 8 mode)
-  const bool pair_mode = (P.Cin == 8);
-  const int PQ = P.Cin >> 4;
+  const int KWP = (KW + 1) >> 1;                                  // tap pairs per filter row (Cin == 8 mode)
+  const bool pair_mode = (Cin == 8);
+  const int PQ = Cin >= 16 ? (Cin >> 4) : 1;
 
   // weight image: [kstep][Cout/8][2 K-chunks][8 rows][8 elems] = canonical no-swizzle K-major B operand
   for (int idx = threadIdx.x; idx < P.ksteps * kCout * 2; idx += blockDim.x) {
@@ -74,10 +86,10 @@ conv_halo_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParam
     uint4 v = make_uint4(0, 0, 0, 0);
     if (pair_mode) {
       const int kh = s / KWP, kw = 2 * (s - kh * KWP) + j;
-      if (kw < P.KW) v = *reinterpret_cast<const uint4*>(P.w + ((size_t)(co * P.KH + kh) * P.KW + kw) * 8);
+      if (kw < KW) v = *reinterpret_cast<const uint4*>(P.w + ((size_t)(co * KH + kh) * KW + kw) * 8);
     } else {
       const int tap = s / PQ, q = s - tap * PQ;
-      v = *reinterpret_cast<const uint4*>(P.w + ((size_t)co * P.KH * P.KW + tap) * P.Cin + (2 * q + j) * 8);
+      v = *reinterpret_cast<const uint4*>(P.w + ((size_t)co * KH * KW + tap) * Cin + (2 * q + j) * 8);
     }
     *reinterpret_cast<uint4*>(wimg + (size_t)s * kCout * 32 + (co >> 3) * 256 + j * 128 + (co & 7) * 16) = v;
   }
@@ -86,7 +98,7 @@ conv_halo_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParam
   if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&tmap_x);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < P.R; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < kAcc; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<kTmemCols>(tmem_ptr);
@@ -97,66 +109,77 @@ conv_halo_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParam
 
   if (warp == 0) {
     if (ptx::elect_one()) {
-      uint32_t g = 0;
+      uint32_t slot = 0, par = 0;
       for (int c = blockIdx.x; c < P.total_chunks; c += gridDim.x) {
         const int col = c / P.chunks_per_col, cy = c - col * P.chunks_per_col;
         const int n = col / P.strips, xs = col - n * P.strips;
         const int y0 = cy * P.rows_per_chunk;
         const int rows = min(P.rows_per_chunk, P.H - y0);
         const int x0 = xs * 128 - P.pad;
-        for (int i = 0; i < rows + P.KH - 1; ++i, ++g) {
-          const uint32_t slot = g % (uint32_t)P.R, par = (g / (uint32_t)P.R) & 1u;
+        for (int i = 0; i < rows + KH - 1; ++i) {
           ptx::mbar_wait(&empty_bar[slot], par ^ 1u);
           ptx::mbar_expect_tx(&full_bar[slot], (uint32_t)slot_bytes);
           uint8_t* dst = ring + (size_t)slot * slot_bytes;
-          for (int p = 0; p < P.P; ++p)
+#pragma unroll
+          for (int p = 0; p < NP; ++p)
             ptx::tma_load_4d(dst + p * plane_bytes, &tmap_x, &full_bar[slot], p * 8, x0, y0 - P.pad + i, n);
+          if (++slot == (uint32_t)P.R) { slot = 0; par ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     if (ptx::elect_one()) {
       const uint32_t idesc = ptx::make_idesc_bf16(128, kCout, 0, 0);
-      const uint32_t ring_u32 = ptx::smem_u32(ring), wimg_u32 = ptx::smem_u32(wimg);
-      uint32_t gbase = 0, ready = 0;
+      const uint32_t R = (uint32_t)P.R;
+      const uint32_t slot_u = (uint32_t)slot_bytes >> 4;                         // descriptor address units (16 B)
+      const uint32_t a_lo0 = (ptx::smem_u32(ring) >> 4) | ((pair_mode ? 1u : ((uint32_t)plane_bytes >> 4)) << 16);
+      const uint32_t b_lo0 = (ptx::smem_u32(wimg) >> 4) | (8u << 16);           // LBO 128 B
+      constexpr uint32_t a_hi = halo_desc_hi(128), b_hi = halo_desc_hi(256);
+      uint32_t slot0 = 0;                      // ring slot of the first input row of the current output row
+      uint32_t rslot = 0, rpar = 0;            // next ring slot to wait for
       int acc = 0; uint32_t acc_phase = 0;
       for (int c = blockIdx.x; c < P.total_chunks; c += gridDim.x) {
         const int cy = c % P.chunks_per_col;
         const int y0 = cy * P.rows_per_chunk;
         const int rows = min(P.rows_per_chunk, P.H - y0);
         for (int j = 0; j < rows; ++j) {
-          while (ready < gbase + (uint32_t)(j + P.KH)) {
-            ptx::mbar_wait(&full_bar[ready % (uint32_t)P.R], (ready / (uint32_t)P.R) & 1u);
-            ++ready;
+          const int need = j == 0 ? KH : 1;
+          for (int t = 0; t < need; ++t) {
+            ptx::mbar_wait(&full_bar[rslot], rpar);
+            if (++rslot == R) { rslot = 0; rpar ^= 1u; }
           }
           ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
           ptx::tcgen05_fence_after();
           const uint32_t tacc = tmem_base + (uint32_t)acc * kCout;
+          uint32_t sl = slot0;
           int s = 0;
-          for (int kh = 0; kh < P.KH; ++kh) {
-            const uint32_t srow = ring_u32 + ((gbase + (uint32_t)(j + kh)) % (uint32_t)P.R) * (uint32_t)slot_bytes;
+#pragma unroll
+          for (int kh = 0; kh < KH; ++kh) {
+            const uint32_t row_lo = a_lo0 + sl * slot_u;
             if (pair_mode) {
-              for (int pp = 0; pp < KWP; ++pp, ++s) {
-                const uint64_t da = ptx::make_smem_desc(srow + (uint32_t)(2 * pp) * 16u, 16, 128, 0);
-                const uint64_t db = ptx::make_smem_desc(wimg_u32 + (uint32_t)s * kCout * 32u, 128, 256, 0);
-                ptx::umma_bf16(tacc, da, db, idesc, s != 0 ? 1u : 0u);
-              }
+#pragma unroll
+              for (int pp = 0; pp < KWP; ++pp, ++s)
+                ptx::umma_bf16(tacc, halo_desc(row_lo + (uint32_t)(2 * pp), a_hi),
+                               halo_desc(b_lo0 + (uint32_t)(s * kCout * 2), b_hi), idesc, s != 0 ? 1u : 0u);
             } else {
-              for (int kw = 0; kw < P.KW; ++kw)
-                for (int q = 0; q < PQ; ++q, ++s) {
-                  const uint64_t da = ptx::make_smem_desc(srow + (uint32_t)(2 * q) * (uint32_t)plane_bytes + (uint32_t)kw * 16u,
-                                                          (uint32_t)plane_bytes, 128, 0);
-                  const uint64_t db = ptx::make_smem_desc(wimg_u32 + (uint32_t)s * kCout * 32u, 128, 256, 0);
-                  ptx::umma_bf16(tacc, da, db, idesc, s != 0 ? 1u : 0u);
-                }
+#pragma unroll
+              for (int kw = 0; kw < KW; ++kw)
+#pragma unroll
+                for (int q = 0; q < PQ; ++q, ++s)
+                  ptx::umma_bf16(tacc, halo_desc(row_lo + (uint32_t)(2 * q) * ((uint32_t)plane_bytes >> 4) + (uint32_t)kw, a_hi),
+                                 halo_desc(b_lo0 + (uint32_t)(s * kCout * 2), b_hi), idesc, s != 0 ? 1u : 0u);
             }
+            if (++sl == R) sl = 0;
           }
-          ptx::umma_commit(&empty_bar[(gbase + (uint32_t)j) % (uint32_t)P.R]);     // oldest row is no longer needed
+          ptx::umma_commit(&empty_bar[slot0]);                   // the oldest row of the window is no longer needed
           ptx::umma_commit(&tfull_bar[acc]);
-          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          if (++slot0 == R) slot0 = 0;
+          if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
         }
-        for (int t = 0; t < P.KH - 1; ++t) ptx::umma_commit(&empty_bar[(gbase + (uint32_t)(rows + t)) % (uint32_t)P.R]);
-        gbase += (uint32_t)(rows + P.KH - 1);
+        for (int t = 0; t < KH - 1; ++t) {                       // rows only the finished chunk used
+          ptx::umma_commit(&empty_bar[slot0]);
+          if (++slot0 == R) slot0 = 0;
+        }
       }
     }
   } else {
@@ -187,7 +210,7 @@ conv_halo_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParam
         ptx::tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) {
           float f[16];
@@ -264,14 +287,17 @@ conv_halo_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParam
 // ------------------------------------------------------------------------------------------------------------
 // weight gradient: dW[co][kh][kw][ci] += sum_{n,y,x} dY[n,y,x,co] * X[n, y+kh-pad, x+kw-pad, ci]
 // TMEM block (kh, plane p) = 128 lanes (m = kw*8 + ci%8, kw < 16) x Cout columns.
-__global__ void __launch_bounds__(192)
+template <int KS, int CIN>
+__global__ void __launch_bounds__(192, 4)
 conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                        const HaloParams P, const uint32_t tmem_cols_pow2) {
+  const int KH = KS > 0 ? KS : P.KH;
+  const int NP = CIN > 0 ? (CIN >> 3) : P.P;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  const int plane_bytes = P.BW * 16;
-  const int slot_bytes = P.P * plane_bytes;
-  const int dy_plane_bytes = 128 * 16;
+  constexpr int plane_bytes = 144 * 16;                     // P.BW == 144 always for the weight gradient
+  const int slot_bytes = NP * plane_bytes;
+  constexpr int dy_plane_bytes = 128 * 16;
   const int dy_slot_bytes = P.PO * dy_plane_bytes;
   uint8_t* ring = smem;
   uint8_t* dyring = ring + (size_t)P.R * slot_bytes;
@@ -302,31 +328,30 @@ conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 
   if (warp == 0) {
     if (ptx::elect_one()) {
-      uint32_t g = 0, gd = 0;
+      uint32_t slot = 0, par = 0, ds = 0, dpar = 0;
       for (int c = blockIdx.x; c < P.total_chunks; c += gridDim.x) {
         const int col = c / P.chunks_per_col, cy = c - col * P.chunks_per_col;
         const int n = col / P.strips, xs = col - n * P.strips;
         const int y0 = cy * P.rows_per_chunk;
         const int rows = min(P.rows_per_chunk, P.H - y0);
         const int x0 = xs * 128;
-        // input row i feeds output rows i-KH+1..i: interleave so that dY row j is requested right after the last
-        // input row it needs
-        for (int i = 0; i < rows + P.KH - 1; ++i, ++g) {
-          const uint32_t slot = g % (uint32_t)P.R, par = (g / (uint32_t)P.R) & 1u;
+        // dY row j is requested right after the last input row (j + KH - 1) it needs
+        for (int i = 0; i < rows + KH - 1; ++i) {
           ptx::mbar_wait(&empty_bar[slot], par ^ 1u);
           ptx::mbar_expect_tx(&full_bar[slot], (uint32_t)slot_bytes);
           uint8_t* dst = ring + (size_t)slot * slot_bytes;
-          for (int p = 0; p < P.P; ++p)
+#pragma unroll
+          for (int p = 0; p < NP; ++p)
             ptx::tma_load_4d(dst + p * plane_bytes, &tmap_x, &full_bar[slot], p * 8, x0 - P.pad, y0 - P.pad + i, n);
-          const int j = i - (P.KH - 1);
+          if (++slot == (uint32_t)P.R) { slot = 0; par ^= 1u; }
+          const int j = i - (KH - 1);
           if (j >= 0) {
-            const uint32_t ds = gd % (uint32_t)P.RD, dpar = (gd / (uint32_t)P.RD) & 1u;
             ptx::mbar_wait(&dempty_bar[ds], dpar ^ 1u);
             ptx::mbar_expect_tx(&dfull_bar[ds], (uint32_t)dy_slot_bytes);
             uint8_t* dd = dyring + (size_t)ds * dy_slot_bytes;
             for (int p = 0; p < P.PO; ++p)
               ptx::tma_load_4d(dd + p * dy_plane_bytes, &tmap_dy, &dfull_bar[ds], p * 8, x0, y0 + j, n);
-            ++gd;
+            if (++ds == (uint32_t)P.RD) { ds = 0; dpar ^= 1u; }
           }
         }
       }
@@ -334,42 +359,52 @@ conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   } else if (warp == 1) {
     if (ptx::elect_one()) {
       const uint32_t idesc = ptx::make_idesc_bf16(128, P.Cout, 1, 1);
-      const uint32_t ring_u32 = ptx::smem_u32(ring), dy_u32 = ptx::smem_u32(dyring);
-      uint32_t gbase = 0, ready = 0, gd = 0;
-      bool first = true;
+      const uint32_t R = (uint32_t)P.R, RD = (uint32_t)P.RD;
+      const uint32_t slot_u = (uint32_t)slot_bytes >> 4, dy_slot_u = (uint32_t)dy_slot_bytes >> 4;
+      // A: MN-major, MN chunk (pixel shift) stride 16 B ("SBO"), K group (8 px) stride 128 B ("LBO")
+      const uint32_t a_lo0 = (ptx::smem_u32(ring) >> 4) | (8u << 16);
+      // B: MN-major, MN chunk (8 output channels) stride = dY plane, K group stride 128 B
+      const uint32_t b_lo0 = (ptx::smem_u32(dyring) >> 4) | (8u << 16);
+      constexpr uint32_t a_hi = halo_desc_hi(16), b_hi = halo_desc_hi(dy_plane_bytes);
+      uint32_t slot0 = 0, rslot = 0, rpar = 0, ds = 0, dpar = 0;
+      uint32_t accum = 0;
       for (int c = blockIdx.x; c < P.total_chunks; c += gridDim.x) {
         const int cy = c % P.chunks_per_col;
         const int y0 = cy * P.rows_per_chunk;
         const int rows = min(P.rows_per_chunk, P.H - y0);
-        for (int j = 0; j < rows; ++j, ++gd) {
-          while (ready < gbase + (uint32_t)(j + P.KH)) {
-            ptx::mbar_wait(&full_bar[ready % (uint32_t)P.R], (ready / (uint32_t)P.R) & 1u);
-            ++ready;
+        for (int j = 0; j < rows; ++j) {
+          const int need = j == 0 ? KH : 1;
+          for (int t = 0; t < need; ++t) {
+            ptx::mbar_wait(&full_bar[rslot], rpar);
+            if (++rslot == R) { rslot = 0; rpar ^= 1u; }
           }
-          const uint32_t ds = gd % (uint32_t)P.RD;
-          ptx::mbar_wait(&dfull_bar[ds], (gd / (uint32_t)P.RD) & 1u);
+          ptx::mbar_wait(&dfull_bar[ds], dpar);
           ptx::tcgen05_fence_after();
-          const uint32_t sdy = dy_u32 + ds * (uint32_t)dy_slot_bytes;
-          for (int kh = 0; kh < P.KH; ++kh) {
-            const uint32_t srow = ring_u32 + ((gbase + (uint32_t)(j + kh)) % (uint32_t)P.R) * (uint32_t)slot_bytes;
-            for (int p = 0; p < P.P; ++p) {
-              const uint32_t tacc = tmem_base + (uint32_t)((kh * P.P + p) * P.Cout);
+          const uint32_t dy_lo = b_lo0 + ds * dy_slot_u;
+          uint32_t sl = slot0;
 #pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                // A: MN-major, MN chunk (pixel shift) stride 16 B, K group (8 px) stride 128 B
-                const uint64_t da = ptx::make_smem_desc(srow + (uint32_t)p * (uint32_t)plane_bytes + (uint32_t)t * 256u, 128, 16, 0);
-                // B: MN-major, MN chunk (8 output channels) stride = dY plane, K group stride 128 B
-                const uint64_t db = ptx::make_smem_desc(sdy + (uint32_t)t * 256u, 128, (uint32_t)dy_plane_bytes, 0);
-                ptx::umma_bf16(tacc, da, db, idesc, (first && t == 0) ? 0u : 1u);
-              }
+          for (int kh = 0; kh < KH; ++kh) {
+            const uint32_t row_lo = a_lo0 + sl * slot_u;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              const uint32_t tacc = tmem_base + (uint32_t)((kh * NP + p) * P.Cout);
+#pragma unroll
+              for (int t = 0; t < 8; ++t)
+                ptx::umma_bf16(tacc, halo_desc(row_lo + (uint32_t)(p * (plane_bytes >> 4) + t * 16), a_hi),
+                               halo_desc(dy_lo + (uint32_t)(t * 16), b_hi), idesc, t == 0 ? accum : 1u);
             }
+            if (++sl == R) sl = 0;
           }
-          first = false;
-          ptx::umma_commit(&empty_bar[(gbase + (uint32_t)j) % (uint32_t)P.R]);
+          accum = 1u;
+          ptx::umma_commit(&empty_bar[slot0]);
           ptx::umma_commit(&dempty_bar[ds]);
+          if (++slot0 == R) slot0 = 0;
+          if (++ds == RD) { ds = 0; dpar ^= 1u; }
         }
-        for (int t = 0; t < P.KH - 1; ++t) ptx::umma_commit(&empty_bar[(gbase + (uint32_t)(rows + t)) % (uint32_t)P.R]);
-        gbase += (uint32_t)(rows + P.KH - 1);
+        for (int t = 0; t < KH - 1; ++t) {
+          ptx::umma_commit(&empty_bar[slot0]);
+          if (++slot0 == R) slot0 = 0;
+        }
       }
       ptx::umma_commit(done_bar);
     }
@@ -436,16 +471,28 @@ static bool halo_wgrad_eligible(const c3d_conv_desc* d) {
   if (d->KH * (d->Cin / 8) * d->Cout > 512) return false;
   return true;
 }
-static void halo_chunking(const c3d_conv_desc* d, HaloParams* P, int* grid) {
+// ring depth: the TMA rows are only 2-4 KB, so hiding ~1.5 us of L2/HBM latency at ~40 B/ns per SM needs tens of rows in
+// flight; C3D_HALO_PREFETCH overrides the number of rows beyond the filter window
+static int halo_ring_rows(int window, int slot_bytes, int budget) {
+  static const char* env = getenv("C3D_HALO_PREFETCH");
+  int pf = budget / slot_bytes - window;
+  if (pf > 48) pf = 48;
+  if (env) pf = atoi(env);
+  if (pf < 2) pf = 2;
+  return window + pf;
+}
+static int halo_fwd_ctas_per_sm(int Cout) { return Cout == 16 ? 3 : 2; }     // = __launch_bounds__ of the instances
+static void halo_chunking(const c3d_conv_desc* d, HaloParams* P, int ctas_per_sm, int* grid) {
   P->strips = (d->W + 127) / 128;
   P->rows_per_chunk = d->H < 32 ? d->H : 32;
   P->chunks_per_col = (d->H + P->rows_per_chunk - 1) / P->rows_per_chunk;
   P->total_chunks = d->N * P->strips * P->chunks_per_col;
-  *grid = P->total_chunks < kNumSMs ? P->total_chunks : kNumSMs;
+  const int slots = kNumSMs * ctas_per_sm;
+  *grid = P->total_chunks < slots ? P->total_chunks : slots;
 }
 static int halo_fwd_grid(const c3d_conv_desc* d) {
   HaloParams P; int grid;
-  halo_chunking(d, &P, &grid);
+  halo_chunking(d, &P, halo_fwd_ctas_per_sm(d->Cout), &grid);
   return grid;
 }
 static CUresult halo_tensormap(PFN_encodeTiled enc, CUtensorMap* m, const void* base, int C, int W, int H, int N, int boxw) {
@@ -458,6 +505,19 @@ static CUresult halo_tensormap(PFN_encodeTiled enc, CUtensorMap* m, const void* 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
+template <int CH, int KS, int CIN>
+static int32_t launch_halo_fwd_inst(const CUtensorMap& mx, const HaloParams& P, int grid, size_t smem, cudaStream_t st) {
+  auto kern = conv_halo_fwd_kernel<CH, KS, CIN>;
+  static size_t cur = 0;
+  if (smem > cur) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(C3D_ECUDA, "halo smem attr: %s", cudaGetErrorString(e));
+    cur = smem;
+  }
+  kern<<<grid, 192, smem, st>>>(mx, P);
+  return check_launch("conv_halo_fwd_kernel");
+}
+
 static int32_t launch_halo_fwd(const c3d_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                                float* stats, cudaStream_t st) {
   PFN_encodeTiled enc = get_encode();
@@ -465,11 +525,12 @@ static int32_t launch_halo_fwd(const c3d_conv_desc* d, const void* x, const void
   HaloParams P;
   memset(&P, 0, sizeof(P));
   int grid;
-  halo_chunking(d, &P, &grid);
+  const int ctas = halo_fwd_ctas_per_sm(d->Cout);
+  halo_chunking(d, &P, ctas, &grid);
   P.N = d->N; P.H = d->H; P.W = d->W; P.Cin = d->Cin; P.Cout = d->Cout; P.KH = d->KH; P.KW = d->KW; P.pad = d->pad;
   P.P = d->Cin / 8;
   P.BW = (128 + d->KW - 1 + 7) / 8 * 8;
-  P.R = d->KH + 4;
+  P.R = halo_ring_rows(d->KH, P.P * P.BW * 16, ctas == 3 ? 48 * 1024 : 64 * 1024);
   P.ksteps = d->Cin == 8 ? d->KH * ((d->KW + 1) / 2) : d->KH * d->KW * (d->Cin / 16);
   P.w = static_cast<const bf16*>(w); P.bias = bias; P.relu = d->relu; P.out_fp32 = d->out_fp32; P.out = y;
   P.out_pix_stride = d->y_pix_stride ? d->y_pix_stride : d->Cout;
@@ -483,29 +544,34 @@ static int32_t launch_halo_fwd(const c3d_conv_desc* d, const void* x, const void
   CUresult r = halo_tensormap(enc, &mx, x, d->Cin, d->W, d->H, d->N, P.BW);
   if (r != CUDA_SUCCESS) return set_error(C3D_ECUDA, "encode halo x tensormap failed: %d", (int)r);
   const int wimg = (P.ksteps * d->Cout * 32 + 127) & ~127;
-  const size_t smem = 128 + (size_t)wimg + (size_t)P.R * P.P * P.BW * 16 + (size_t)(2 * P.R + 4) * 8 + 16 +
+  const size_t smem = 128 + (size_t)wimg + (size_t)P.R * P.P * P.BW * 16 + (size_t)(2 * P.R + 8) * 8 + 16 +
                       4 * 2 * d->Cout * sizeof(float) + 64;
   if (smem > 200 * 1024) return set_error(C3D_EINVAL, "halo conv: smem %zu too large", smem);
-  if (d->Cout == 16) {
-    auto kern = conv_halo_fwd_kernel<1>;
-    static size_t cur = 0;
-    if (smem > cur) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return set_error(C3D_ECUDA, "halo smem attr: %s", cudaGetErrorString(e));
-      cur = smem;
-    }
-    kern<<<grid, 192, smem, st>>>(mx, P);
-  } else {
-    auto kern = conv_halo_fwd_kernel<2>;
-    static size_t cur = 0;
-    if (smem > cur) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return set_error(C3D_ECUDA, "halo smem attr: %s", cudaGetErrorString(e));
-      cur = smem;
-    }
-    kern<<<grid, 192, smem, st>>>(mx, P);
+#define C3D_HALO_F(ch, ks, cin) \
+  if (d->Cout == ch * 16 && d->KH == ks && d->Cin == cin) return launch_halo_fwd_inst<ch, ks, cin>(mx, P, grid, smem, st);
+  C3D_HALO_F(1, 7, 8)
+  C3D_HALO_F(1, 3, 16)
+  C3D_HALO_F(1, 3, 32)
+  C3D_HALO_F(2, 7, 8)
+  C3D_HALO_F(2, 3, 16)
+  C3D_HALO_F(2, 3, 32)
+#undef C3D_HALO_F
+  if (d->Cout == 16) return launch_halo_fwd_inst<1, 0, 0>(mx, P, grid, smem, st);
+  return launch_halo_fwd_inst<2, 0, 0>(mx, P, grid, smem, st);
+}
+
+template <int KS, int CIN>
+static int32_t launch_halo_wgrad_inst(const CUtensorMap& mx, const CUtensorMap& mdy, const HaloParams& P, int grid, size_t smem,
+                                      uint32_t tcols, cudaStream_t st) {
+  auto kern = conv_halo_wgrad_kernel<KS, CIN>;
+  static size_t cur = 0;
+  if (smem > cur) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(C3D_ECUDA, "halo wgrad smem attr: %s", cudaGetErrorString(e));
+    cur = smem;
   }
-  return check_launch("conv_halo_fwd_kernel");
+  kern<<<grid, 192, smem, st>>>(mx, mdy, P, tcols);
+  return check_launch("conv_halo_wgrad_kernel");
 }
 
 static int32_t launch_halo_wgrad(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, int oihw,
@@ -515,32 +581,27 @@ static int32_t launch_halo_wgrad(const c3d_conv_desc* d, const void* x, const vo
   HaloParams P;
   memset(&P, 0, sizeof(P));
   int grid;
-  halo_chunking(d, &P, &grid);
+  const int cols = d->KH * (d->Cin / 8) * d->Cout;
+  const uint32_t tcols = cols <= 128 ? 128u : (cols <= 256 ? 256u : 512u);
+  halo_chunking(d, &P, (int)(512u / tcols), &grid);           // co-resident CTAs are bounded by their TMEM blocks
   P.N = d->N; P.H = d->H; P.W = d->W; P.Cin = d->Cin; P.Cout = d->Cout; P.KH = d->KH; P.KW = d->KW; P.pad = d->pad;
   P.P = d->Cin / 8; P.PO = d->Cout / 8;
   P.BW = 144;
-  P.R = d->KH + 4;
-  P.RD = 4;
+  P.R = halo_ring_rows(d->KH, P.P * P.BW * 16, 32 * 1024);
+  P.RD = halo_ring_rows(0, P.PO * 128 * 16, 16 * 1024);
   P.dw = dw; P.oihw = oihw;
   CUtensorMap mx, mdy;
   CUresult r = halo_tensormap(enc, &mx, x, d->Cin, d->W, d->H, d->N, P.BW);
   if (r != CUDA_SUCCESS) return set_error(C3D_ECUDA, "encode halo x tensormap failed: %d", (int)r);
   r = halo_tensormap(enc, &mdy, dy, d->Cout, d->W, d->H, d->N, 128);
   if (r != CUDA_SUCCESS) return set_error(C3D_ECUDA, "encode halo dy tensormap failed: %d", (int)r);
-  const int cols = d->KH * P.P * d->Cout;
-  const uint32_t tcols = cols <= 128 ? 128u : (cols <= 256 ? 256u : 512u);
   const size_t smem = 128 + (size_t)P.R * P.P * P.BW * 16 + (size_t)P.RD * P.PO * 128 * 16 +
                       (size_t)(2 * P.R + 2 * P.RD + 1) * 8 + 16 + 64;
   if (smem > 200 * 1024) return set_error(C3D_EINVAL, "halo wgrad: smem %zu too large", smem);
-  auto kern = conv_halo_wgrad_kernel;
-  static size_t cur = 0;
-  if (smem > cur) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error(C3D_ECUDA, "halo wgrad smem attr: %s", cudaGetErrorString(e));
-    cur = smem;
-  }
-  kern<<<grid, 192, smem, st>>>(mx, mdy, P, tcols);
-  return check_launch("conv_halo_wgrad_kernel");
+  if (d->KH == 7 && d->Cin == 8) return launch_halo_wgrad_inst<7, 8>(mx, mdy, P, grid, smem, tcols, st);
+  if (d->KH == 3 && d->Cin == 16) return launch_halo_wgrad_inst<3, 16>(mx, mdy, P, grid, smem, tcols, st);
+  if (d->KH == 3 && d->Cin == 32) return launch_halo_wgrad_inst<3, 32>(mx, mdy, P, grid, smem, tcols, st);
+  return launch_halo_wgrad_inst<0, 0>(mx, mdy, P, grid, smem, tcols, st);
 }
 
 }  // namespace c3d
