@@ -229,13 +229,13 @@ def run_ours(args):
     trainer = FlatSGDTrainer(cfg, model)
     B, S = args.batch, args.size
     # two distinct synthetic batches, alternated so that consecutive steps never re-read the same inputs from L2
-    host = [synth.make_batch(B, S, S, num_gt=8, seed=100 + rank * 7 + j) for j in range(2)]
+    host = [synth.make_batch(B, S, S, num_gt=8, seed=100 + rank * 7 + j, image_dtype=torch.uint8) for j in range(2)]
     for hb in host:
         for it in hb:
             it["image"] = it["image"].pin_memory()
     resident = [[{**it, "image": it["image"].to(dev), "gt": {k: v.to(dev) for k, v in it["gt"].items()}} for it in hb]
                 for hb in host]
-    h2d = sum(it["image"].numel() * 4 for it in host[0]) + sum(sum(v.numel() * v.element_size() for v in it["gt"].values())
+    h2d = sum(it["image"].numel() * it["image"].element_size() for it in host[0]) + sum(sum(v.numel() * v.element_size() for v in it["gt"].values())
                                                                for it in host[0])
 
     def timed(batches, steps, read_loss):

@@ -148,11 +148,18 @@ int32_t c3d_maxpool2_bwd(const void* x, const void* dy, void* dx, int32_t N, int
 /* (3,H,W) fp32 BGR image -> (Hp,Wp,Cp) bf16 NHWC slot: (x-mean)/std in channels 0..2, zeros elsewhere */
 int32_t c3d_preprocess_image(const float* img, int32_t H, int32_t W, void* out_slot, int32_t Hp, int32_t Wp,
                              int32_t Cp, const float* mean3_host, const float* std3_host, void* stream);
+/* same for the uint8 (3,H,W) image tensor detectron2's DatasetMapper produces (dataset_mapper.py: image as uint8) */
+int32_t c3d_preprocess_image_u8(const uint8_t* img, int32_t H, int32_t W, void* out_slot, int32_t Hp, int32_t Wp,
+                                int32_t Cp, const float* mean3_host, const float* std3_host, void* stream);
 /* flag |= 1 if any gradient element is NaN/Inf */
 int32_t c3d_grad_finite(const float* g, int64_t n, int32_t* flag, void* stream);
 /* torch.optim.SGD(momentum, weight_decay) over a flat arena; no-op if *skip_flag != 0 */
 int32_t c3d_sgd_momentum(float* p, const float* g, float* mom, int64_t n, float lr, float momentum,
                          float weight_decay, float grad_scale, const int32_t* skip_flag, void* stream);
+/* same update with the learning rate read from device memory at run time (schedule changes without re-recording a
+ * captured CUDA graph of the step) */
+int32_t c3d_sgd_momentum_dev(float* p, const float* g, float* mom, int64_t n, const float* lr_dev, float momentum,
+                             float weight_decay, float grad_scale, const int32_t* skip_flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-level ROIAlign (aligned=True, sampling_ratio 0) on NHWC bf16 FPN maps.
@@ -186,6 +193,22 @@ int32_t c3d_nms_batched(const float* boxes, const int32_t* nvalid, const float* 
                         int32_t trick_max_numel, int32_t B, int32_t n, float iou_thresh,
                         int32_t max_keep, int32_t* keep_idx, int32_t* keep_cnt, void* workspace,
                         size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * RPN anchor <-> ground-truth matching for a whole batch (two passes, GT boxes of an image in shared memory).
+ * Replaces detectron2 pairwise_iou + Matcher(thresholds, allow_low_quality_matches=True) and the ignore-region IoA
+ * of cubercnn/modeling/proposal_generator/rpn.py:93-105 (label_and_sample_anchors), :286-330.
+ *   anchors [A][4], gt_boxes [B][G][4] (x1,y1,x2,y2 fp32, padded), gt_valid / gt_ign [B][G] (0/1 bytes)
+ *   matched_idx [B][A] int64: first GT of maximal IoU among valid ones (0 if none)
+ *   matched_iou [B][A]: that IoU (0 if none);  max_ioa [B][A]: max over ignore regions of inter / anchor area
+ *   labels [B][A] int8: 1 if IoU >= fg_thresh or the anchor attains the maximum IoU of some valid GT, else 0
+ *   best_idx [B][G] int32: first anchor attaining that GT's maximum (A for non-valid GTs)
+ *   rowmax_ws [B][G] int32 scratch.  Bit-identical to the fp32 torch formulation (explicit rn arithmetic).
+ * ------------------------------------------------------------------------------------------ */
+int32_t c3d_anchor_match(const float* anchors, int64_t A, const float* gt_boxes, const uint8_t* gt_valid,
+                         const uint8_t* gt_ign, int32_t B, int32_t G, float fg_thresh, int64_t* matched_idx,
+                         float* matched_iou, int8_t* labels, float* max_ioa, int32_t* best_idx, int32_t* rowmax_ws,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * CubeHead decode + disentangled 3D corner losses, fused forward / backward (one thread per RoI).

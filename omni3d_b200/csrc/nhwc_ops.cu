@@ -386,7 +386,8 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
 }
 
 // ---- image normalisation: (3,H,W) fp32 BGR -> (Hp,Wp,Cp) bf16 NHWC slot, zero padded --------------
-__global__ void preprocess_kernel(const float* __restrict__ img, int H, int W, bf16* __restrict__ out, int Hp,
+template <typename T>
+__global__ void preprocess_kernel(const T* __restrict__ img, int H, int W, bf16* __restrict__ out, int Hp,
                                   int Wp, int Cp, float m0, float m1, float m2, float s0, float s1, float s2) {
   const long long total = (long long)Hp * Wp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -395,9 +396,9 @@ __global__ void preprocess_kernel(const float* __restrict__ img, int H, int W, b
     float v0 = 0.f, v1 = 0.f, v2 = 0.f;
     if (h < H && w < W) {
       const long long o = (long long)h * W + w;
-      v0 = (img[o] - m0) / s0;
-      v1 = (img[(long long)H * W + o] - m1) / s1;
-      v2 = (img[2LL * H * W + o] - m2) / s2;
+      v0 = ((float)img[o] - m0) / s0;
+      v1 = ((float)img[(long long)H * W + o] - m1) / s1;
+      v2 = ((float)img[2LL * H * W + o] - m2) / s2;
     }
     bf16* dst = out + i * Cp;
     for (int c = 0; c < Cp; c += 8) {
@@ -422,9 +423,10 @@ __global__ void grad_finite_kernel(const float* __restrict__ g, long long n, int
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom,
-                                    long long n, float lr, float momentum, float wd, float grad_scale,
-                                    const int* __restrict__ skip_flag) {
+                                    long long n, float lr, const float* __restrict__ lr_dev, float momentum, float wd,
+                                    float grad_scale, const int* __restrict__ skip_flag) {
   if (skip_flag && *skip_flag) return;
+  if (lr_dev) lr = *lr_dev;                  // learning rate in device memory: the launch can live in a CUDA graph
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float d = g[i] * grad_scale + wd * p[i];
     float b = momentum * mom[i] + d;        // torch.optim.SGD: buf = momentum*buf + d (dampening 0)
@@ -517,10 +519,19 @@ extern "C" int32_t c3d_preprocess_image(const float* img, int32_t H, int32_t W, 
                                         int32_t Wp, int32_t Cp, const float* mean3_host, const float* std3_host,
                                         void* stream) {
   C3D_REQ(img && out_slot && mean3_host && std3_host && Cp % 8 == 0 && Hp >= H && Wp >= W, "preprocess: bad args");
-  preprocess_kernel<<<grid_for((long long)Hp * Wp, 256), 256, 0, (cudaStream_t)stream>>>(
+  preprocess_kernel<float><<<grid_for((long long)Hp * Wp, 256), 256, 0, (cudaStream_t)stream>>>(
       img, H, W, (bf16*)out_slot, Hp, Wp, Cp, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0],
       std3_host[1], std3_host[2]);
   return check_launch("preprocess");
+}
+extern "C" int32_t c3d_preprocess_image_u8(const uint8_t* img, int32_t H, int32_t W, void* out_slot, int32_t Hp,
+                                           int32_t Wp, int32_t Cp, const float* mean3_host, const float* std3_host,
+                                           void* stream) {
+  C3D_REQ(img && out_slot && mean3_host && std3_host && Cp % 8 == 0 && Hp >= H && Wp >= W, "preprocess: bad args");
+  preprocess_kernel<uint8_t><<<grid_for((long long)Hp * Wp, 256), 256, 0, (cudaStream_t)stream>>>(
+      img, H, W, (bf16*)out_slot, Hp, Wp, Cp, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0],
+      std3_host[1], std3_host[2]);
+  return check_launch("preprocess_u8");
 }
 extern "C" int32_t c3d_grad_finite(const float* g, int64_t n, int32_t* flag, void* stream) {
   C3D_REQ(g && flag, "grad_finite: bad args");
@@ -532,8 +543,17 @@ extern "C" int32_t c3d_sgd_momentum(float* p, const float* g, float* mom, int64_
                                     float weight_decay, float grad_scale, const int32_t* skip_flag, void* stream) {
   C3D_REQ(p && g && mom, "sgd: bad args");
   if (n == 0) return C3D_OK;
-  sgd_momentum_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, mom, n, lr, momentum, weight_decay,
-                                                                           grad_scale, skip_flag);
+  sgd_momentum_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, mom, n, lr, nullptr, momentum,
+                                                                           weight_decay, grad_scale, skip_flag);
+  return check_launch("sgd");
+}
+extern "C" int32_t c3d_sgd_momentum_dev(float* p, const float* g, float* mom, int64_t n, const float* lr_dev,
+                                        float momentum, float weight_decay, float grad_scale,
+                                        const int32_t* skip_flag, void* stream) {
+  C3D_REQ(p && g && mom && lr_dev, "sgd: bad args");
+  if (n == 0) return C3D_OK;
+  sgd_momentum_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, mom, n, 0.f, lr_dev, momentum,
+                                                                           weight_decay, grad_scale, skip_flag);
   return check_launch("sgd");
 }
 

@@ -68,31 +68,53 @@ class RCNN3D(nn.Module):
         return self.pixel_mean.device
 
     def preprocess_image(self, batched_inputs):
-        imgs = [x["image"].to(self.device, non_blocking=True).float().contiguous() for x in batched_inputs]
+        st = self.stage_inputs(batched_inputs, with_gt=False)
+        return self._normalize(st), st["sizes"]
+
+    def _normalize(self, st):
+        return Kx.preprocess_images(st["images"], self._mean, self._std, self.backbone.size_divisibility,
+                                    cpad=getattr(self.backbone.bottom_up, "stem_cpad", 16))
+
+    def stage_inputs(self, batched_inputs, with_gt=True):
+        """ALL host->device traffic of a step, and nothing else: images (uint8 as the mapper emits them, or float),
+        one (B,12) row of per-image scalars [h, w, height/h, K (9)], and the padded GT.  `forward_staged` consumes
+        only these device tensors (no host reads), so it can be recorded into a CUDA graph."""
+        dev = self.device
+        imgs = [x["image"].to(dev, non_blocking=True) for x in batched_inputs]
+        imgs = [(im if im.dtype == torch.uint8 else im.float()).contiguous() for im in imgs]
         sizes = [(int(im.shape[1]), int(im.shape[2])) for im in imgs]
-        x = Kx.preprocess_images(imgs, self._mean, self._std, self.backbone.size_divisibility,
-                                 cpad=getattr(self.backbone.bottom_up, "stem_cpad", 16))
-        return x, sizes
+        rows = [[float(h), float(w), info["height"] / h] + [float(v) for r in info["K"] for v in r]
+                for info, (h, w) in zip(batched_inputs, sizes)]
+        meta = torch.tensor(rows, dtype=torch.float32)
+        if dev.type == "cuda":
+            meta = meta.pin_memory()
+        st = {"images": imgs, "sizes": sizes, "meta": meta.to(dev, non_blocking=True)}
+        if with_gt and self.training:
+            st["gt"] = collate_gt(batched_inputs, dev)
+        return st
+
+    def forward_staged(self, st, _inject=None, batched_inputs=None):
+        x = self._normalize(st)
+        sizes, meta = st["sizes"], st["meta"]
+        hw, ratios, Ks = meta[:, :2], meta[:, 2], meta[:, 3:12].reshape(-1, 3, 3)
+        features = self.backbone(x)
+        if self.training:
+            gt = dict(st["gt"])
+            if _inject:
+                gt.update(_inject)
+            proposals, l_rpn = self.proposal_generator(features, sizes, gt, sizes_dev=hw)
+            _, losses = self.roi_heads(features, proposals, sizes, Ks, ratios, gt, im_h=hw[:, 0])
+            losses.update(l_rpn)
+            self.metrics = {**self.proposal_generator.stats, **self.roi_heads.stats}
+            return losses
+        proposals, _ = self.proposal_generator(features, sizes, None, sizes_dev=hw)
+        results, _ = self.roi_heads(features, proposals, sizes, Ks, ratios, None, im_h=hw[:, 0])
+        return self._postprocess(results, batched_inputs, sizes)
 
     def forward(self, batched_inputs, _inject=None):
         if self.device.type != "cuda":
             raise _lib.C3DError("omni3d_b200 RCNN3D runs on CUDA only (MODEL.DEVICE=cpu is the oracle's job)")
-        x, sizes = self.preprocess_image(batched_inputs)
-        ratios = [info["height"] / s[0] for info, s in zip(batched_inputs, sizes)]
-        Ks = [info["K"] for info in batched_inputs]
-        features = self.backbone(x)
-        if self.training:
-            gt = collate_gt(batched_inputs, self.device)
-            if _inject:
-                gt.update(_inject)
-            proposals, l_rpn = self.proposal_generator(features, sizes, gt)
-            _, losses = self.roi_heads(features, proposals, sizes, Ks, ratios, gt)
-            losses.update(l_rpn)
-            self.metrics = {**self.proposal_generator.stats, **self.roi_heads.stats}
-            return losses
-        proposals, _ = self.proposal_generator(features, sizes, None)
-        results, _ = self.roi_heads(features, proposals, sizes, Ks, ratios, None)
-        return self._postprocess(results, batched_inputs, sizes)
+        return self.forward_staged(self.stage_inputs(batched_inputs), _inject, batched_inputs)
 
     inference = forward
 

@@ -125,6 +125,9 @@ class ROIHeads3D(nn.Module):
         FastRCNNOutputs(self.box_head.out_dim, K)                 # RNG parity with roi_heads.py:151
         self.box_predictor = FastRCNNOutputs(self.box_head.out_dim, K)
         assert H.POOLER_RESOLUTION == self.pooled
+        # same ROIAlign for both heads (Base.yaml:66-68,78-80): the cube head's RoIs are a prefix of the box head's sampled
+        # RoIs, so its pooled features are a slice of the box head's instead of a second ROIAlign forward + backward
+        self.share_pool = (H.POOLER_SAMPLING_RATIO == BH.POOLER_SAMPLING_RATIO and H.POOLER_TYPE == BH.POOLER_TYPE)
         self.cube_head = CubeHead(cfg, in_dim)
         if priors is not None:
             self.priors_dims_per_cat = nn.Parameter(torch.FloatTensor(priors["priors_dims_per_cat"]).unsqueeze(0))
@@ -330,22 +333,26 @@ class ROIHeads3D(nn.Module):
 
     def per_box_camera(self, Ks, ratios, im_h, counts_or_S, B, device):
         """scaled intrinsics per box and the virtual->real depth factor (roi_heads.py:372-404)."""
-        K = torch.stack([torch.as_tensor(k, dtype=torch.float32) for k in Ks]).to(device)         # (B,3,3)
-        r = torch.as_tensor(ratios, dtype=torch.float32, device=device)
+        if torch.is_tensor(Ks):
+            K = Ks
+        else:
+            K = torch.stack([torch.as_tensor(k, dtype=torch.float32) for k in Ks]).to(device)     # (B,3,3)
+        r = ratios if torch.is_tensor(ratios) else torch.as_tensor(ratios, dtype=torch.float32, device=device)
         Ks_scaled = K / r[:, None, None]
         Ks_scaled[:, 2, 2] = 1
-        h = torch.as_tensor(im_h, dtype=torch.float32, device=device)
+        h = im_h if torch.is_tensor(im_h) else torch.as_tensor(im_h, dtype=torch.float32, device=device)
         v2r = (h * K[:, 1, 1]) / (self.virtual_focal * (h * r))
         rep = lambda t: t.repeat_interleave(counts_or_S, dim=0)
         return rep(Ks_scaled), rep(v2r), rep(r)
 
     # -- forward ----------------------------------------------------------------------------------------
-    def forward(self, features, proposals, image_sizes, Ks, ratios, gt=None):
+    def forward(self, features, proposals, image_sizes, Ks, ratios, gt=None, im_h=None):
         feats = [features[f] for f in self.in_features]
         prop_boxes, prop_scores, prop_count = proposals
         B = prop_boxes.shape[0]
         dev = prop_boxes.device
-        im_h = [s[0] for s in image_sizes]
+        if im_h is None:
+            im_h = [s[0] for s in image_sizes]
         if self.training:
             smp = self.label_and_sample_proposals(prop_boxes, prop_count, gt)
             x = self.pool(feats, smp["boxes"], smp["valid"])
@@ -355,7 +362,10 @@ class ROIHeads3D(nn.Module):
             K = self.num_classes
             fb, fc_, fv = smp["boxes"][:, :Fc], smp["classes"][:, :Fc], smp["valid"][:, :Fc]
             fv = fv & (fc_ >= 0) & (fc_ < K)
-            xc = self.pool(feats, fb, fv)
+            if self.share_pool:
+                xc = x.view(B, -1, x.shape[-1])[:, :Fc].reshape(B * Fc, -1)
+            else:
+                xc = self.pool(feats, fb, fv)
             Kb, v2r, _ = self.per_box_camera(Ks, ratios, im_h, Fc, B, dev)
             raw = self.cube_outputs(xc, fc_.reshape(-1))
             cube_fn = self.cube_losses_fused if self.fused_cube else self.cube_losses

@@ -183,13 +183,23 @@ class RPNWithIgnore(nn.Module):
 
     # -- labels -----------------------------------------------------------------------------------
     @torch.no_grad()
-    def match_anchors(self, anchors, gt_boxes, gt_valid):
-        """anchors (A,4); gt_boxes (B,G,4) padded; gt_valid (B,G) bool (valid & not ignore).
-        -> matched_idx (B,A), matched_iou (B,A), labels (B,A) int8 in {0,1}, best (B,A) bool."""
+    def match_anchors(self, anchors, gt_boxes, gt_valid, gt_ign=None):
+        """anchors (A,4); gt_boxes (B,G,4) padded; gt_valid (B,G) bool (valid & not ignore); gt_ign (B,G) ignore regions.
+        -> matched_idx (B,A), matched_iou (B,A), labels (B,A) int8 in {0,1}, best (B,A) bool, max IoA with ignore
+        regions (B,A).  CUDA: two c3d_anchor_match passes; CPU (host-logic tests): the same formulas in torch."""
+        if gt_ign is None:
+            gt_ign = torch.zeros_like(gt_valid)
+        lo = self.iou_thresholds[-1]
+        if anchors.is_cuda:
+            from .. import kernels as Kx
+            idx, vals, labels, ioa, best_idx = Kx.anchor_match(anchors, gt_boxes, gt_valid, gt_ign, lo)
+            A = anchors.shape[0]
+            best = torch.zeros(labels.shape, dtype=torch.int32, device=labels.device)
+            best.scatter_add_(1, best_idx.clamp(max=A - 1).long(), gt_valid.to(torch.int32))
+            return idx, vals, labels, (best > 0) & (labels == 1), ioa
         iou = pairwise_iou(gt_boxes, anchors)                                   # (B,G,A)
         iou = torch.where(gt_valid[:, :, None], iou, torch.full_like(iou, -1.0))
         vals, idx = iou.max(dim=1)
-        lo = self.iou_thresholds[-1]
         labels = (vals >= lo).to(torch.int8)
         rowmax = iou.max(dim=2, keepdim=True).values                            # best IoU of every GT
         lowq = ((iou == rowmax) & gt_valid[:, :, None]).any(dim=1)              # allow_low_quality_matches
@@ -199,14 +209,16 @@ class RPNWithIgnore(nn.Module):
         best = torch.zeros(labels.shape, dtype=torch.int32, device=labels.device)
         best.scatter_add_(1, best_idx, gt_valid.to(torch.int32))
         best = (best > 0) & (labels == 1)
-        return idx, vals.clamp(min=0), labels, best
+        ioa = pairwise_ioa(gt_boxes, anchors)                                    # (B,G,A)
+        ioa = torch.where(gt_ign[:, :, None], ioa, torch.zeros_like(ioa)).max(dim=1).values
+        return idx, vals.clamp(min=0), labels, best, ioa
 
     @torch.no_grad()
     def label_and_sample_anchors(self, anchors, gt_boxes, gt_classes, gt_present):
         """gt_classes (B,G) (-1 = ignore region), gt_present (B,G) bool (non-padding)."""
         valid = gt_present & (gt_classes >= 0)
         ign = gt_present & (gt_classes < 0)
-        idx, miou, lab, best = self.match_anchors(anchors, gt_boxes, valid)
+        idx, miou, lab, best, ioa = self.match_anchors(anchors, gt_boxes, valid, ign)
         B, A = lab.shape
         n_total = self.batch_size_per_image
         cap_pos = int(n_total * self.positive_fraction)
@@ -228,14 +240,15 @@ class RPNWithIgnore(nn.Module):
         ext.scatter_(1, torch.where(p_sel, p_idx, torch.full_like(p_idx, A)), torch.ones_like(p_idx, dtype=out.dtype))
         out = ext[:, :A].contiguous()
         out[best] = 1
-        return self.finish_labels(out, anchors, gt_boxes, ign), idx
+        return self.finish_labels(out, anchors, gt_boxes, ign, ioa), idx
 
     @torch.no_grad()
-    def finish_labels(self, labels, anchors, gt_boxes, ign):
+    def finish_labels(self, labels, anchors, gt_boxes, ign, ioa=None):
         """background anchors lying >= IGNORE_THRESHOLD inside an ignore box become -1 (rpn.py:93-105;
         only when the image has more than one background anchor, as there)."""
-        ioa = pairwise_ioa(gt_boxes, anchors)                                    # (B,G,A)
-        ioa = torch.where(ign[:, :, None], ioa, torch.zeros_like(ioa)).max(dim=1).values
+        if ioa is None:
+            ioa = pairwise_ioa(gt_boxes, anchors)                                # (B,G,A)
+            ioa = torch.where(ign[:, :, None], ioa, torch.zeros_like(ioa)).max(dim=1).values
         bg = labels == 0
         hit = bg & (ioa >= self.ignore_thresh) & (bg.sum(1, keepdim=True) > 1) & ign.any(1, keepdim=True)
         return torch.where(hit, torch.full_like(labels, -1), labels)
@@ -265,7 +278,7 @@ class RPNWithIgnore(nn.Module):
 
     # -- proposals --------------------------------------------------------------------------------
     @torch.no_grad()
-    def predict_proposals(self, anchors_per_level, logits_per_level, deltas_per_level, image_sizes):
+    def predict_proposals(self, anchors_per_level, logits_per_level, deltas_per_level, image_sizes, sizes_dev=None):
         """-> boxes (B,post,4), logits (B,post), count (B,) int32; slots >= count are padding (score -inf)."""
         training = self.training
         B = logits_per_level[0].shape[0]
@@ -280,7 +293,7 @@ class RPNWithIgnore(nn.Module):
             cand_l.append(torch.full((k,), lvl, dtype=torch.float32, device=dev))
         boxes, scores = torch.cat(cand_b, 1), torch.cat(cand_s, 1)
         lvl = torch.cat(cand_l)[None].expand(B, -1)
-        hw = torch.as_tensor(image_sizes, dtype=torch.float32, device=dev)      # (B,2) = (h,w)
+        hw = sizes_dev if sizes_dev is not None else torch.as_tensor(image_sizes, dtype=torch.float32, device=dev)  # (B,2) = (h,w)
         lim = torch.stack((hw[:, 1], hw[:, 0], hw[:, 1], hw[:, 0]), 1)[:, None, :]
         finite = torch.isfinite(boxes).all(-1) & torch.isfinite(scores)
         boxes = torch.minimum(boxes.clamp(min=0), lim)
@@ -306,7 +319,7 @@ class RPNWithIgnore(nn.Module):
         out_s = torch.where(pad, torch.full_like(out_s, -float("inf")), out_s)
         return out_b, out_s, kcnt
 
-    def forward(self, features, image_sizes, gt=None):
+    def forward(self, features, image_sizes, gt=None, sizes_dev=None):
         feats = [features[f] for f in self.in_features]
         shapes = [tuple(f.shape[1:3]) for f in feats]
         anchors_l = self.anchor_generator(shapes, feats[0].device)
@@ -326,5 +339,5 @@ class RPNWithIgnore(nn.Module):
             props = gt["proposals"]
         else:
             props = self.predict_proposals(anchors_l, [l.detach() for l in logits_l], [d.detach() for d in deltas_l],
-                                           image_sizes)
+                                           image_sizes, sizes_dev)
         return props, losses

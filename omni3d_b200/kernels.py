@@ -30,6 +30,7 @@ def _bind():
         "c3d_preprocess_image": [vp, i32, i32, vp, i32, i32, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), vp],
         "c3d_grad_finite": [vp, i64, vp, vp],
         "c3d_sgd_momentum": [vp, vp, vp, i64, f32, f32, f32, f32, vp, vp],
+        "c3d_sgd_momentum_dev": [vp, vp, vp, i64, vp, f32, f32, f32, vp, vp],
         "c3d_roi_align_fwd": [ctypes.POINTER(RoiLevels), vp, i32, i32, i32, i32, vp, vp],
         "c3d_roi_align_bwd": [ctypes.POINTER(RoiLevels), vp, i32, i32, i32, i32, vp, vp],
     }
@@ -43,6 +44,8 @@ def _bind():
     L.c3d_nms_workspace_bytes.restype = ctypes.c_size_t
     L.c3d_nms_workspace_bytes.argtypes = [i32, i32]
     sig["c3d_nms_batched"] = [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, ctypes.c_size_t, vp]
+    sig["c3d_anchor_match"] = [vp, i64, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp]
+    sig["c3d_preprocess_image_u8"] = [vp, i32, i32, vp, i32, i32, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), vp]
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.restype = i32
@@ -114,7 +117,7 @@ def maxpool2_bwd(x, dy):
 
 
 def preprocess_images(images, mean, std, size_divisibility=64, cpad=16):
-    """list of (3,H,W) fp32 CUDA tensors -> (N,Hp,Wp,cpad) bf16 NHWC batch (normalised, zero padded)."""
+    """list of (3,H,W) fp32 or uint8 CUDA tensors -> (N,Hp,Wp,cpad) bf16 NHWC batch (normalised, zero padded)."""
     L = _bind()
     Hm = max(im.shape[1] for im in images)
     Wm = max(im.shape[2] for im in images)
@@ -124,8 +127,9 @@ def preprocess_images(images, mean, std, size_divisibility=64, cpad=16):
     m = (f32 * 3)(*[float(v) for v in mean])
     s = (f32 * 3)(*[float(v) for v in std])
     for i, im in enumerate(images):
-        assert im.dtype == torch.float32 and im.is_contiguous() and im.is_cuda
-        _lib.check(L.c3d_preprocess_image(_p(im), im.shape[1], im.shape[2], _p(out[i]), Hp, Wp, cpad, m, s, _st()))
+        assert im.dtype in (torch.float32, torch.uint8) and im.is_contiguous() and im.is_cuda
+        fn = L.c3d_preprocess_image if im.dtype == torch.float32 else L.c3d_preprocess_image_u8
+        _lib.check(fn(_p(im), im.shape[1], im.shape[2], _p(out[i]), Hp, Wp, cpad, m, s, _st()))
     return out
 
 
@@ -167,9 +171,14 @@ def grad_finite(flat_grad, flag):
 
 
 def sgd_momentum(p, g, mom, lr, momentum, weight_decay, grad_scale=1.0, skip_flag=None):
+    """lr: python float, or a 1-element fp32 CUDA tensor (read by the kernel at run time: CUDA-graph friendly)."""
     L = _bind()
-    _lib.check(L.c3d_sgd_momentum(_p(p), _p(g), _p(mom), p.numel(), lr, momentum, weight_decay, grad_scale,
-                                  _p(skip_flag), _st()))
+    if torch.is_tensor(lr):
+        _lib.check(L.c3d_sgd_momentum_dev(_p(p), _p(g), _p(mom), p.numel(), _p(lr), momentum, weight_decay, grad_scale,
+                                          _p(skip_flag), _st()))
+    else:
+        _lib.check(L.c3d_sgd_momentum(_p(p), _p(g), _p(mom), p.numel(), lr, momentum, weight_decay, grad_scale,
+                                      _p(skip_flag), _st()))
 
 
 _nms_ws = {}
@@ -192,6 +201,26 @@ def nms_batched(boxes, nvalid, iou_thresh, max_keep, cats=None, maxc=None, trick
     _lib.check(L.c3d_nms_batched(_p(boxes), _p(nvalid), _p(cats), _p(maxc), trick_max_numel, B, n, iou_thresh,
                                  max_keep, _p(keep), _p(cnt), _p(ws), ws.numel(), _st()), launches=2)
     return keep, cnt
+
+
+def anchor_match(anchors, gt_boxes, gt_valid, gt_ign, fg_thresh):
+    """anchors (A,4), gt_boxes (B,G,4) fp32, gt_valid / gt_ign (B,G) bool -> matched_idx (B,A) int64, matched_iou (B,A),
+    labels (B,A) int8 {0,1}, max_ioa (B,A), best_idx (B,G) int32 (A for non-valid GTs)."""
+    L = _bind()
+    A = anchors.shape[0]
+    B, G, _ = gt_boxes.shape
+    dev = anchors.device
+    anchors, gt_boxes = anchors.contiguous().float(), gt_boxes.contiguous().float()
+    v8, i8 = gt_valid.to(torch.uint8).contiguous(), gt_ign.to(torch.uint8).contiguous()
+    idx = torch.empty((B, A), dtype=torch.int64, device=dev)
+    iou = torch.empty((B, A), dtype=torch.float32, device=dev)
+    ioa = torch.empty((B, A), dtype=torch.float32, device=dev)
+    lab = torch.empty((B, A), dtype=torch.int8, device=dev)
+    best = torch.empty((B, G), dtype=torch.int32, device=dev)
+    ws = torch.empty((B, G), dtype=torch.int32, device=dev)
+    _lib.check(L.c3d_anchor_match(_p(anchors), A, _p(gt_boxes), _p(v8), _p(i8), B, G, float(fg_thresh), _p(idx), _p(iou),
+                                  _p(lab), _p(ioa), _p(best), _p(ws), _st()), launches=3)
+    return idx, iou, lab, ioa, best
 
 
 def bias_act_bwd(dout, out, relu, dbias):

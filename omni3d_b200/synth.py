@@ -2,7 +2,7 @@
 
 Plain tensors only (no detectron2 types): each item mirrors the batched-input schema the reference's
 DatasetMapper3D emits (cubercnn/data/dataset_mapper.py:133-155) —
-  image (3,H,W) BGR float in [0,255], height, width, K 3x3, and `gt` = dict(classes int64 (G,),
+  image (3,H,W) BGR in [0,255] (float32, or uint8 as the mapper's torch.as_tensor(image) yields), height, width, K 3x3, and `gt` = dict(classes int64 (G,),
   boxes (G,4) XYXY, boxes3D (G,9) = [u,v,z,W,H,L,X,Y,Z], poses (G,3,3)).
 One of the G boxes per image is an ignore region (class -1) to exercise the ignore path.
 """
@@ -17,11 +17,12 @@ def _rand_rot(n, g):
     return q
 
 
-def make_batch(batch, height=640, width=640, num_gt=8, num_classes=50, seed=0, with_gt=True, with_ignore=True):
+def make_batch(batch, height=640, width=640, num_gt=8, num_classes=50, seed=0, with_gt=True, with_ignore=True,
+               image_dtype=torch.float32):
     g = torch.Generator().manual_seed(seed)
     items = []
     for _ in range(batch):
-        img = torch.randint(0, 256, (3, height, width), generator=g).float()
+        img = torch.randint(0, 256, (3, height, width), generator=g).to(image_dtype)   # uint8 = what DatasetMapper3D emits
         f = float(torch.empty(1).uniform_(400, 800, generator=g))
         K = [[f, 0.0, width / 2.0], [0.0, f, height / 2.0], [0.0, 0.0, 1.0]]
         item = {"image": img, "height": height, "width": width, "K": K}

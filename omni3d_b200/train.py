@@ -15,6 +15,7 @@ import math
 import torch
 import torch.distributed as dist
 
+from . import _lib
 from . import kernels as Kx
 from . import nnfunc
 
@@ -53,7 +54,7 @@ def lr_at(cfg, it):
 
 
 class FlatSGDTrainer:
-    def __init__(self, cfg, model, channels_last_weights=True):
+    def __init__(self, cfg, model, channels_last_weights=True, use_graph=None):
         if cfg.SOLVER.TYPE != "sgd":
             raise ValueError("{} is not supported as an optimizer on the accelerated path.".format(cfg.SOLVER.TYPE))
         self.cfg, self.model = cfg, model
@@ -122,15 +123,28 @@ class FlatSGDTrainer:
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.on_cuda = dev.type == "cuda"
         self.status_host = torch.zeros(len(LOSS_KEYS) + 4, pin_memory=self.on_cuda)
+        self.status_dev = torch.zeros(len(LOSS_KEYS) + 4, device=dev)
         self.status_event = None
         self.iteration = 0
         self.stabilize = cfg.MODEL.STABILIZE > 0
+        # CUDA-graph replay of the step body (see step()).  Multi-GPU: opt-in (NCCL all-reduce inside the graph).
+        import os
+        if use_graph is None:
+            env = os.environ.get("C3D_TRAIN_GRAPH")
+            use_graph = (env != "0") if self.world == 1 or env is not None else False
+        self.use_graph = bool(use_graph) and self.on_cuda and hasattr(model, "forward_staged")
+        self.graph_warmup = 2
+        self.graph = self.static = self.graph_sig = self.graph_losses = None
+        self.graph_launches = 0
+        self.lr_dev = torch.zeros(1, device=dev)
 
     # -------------------------------------------------------------------------------------------------
-    def step(self, batched_inputs):
+    def _body(self, staged, lr):
+        """zero grads, forward, stabiliser, backward, all-reduce, finite check, SGD — device work only (no host reads),
+        so the whole body can be replayed from a CUDA graph.  `lr`: python float (eager) or 1-element device tensor."""
         model, world = self.model, self.world
         self.flat_g.zero_()
-        loss_dict = model(batched_inputs)
+        loss_dict = model.forward_staged(staged) if hasattr(model, "forward_staged") else model(staged)
         vec = torch.stack([loss_dict[k].detach().float() if k in loss_dict else self.flat_g.new_zeros(())
                            for k in LOSS_KEYS])
         if world > 1:                                   # allreduce_dict, train_net.py:471-498 (mean over ranks)
@@ -150,7 +164,6 @@ class FlatSGDTrainer:
         self.flag.copy_(diverging.to(torch.int32).reshape(1))
         if self.stabilize:
             Kx.grad_finite(self.flat_g[:self.n_update], self.flag)
-        lr = lr_at(self.cfg, self.iteration)
         S = self.cfg.SOLVER
         gs = 1.0 / world
         d0, d1 = self.bounds["decay"]
@@ -161,9 +174,52 @@ class FlatSGDTrainer:
         nnfunc.invalidate_packed()
         skipped = (self.flag > 0).float().squeeze(0)
         new_recent = torch.where(diverging, recent, recent * (1 - GAMMA_ROLL) + total_reduced * GAMMA_ROLL)
-        self.state = torch.stack([new_recent, st[1] + (1 - skipped), st[2] + skipped, torch.ones_like(st[3])])
+        self.state.copy_(torch.stack([new_recent, st[1] + (1 - skipped), st[2] + skipped, torch.ones_like(st[3])]))
+        self.status_dev.copy_(torch.cat([vec, self.state]))
+        return loss_dict
+
+    @staticmethod
+    def _signature(staged):
+        g = staged.get("gt")
+        return (tuple((tuple(im.shape), im.dtype) for im in staged["images"]), None if g is None else g["boxes"].shape[1])
+
+    def _copy_into_static(self, staged):
+        """new batch -> the static buffers the recorded graph reads (device-to-device, async)."""
+        st = self.static
+        for dst, src in zip(st["images"], staged["images"]):
+            dst.copy_(src, non_blocking=True)
+        st["meta"].copy_(staged["meta"], non_blocking=True)
+        G = staged["gt"]["boxes"].shape[1]
+        for k, dst in st["gt"].items():
+            if G < dst.shape[1]:                        # pad to the recorded capacity (collate_gt's padding values)
+                dst[:, G:] = {"classes": -2, "present": False}.get(k, 0)
+                if k == "poses":
+                    dst[:, G:] = torch.eye(3, device=dst.device)
+            dst[:, :G].copy_(staged["gt"][k], non_blocking=True)
+
+    def step(self, batched_inputs):
+        """One training step.  With `use_graph` (default on one GPU, CUDA): two eager warm-up steps, then the body is
+        recorded once into a CUDA graph per input signature (image shapes / GT capacity) and replayed — the host then
+        only stages inputs (async copies), writes the learning rate and launches ONE graph instead of ~5000 kernels."""
+        lr = lr_at(self.cfg, self.iteration)
+        staged = self.model.stage_inputs(batched_inputs) if hasattr(self.model, "stage_inputs") else batched_inputs
+        loss_dict = None
+        if self.use_graph and self.iteration >= self.graph_warmup:
+            sig = self._signature(staged)
+            if self.graph is not None and (sig[0] != self.graph_sig[0] or sig[1] > self.graph_sig[1]):
+                self.graph, self.static = None, None     # other shapes: record again
+            if self.graph is None:
+                loss_dict = self._capture(staged, sig, lr)
+            else:
+                self._copy_into_static(staged)
+                self.lr_dev.fill_(lr)
+                self.graph.replay()
+                _lib.LAUNCHES["n"] += self.graph_launches
+                loss_dict = self.graph_losses
+        if loss_dict is None:
+            loss_dict = self._body(staged, lr)
         # async status readback (previous step's values are inspected by `status()` without blocking the GPU)
-        self.status_host.copy_(torch.cat([vec, self.state]), non_blocking=True)
+        self.status_host.copy_(self.status_dev, non_blocking=True)
         if self.on_cuda:
             self.status_event = torch.cuda.Event()
             self.status_event.record()
@@ -171,6 +227,28 @@ class FlatSGDTrainer:
             self.status_event = True
         self.iteration += 1
         return loss_dict
+
+    def _capture(self, staged, sig, lr):
+        try:
+            self.static = {"images": [im.clone() for im in staged["images"]], "sizes": staged["sizes"],
+                           "meta": staged["meta"].clone(), "gt": {k: v.clone() for k, v in staged["gt"].items()}}
+            self.lr_dev.fill_(lr)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            n0 = _lib.LAUNCHES["n"]
+            with torch.cuda.graph(graph):
+                losses = self._body(self.static, self.lr_dev)
+            self.graph_launches = _lib.LAUNCHES["n"] - n0
+            self.graph, self.graph_sig, self.graph_losses = graph, sig, losses
+            graph.replay()          # recording does not execute: run the step that was just recorded
+            return losses
+        except Exception as e:      # noqa: BLE001 — never silently: say so, then keep training eagerly
+            import sys
+            print("omni3d_b200: CUDA graph capture of the train step failed (%s: %s); continuing eagerly"
+                  % (type(e).__name__, e), file=sys.stderr)
+            self.use_graph, self.graph, self.static = False, None, None
+            torch.cuda.synchronize()
+            return None
 
     def status(self, wait=True):
         """{'losses': {...}, 'total_loss', 'recent_loss', 'iterations_success', 'iterations_explode', 'retry'}."""

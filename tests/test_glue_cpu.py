@@ -37,7 +37,7 @@ def test_anchors_and_matcher_bit_exact():
     head = prpn.RPNWithIgnore.__new__(prpn.RPNWithIgnore)
     head.iou_thresholds = [0.05, 0.05]
     valid = gt["present"] & (gt["classes"] >= 0)
-    idx, miou, lab, best = prpn.RPNWithIgnore.match_anchors(head, anchors, gt["boxes"], valid)
+    idx, miou, lab, best, _ = prpn.RPNWithIgnore.match_anchors(head, anchors, gt["boxes"], valid)
     m = Matcher([0.05, 0.05], [0, -1, 1], allow_low_quality_matches=True)
     for i, it in enumerate(model_io.to_d2_inputs(items)):
         inst = it["instances"]

@@ -256,3 +256,34 @@ def test_fused_cube_loss_matches_torch_formulation():
         assert ((gf - gref).norm() / (gref.norm() + 1e-12)).item() < 2e-3, k    # chamfer argmin ties aside
     for k in ("Cube/z_error", "Cube/dims_error", "Cube/xy_error", "Cube/conf"):
         assert abs(out["fused"][2][k] - out["torch"][2][k]) <= 1e-4 * abs(out["torch"][2][k]) + 1e-6, k
+
+
+@pytest.mark.parametrize("B,G,thr", [(3, 6, 0.7), (2, 1, 0.3), (4, 37, 0.05)])
+def test_anchor_match_kernel_equals_torch_formulation(B, G, thr):
+    """c3d_anchor_match (2 launches) == the (B,G,A) torch passes it replaces, bit for bit: matched GT, IoU, labels with
+    low-quality matches, per-GT arg-max anchors, ignore-region IoA; incl. padded / ignore GTs and an image without GT."""
+    from omni3d_b200.cubercnn import rpn as prpn
+    ag = prpn.AnchorGenerator([[32], [64], [128], [256], [512]], [[0.5, 1.0, 2.0]], [4, 8, 16, 32, 64])
+    anchors = torch.cat(ag([(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)], torch.device("cuda")))
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + G)
+    xy = torch.rand(B, G, 2, device="cuda", generator=g) * torch.tensor([200.0, 140.0], device="cuda")
+    wh = torch.rand(B, G, 2, device="cuda", generator=g) * 120 + 4
+    boxes = torch.cat([xy, xy + wh], -1)
+    boxes[0, 0] = anchors[777]                                 # an exact hit (IoU == 1) and a duplicate GT (ties)
+    if G > 1:
+        boxes[0, 1] = boxes[0, 0]
+    present = torch.rand(B, G, device="cuda", generator=g) > 0.2
+    ignore = torch.rand(B, G, device="cuda", generator=g) > 0.7
+    present[-1] = False                                        # image without any GT
+    valid, ign = present & ~ignore, present & ignore
+    head = prpn.RPNWithIgnore.__new__(prpn.RPNWithIgnore)
+    head.iou_thresholds = [thr, thr]
+    got = prpn.RPNWithIgnore.match_anchors(head, anchors, boxes, valid, ign)
+    ref = prpn.RPNWithIgnore.match_anchors(head, anchors.cpu(), boxes.cpu(), valid.cpu(), ign.cpu())
+    names = ["matched_idx", "matched_iou", "labels", "best", "max_ioa"]
+    for n, a, b in zip(names, got, ref):
+        if n == "matched_idx":       # ties between duplicate GT boxes: both resolve to the first one
+            assert torch.equal(boxes.cpu()[torch.arange(B)[:, None], a.cpu()], boxes.cpu()[torch.arange(B)[:, None], b]), n
+            assert torch.equal(a.cpu(), b), n
+        else:
+            assert torch.equal(a.cpu(), b), n
