@@ -40,6 +40,7 @@ def _packed(w, kind):
 
 
 _phase_cache = {}
+_tap_index = {}
 
 
 def _phase_packs(w):
@@ -51,12 +52,14 @@ def _phase_packs(w):
     hit = _phase_cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]
-    taps = {0: [1], 1: [2, 0]}
+    taps = _tap_index.get(w.device)
+    if taps is None:          # device-resident index tensors, built once (a python-list index is a host->device copy)
+        taps = _tap_index[w.device] = {0: torch.tensor([1], device=w.device), 1: torch.tensor([2, 0], device=w.device)}
     packs = {}
     with torch.no_grad():
         for a in (0, 1):
             for b in (0, 1):
-                sub = w[:, :, taps[a]][:, :, :, taps[b]]                   # (Cout,Cin,KH',KW')
+                sub = w.index_select(2, taps[a]).index_select(3, taps[b])   # (Cout,Cin,KH',KW')
                 packs[(a, b)] = sub.permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)
     if w.is_leaf:
         _phase_cache[key] = (ver, packs)

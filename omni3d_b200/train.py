@@ -11,6 +11,7 @@ cubercnn/solver/build.py:6-69 (build_optimizer), re-designed for one-process-per
   memory one step late (no per-step synchronisation, vs 3 barriers + 3 scalar all-reduces + ~10 .item()).
 """
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -128,7 +129,6 @@ class FlatSGDTrainer:
         self.iteration = 0
         self.stabilize = cfg.MODEL.STABILIZE > 0
         # CUDA-graph replay of the step body (see step()).  Multi-GPU: opt-in (NCCL all-reduce inside the graph).
-        import os
         if use_graph is None:
             env = os.environ.get("C3D_TRAIN_GRAPH")
             use_graph = (env != "0") if self.world == 1 or env is not None else False
@@ -244,6 +244,9 @@ class FlatSGDTrainer:
             return losses
         except Exception as e:      # noqa: BLE001 — never silently: say so, then keep training eagerly
             import sys
+            import traceback
+            if os.environ.get("C3D_DEBUG"):
+                traceback.print_exc()
             print("omni3d_b200: CUDA graph capture of the train step failed (%s: %s); continuing eagerly"
                   % (type(e).__name__, e), file=sys.stderr)
             self.use_graph, self.graph, self.static = False, None, None
