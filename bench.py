@@ -134,6 +134,16 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
+def _top_kernel_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant conv kernel from the committed
+    `ncu --set full` capture (profiles/top_kernel_traffic.json: {"bytes_per_launch": ...}); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
+    try:
+        return json.load(open(p))["bytes_per_launch"]
+    except Exception:      # noqa: BLE001
+        return None
+
+
 def conv_roofline(trainer, items, peak_tflops, peak_src):
     """One instrumented step: CUDA events around every conv_tc launch (on the launching stream) ->
     algorithmic FLOPs / summed duration for the dominant kernel family."""
@@ -161,11 +171,14 @@ def conv_roofline(trainer, items, peak_tflops, peak_src):
 
     K.conv2d_fwd, K.conv2d_wgrad = fwd, wgrad
     import omni3d_b200.nnfunc as nf
+    graph_mode = trainer.use_graph
+    trainer.use_graph = False          # the instrumented step runs eagerly (the timed steps replay a CUDA graph)
     try:
         trainer.step(items)
         torch.cuda.synchronize()
     finally:
         K.conv2d_fwd, K.conv2d_wgrad = o_f, o_w
+        trainer.use_graph = graph_mode
     ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
     # ALGORITHMIC conv FLOPs of one train step: DLA34 25.081 + FPN 20.913 + RPN head 20.244
     # GMAC/img forward; backward = dgrad (no dgrad for the 0.963-GMAC stem) + wgrad.  Executed FLOPs are higher
@@ -177,8 +190,8 @@ def conv_roofline(trainer, items, peak_tflops, peak_src):
     for a, b, f, kind in rec:
         t = by.setdefault(kind, [0.0, 0.0, 0])
         t[0] += a.elapsed_time(b); t[1] += f; t[2] += 1
-    return {"bound": "tensor", "kernel": "conv_tc_kernel + conv_wgrad_tc_kernel (tcgen05 implicit GEMM)",
-            "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": None,
+    return {"bound": "tensor", "kernel": "conv_tc_* / conv_halo_* / conv_wgrad_tc_kernel (tcgen05 implicit GEMM, fwd + dgrad + wgrad)",
+            "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": _top_kernel_traffic(),
             "peak_source": peak_src + ", bf16 sustained (kernel timed inside a long step)",
             "launches_per_step": len(rec), "conv_ms_per_step": ms, "algorithmic_tflop_per_step": fl / 1e12,
             "executed_tflop_per_step": sum(f for _, _, f, _ in rec) / 1e12,
@@ -288,8 +301,10 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": f"Cube R-CNN DLA34_FPN train step, batch {B}/GPU synthetic {S}x{S}, K=50, G=8 GT/img "
                                "(BASELINE configs[1]; weak scaling, global batch %d)" % (B * world),
-                   "parallelism": f"dp{world}", "l2": "two alternating input batches (157 MB each) + ~10 GB of activations "
-                                                      "per step: working set >> 126 MB L2",
+                   "parallelism": f"dp{world}", "l2": "two alternating input batches (39 MB uint8 images each) + ~10 GB of "
+                                                      "activations per step: working set >> 126 MB L2",
+                   "cuda_graph": bool(trainer.graph is not None),
+                   "images": "uint8 (3,H,W), as cubercnn/data/dataset_mapper.py:35 emits them",
                    "train_gflop_per_image": GFLOP_TRAIN_PER_IMAGE},
         "clocks": clocks,
         "e2e": {"value": ips_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 56,

@@ -12,7 +12,7 @@ cfg = pc.load_cfg("cubercnn_DLA34_FPN.yaml", ["MODEL.WEIGHTS_PRETRAIN", "none", 
 torch.manual_seed(0)
 model = pc.build_model(cfg).train()
 tr = FlatSGDTrainer(cfg, model)
-items = synth.make_batch(B, S, S, num_gt=8, seed=0)
+items = synth.make_batch(B, S, S, num_gt=8, seed=0, image_dtype=torch.uint8)
 items = [{**it, "image": it["image"].cuda(), "gt": {k: v.cuda() for k, v in it["gt"].items()}} for it in items]
 for _ in range(2):
     tr.step(items)
