@@ -67,16 +67,36 @@ static inline void launch_colsum(const float* m, int rows, int cols, double* scr
 }
 
 // partial: [rows][2][C] per-tile (sum, sumsq) from the conv epilogue -> slab sums -> statistics.
+// Second stage of the column sums: <= kSlabs rows of doubles.  A block is 32 channels x 8 row lanes; every lane sums
+// each 8th slab (16 loads instead of a 128-long serial chain), then the 8 partials are combined through shared memory.
+// Returns the two sums (offsets off0 / off1 inside a slab row; pass off1 < 0 for a single sum) to row-lane 0.
+__device__ __forceinline__ void slab_sums(const double* __restrict__ slab, int slabs, size_t row_stride, int off0, int off1,
+                                          int c, bool active, double* s_out, double* t_out) {
+  __shared__ double sh[2][8][32];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  double s = 0.0, t = 0.0;
+  if (active) {
+    for (int r = ry; r < slabs; r += 8) {
+      s += slab[(size_t)r * row_stride + off0 + c];
+      if (off1 >= 0) t += slab[(size_t)r * row_stride + off1 + c];
+    }
+  }
+  sh[0][ry][cx] = s; sh[1][ry][cx] = t;
+  __syncthreads();
+  if (ry == 0) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { s += sh[0][k][cx]; t += sh[1][k][cx]; }
+  }
+  *s_out = s; *t_out = t;
+}
+
 __global__ void bn_finalize_kernel(const double* __restrict__ slab, int slabs, int C, double count, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, s2 = 0.0;
-  for (int r = 0; r < slabs; ++r) {
-    s += slab[(size_t)r * 2 * C + c];
-    s2 += slab[(size_t)r * 2 * C + C + c];
-  }
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  double s, s2;
+  slab_sums(slab, slabs, (size_t)2 * C, 0, C, c, c < C, &s, &s2);
+  if (c >= C || (threadIdx.x >> 5) != 0) return;
   double mean = s / count;
   double var = s2 / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -90,27 +110,37 @@ __global__ void bn_finalize_kernel(const double* __restrict__ slab, int slabs, i
 }
 
 // out = [relu]( (y - mean) * rstd * gamma + beta [+ residual] ), P pixels x C channels
-__global__ void bn_apply_kernel(const bf16* __restrict__ y, const float* __restrict__ mean,
-                                const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, const bf16* __restrict__ residual, int relu,
-                                bf16* __restrict__ out, long long P, int C, long long res_stride,
-                                long long out_stride) {
+// thread layout of the streaming BN kernels: tx = channel vector (8 channels, fixed for the thread's lifetime so the
+// per-channel constants live in registers), ty = pixel row lane; pixels are strided by gridDim * rows_per_block.  No
+// integer division and no parameter loads inside the loop: these kernels must sustain ~1.4 16-byte vectors per clock
+// per SM to reach HBM speed, so the loop body is kept to the loads, 8 FMAs and the store.
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const bf16* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                const float* __restrict__ gamma, const float* __restrict__ beta, const bf16* __restrict__ residual, int relu,
+                bf16* __restrict__ out, long long P, int C, long long res_stride, long long out_stride) {
   const int cv = C >> 3;
-  const long long total = P * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / cv;
-    const int c = (int)(i - p * cv) << 3;
-    V8 a = ld8(y + p * C + c);
-    V8 r;
-    if (residual) r = ld8(residual + p * res_stride + c);
-    V8 o;
+  const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
+  const int rows_per_block = blockDim.x / cv;
+  if (ty >= rows_per_block) return;
+  const int c = tx << 3;
+  float m[8], sc[8], bt[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float sc = __ldg(rstd + c + k) * __ldg(gamma + c + k);
-      float v = (a.v[k] - __ldg(mean + c + k)) * sc + __ldg(beta + c + k);
-      if (residual) v += r.v[k];
-      o.v[k] = relu ? fmaxf(v, 0.f) : v;
+  for (int k = 0; k < 8; ++k) { m[k] = mean[c + k]; sc[k] = rstd[c + k] * gamma[c + k]; bt[k] = beta[c + k]; }
+  const long long step = (long long)gridDim.x * rows_per_block;
+  for (long long p = (long long)blockIdx.x * rows_per_block + ty; p < P; p += step) {
+    V8 a = ld8(y + p * C + c);
+    V8 o;
+    if (residual) {
+      V8 r = ld8(residual + p * res_stride + c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = (a.v[k] - m[k]) * sc[k] + bt[k] + r.v[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = (a.v[k] - m[k]) * sc[k] + bt[k];
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(o.v[k], 0.f);
     }
     st8(out + p * out_stride + c, o);
   }
@@ -166,13 +196,10 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int b
                                        const float* __restrict__ gamma, const float* __restrict__ rstd,
                                        float* __restrict__ coef, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, int frozen) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, t = 0.0;
-  for (int b = 0; b < blocks; ++b) {
-    s += partial[((size_t)b * 2 + 0) * C + c];
-    t += partial[((size_t)b * 2 + 1) * C + c];
-  }
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  double s, t;
+  slab_sums(partial, blocks, (size_t)2 * C, 0, C, c, c < C, &s, &t);
+  if (c >= C || (threadIdx.x >> 5) != 0) return;
   coef[c] = gamma[c] * rstd[c];
   // frozen (eval-mode / freeze_bn) statistics do not depend on the batch: dy = gamma * rstd * dz
   coef[C + c] = frozen ? 0.f : (float)(s / count);
@@ -182,17 +209,24 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int b
 }
 
 // dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat));  optionally dres = dz
-__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out,
-                                    const bf16* __restrict__ y, const float* __restrict__ mean,
-                                    const float* __restrict__ rstd, const float* __restrict__ coef, int relu,
-                                    bf16* __restrict__ dy, bf16* __restrict__ dres, long long P, int C,
-                                    long long dout_stride, long long out_stride, long long dres_stride) {
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out, const bf16* __restrict__ y,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ coef, int relu,
+                    bf16* __restrict__ dy, bf16* __restrict__ dres, long long P, int C, long long dout_stride,
+                    long long out_stride, long long dres_stride) {
   const int cv = C >> 3;
-  const long long total = P * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / cv;
-    const int c = (int)(i - p * cv) << 3;
+  const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
+  const int rows_per_block = blockDim.x / cv;
+  if (ty >= rows_per_block) return;
+  const int c = tx << 3;
+  float m[8], rs[8], c0[8], c1[8], c2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    m[k] = mean[c + k]; rs[k] = rstd[c + k];
+    c0[k] = coef[c + k]; c1[k] = coef[C + c + k]; c2[k] = coef[2 * C + c + k];
+  }
+  const long long step = (long long)gridDim.x * rows_per_block;
+  for (long long p = (long long)blockIdx.x * rows_per_block + ty; p < P; p += step) {
     V8 d = ld8(dout + p * dout_stride + c);
     V8 yy = ld8(y + p * C + c);
     if (relu) {
@@ -203,8 +237,8 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* _
     V8 g;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float xh = (yy.v[k] - __ldg(mean + c + k)) * __ldg(rstd + c + k);
-      g.v[k] = __ldg(coef + c + k) * (d.v[k] - __ldg(coef + C + c + k) - xh * __ldg(coef + 2 * C + c + k));
+      const float xh = (yy.v[k] - m[k]) * rs[k];
+      g.v[k] = c0[k] * (d.v[k] - c1[k] - xh * c2[k]);
     }
     st8(dy + p * C + c, g);
     if (dres) st8(dres + p * dres_stride + c, d);
@@ -258,10 +292,10 @@ __global__ void bias_act_bwd_kernel(const TIN* __restrict__ dout, const TIN* __r
   }
 }
 __global__ void bias_bwd_finalize_kernel(const double* __restrict__ slab, int slabs, int C, float* __restrict__ dbias) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0;
-  for (int b = 0; b < slabs; ++b) s += slab[(size_t)b * C + c];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  double s, t;
+  slab_sums(slab, slabs, (size_t)C, 0, -1, c, c < C, &s, &t);
+  if (c >= C || (threadIdx.x >> 5) != 0) return;
   dbias[c] += (float)s;
 }
 
@@ -447,7 +481,7 @@ extern "C" int32_t c3d_bn_finalize(const float* partial, int32_t rows, int32_t C
   C3D_REQ(partial && mean_out && rstd_out && scratch && rows > 0 && C > 0, "bn_finalize: bad args");
   int slabs;
   launch_colsum(partial, rows, 2 * C, (double*)scratch, &slabs, (cudaStream_t)stream);
-  bn_finalize_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>((const double*)scratch, slabs, C, count, eps,
+  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>((const double*)scratch, slabs, C, count, eps,
                                                                      momentum, running_mean, running_var, mean_out,
                                                                      rstd_out);
   return check_launch("bn_finalize");
@@ -457,6 +491,7 @@ extern "C" int32_t c3d_bn_apply(const void* y, const float* mean, const float* r
                                 int32_t C, int64_t res_stride, int64_t out_stride, void* stream) {
   C3D_REQ(y && mean && rstd && gamma && beta && out && C % 8 == 0, "bn_apply: bad args");
   if (P == 0) return C3D_OK;
+  C3D_REQ(C <= 2048, "bn_apply: C too large");
   bn_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)y, mean, rstd, gamma, beta, (const bf16*)residual, relu, (bf16*)out, P, C,
       res_stride ? res_stride : C, out_stride ? out_stride : C);
@@ -490,7 +525,7 @@ extern "C" int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, 
     return set_error(C3D_EINVAL, "bn_bwd: C too large");
   int slabs;
   launch_colsum(partial, blocks, 2 * C, (double*)scratch, &slabs, st);
-  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>((const double*)scratch, slabs, C, (double)P, gamma, rstd, coef,
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>((const double*)scratch, slabs, C, (double)P, gamma, rstd, coef,
                                                        dgamma, dbeta, frozen_stats);
   bn_bwd_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)y,
                                                                    mean, rstd, coef, relu, (bf16*)dy, (bf16*)dres, P, C,
@@ -574,7 +609,7 @@ extern "C" int32_t c3d_bias_act_bwd(const void* dout, const void* out, int32_t r
   if (dbias) {
     int slabs;
     launch_colsum(partial, blocks, C, (double*)scratch, &slabs, st);
-    bias_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>((const double*)scratch, slabs, C, dbias);
+    bias_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>((const double*)scratch, slabs, C, dbias);
   }
   return check_launch("bias_act_bwd");
 }
