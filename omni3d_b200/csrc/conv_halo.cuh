@@ -286,7 +286,11 @@ conv_halo_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParam
 
 // ------------------------------------------------------------------------------------------------------------
 // weight gradient: dW[co][kh][kw][ci] += sum_{n,y,x} dY[n,y,x,co] * X[n, y+kh-pad, x+kw-pad, ci]
-// TMEM block (kh, plane p) = 128 lanes (m = kw*8 + ci%8, kw < 16) x Cout columns.
+// One input row X[i] meets the KH gradient rows dY[i-KH+1 .. i] that use it: those rows sit in CONSECUTIVE ring slots
+// (the first KH-1 slots are mirrored behind the ring, so a window never wraps), which makes (row, Cout) one long N
+// dimension of a single MMA:  D[m = (kw shift, ci)][n = (dY row, co)] += X_row^T . dY_window,  K = 16 pixels.
+// TMEM block b of plane p (Cout columns at (p*KH + b)*Cout) holds kh = KH-1-b.  At the first/last rows of a chunk the
+// window is clipped to the chunk's own rows (narrower N, shifted block), so every (row, kh) pair is counted once.
 template <int KS, int CIN>
 __global__ void __launch_bounds__(192, 4)
 conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
@@ -300,13 +304,14 @@ conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   constexpr int dy_plane_bytes = 128 * 16;
   const int dy_slot_bytes = P.PO * dy_plane_bytes;
   uint8_t* ring = smem;
-  uint8_t* dyring = ring + (size_t)P.R * slot_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(dyring + (size_t)P.RD * dy_slot_bytes);
+  uint8_t* dyring = ring + (size_t)P.R * slot_bytes;                        // RD slots + KH-1 mirror slots
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(dyring + (size_t)(P.RD + KH - 1) * dy_slot_bytes);
   uint64_t* empty_bar = full_bar + P.R;
   uint64_t* dfull_bar = empty_bar + P.R;
   uint64_t* dempty_bar = dfull_bar + P.RD;
   uint64_t* done_bar = dempty_bar + P.RD;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
+  uint64_t* zero_bar = done_bar + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(zero_bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&tmap_x); ptx::prefetch_tensormap(&tmap_dy); }
@@ -314,6 +319,7 @@ conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     for (int s = 0; s < P.R; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < P.RD; ++s) { ptx::mbar_init(&dfull_bar[s], 1); ptx::mbar_init(&dempty_bar[s], 1); }
     ptx::mbar_init(done_bar, 1);
+    ptx::mbar_init(zero_bar, 4);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -325,6 +331,7 @@ conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const int ncols = NP * KH * P.Cout;                        // multiple of 16
 
   if (warp == 0) {
     if (ptx::elect_one()) {
@@ -335,8 +342,20 @@ conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         const int y0 = cy * P.rows_per_chunk;
         const int rows = min(P.rows_per_chunk, P.H - y0);
         const int x0 = xs * 128;
-        // dY row j is requested right after the last input row (j + KH - 1) it needs
         for (int i = 0; i < rows + KH - 1; ++i) {
+          if (i < rows) {                                   // dY row i is first needed together with input row i
+            ptx::mbar_wait(&dempty_bar[ds], dpar ^ 1u);
+            const bool mirror = ds < (uint32_t)(KH - 1);
+            ptx::mbar_expect_tx(&dfull_bar[ds], (uint32_t)dy_slot_bytes * (mirror ? 2u : 1u));
+            uint8_t* dd = dyring + (size_t)ds * dy_slot_bytes;
+            for (int p = 0; p < P.PO; ++p) {
+              ptx::tma_load_4d(dd + p * dy_plane_bytes, &tmap_dy, &dfull_bar[ds], p * 8, x0, y0 + i, n);
+              if (mirror)
+                ptx::tma_load_4d(dd + (size_t)P.RD * dy_slot_bytes + p * dy_plane_bytes, &tmap_dy, &dfull_bar[ds], p * 8, x0,
+                                 y0 + i, n);
+            }
+            if (++ds == (uint32_t)P.RD) { ds = 0; dpar ^= 1u; }
+          }
           ptx::mbar_wait(&empty_bar[slot], par ^ 1u);
           ptx::mbar_expect_tx(&full_bar[slot], (uint32_t)slot_bytes);
           uint8_t* dst = ring + (size_t)slot * slot_bytes;
@@ -344,66 +363,55 @@ conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
           for (int p = 0; p < NP; ++p)
             ptx::tma_load_4d(dst + p * plane_bytes, &tmap_x, &full_bar[slot], p * 8, x0 - P.pad, y0 - P.pad + i, n);
           if (++slot == (uint32_t)P.R) { slot = 0; par ^= 1u; }
-          const int j = i - (KH - 1);
-          if (j >= 0) {
-            ptx::mbar_wait(&dempty_bar[ds], dpar ^ 1u);
-            ptx::mbar_expect_tx(&dfull_bar[ds], (uint32_t)dy_slot_bytes);
-            uint8_t* dd = dyring + (size_t)ds * dy_slot_bytes;
-            for (int p = 0; p < P.PO; ++p)
-              ptx::tma_load_4d(dd + p * dy_plane_bytes, &tmap_dy, &dfull_bar[ds], p * 8, x0, y0 + j, n);
-            if (++ds == (uint32_t)P.RD) { ds = 0; dpar ^= 1u; }
-          }
         }
       }
     }
   } else if (warp == 1) {
     if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::make_idesc_bf16(128, P.Cout, 1, 1);
+      const uint32_t idesc0 = ptx::make_idesc_bf16(128, 0, 1, 1);
       const uint32_t R = (uint32_t)P.R, RD = (uint32_t)P.RD;
       const uint32_t slot_u = (uint32_t)slot_bytes >> 4, dy_slot_u = (uint32_t)dy_slot_bytes >> 4;
       // A: MN-major, MN chunk (pixel shift) stride 16 B ("SBO"), K group (8 px) stride 128 B ("LBO")
       const uint32_t a_lo0 = (ptx::smem_u32(ring) >> 4) | (8u << 16);
-      // B: MN-major, MN chunk (8 output channels) stride = dY plane, K group stride 128 B
+      // B: MN-major, MN chunk (8 output channels; planes of a row, then the next row's) stride = dY plane
       const uint32_t b_lo0 = (ptx::smem_u32(dyring) >> 4) | (8u << 16);
       constexpr uint32_t a_hi = halo_desc_hi(16), b_hi = halo_desc_hi(dy_plane_bytes);
-      uint32_t slot0 = 0, rslot = 0, rpar = 0, ds = 0, dpar = 0;
-      uint32_t accum = 0;
+      uint32_t xslot = 0, xpar = 0;            // input-row FIFO
+      uint32_t dwait = 0, dwpar = 0;           // next dY slot to wait for
+      uint32_t dlo = 0;                        // ring slot of the oldest dY row still in use
+      ptx::mbar_wait(zero_bar, 0);             // accumulators were zeroed by the epilogue warps
+      ptx::tcgen05_fence_after();
       for (int c = blockIdx.x; c < P.total_chunks; c += gridDim.x) {
         const int cy = c % P.chunks_per_col;
         const int y0 = cy * P.rows_per_chunk;
         const int rows = min(P.rows_per_chunk, P.H - y0);
-        for (int j = 0; j < rows; ++j) {
-          const int need = j == 0 ? KH : 1;
-          for (int t = 0; t < need; ++t) {
-            ptx::mbar_wait(&full_bar[rslot], rpar);
-            if (++rslot == R) { rslot = 0; rpar ^= 1u; }
+        for (int i = 0; i < rows + KH - 1; ++i) {
+          if (i < rows) {
+            ptx::mbar_wait(&dfull_bar[dwait], dwpar);
+            if (++dwait == RD) { dwait = 0; dwpar ^= 1u; }
           }
-          ptx::mbar_wait(&dfull_bar[ds], dpar);
+          ptx::mbar_wait(&full_bar[xslot], xpar);
           ptx::tcgen05_fence_after();
-          const uint32_t dy_lo = b_lo0 + ds * dy_slot_u;
-          uint32_t sl = slot0;
+          const int jlo = max(0, i - KH + 1), jhi = min(rows - 1, i);
+          const int nvalid = jhi - jlo + 1;
+          const int blo = KH - 1 - i + jlo;                  // TMEM block of dY row jlo (kh = i - jlo)
+          const uint32_t idesc = idesc0 | ((uint32_t)(nvalid * P.Cout) >> 3) << 17;
+          const uint32_t dy_lo = b_lo0 + dlo * dy_slot_u;    // dlo is the slot of row jlo (rows below jlo are released)
+          const uint32_t row_lo = a_lo0 + xslot * slot_u;
 #pragma unroll
-          for (int kh = 0; kh < KH; ++kh) {
-            const uint32_t row_lo = a_lo0 + sl * slot_u;
+          for (int p = 0; p < NP; ++p) {
+            const uint32_t tacc = tmem_base + (uint32_t)((p * KH + blo) * P.Cout);
 #pragma unroll
-            for (int p = 0; p < NP; ++p) {
-              const uint32_t tacc = tmem_base + (uint32_t)((kh * NP + p) * P.Cout);
-#pragma unroll
-              for (int t = 0; t < 8; ++t)
-                ptx::umma_bf16(tacc, halo_desc(row_lo + (uint32_t)(p * (plane_bytes >> 4) + t * 16), a_hi),
-                               halo_desc(dy_lo + (uint32_t)(t * 16), b_hi), idesc, t == 0 ? accum : 1u);
-            }
-            if (++sl == R) sl = 0;
+            for (int t = 0; t < 8; ++t)
+              ptx::umma_bf16(tacc, halo_desc(row_lo + (uint32_t)(p * (plane_bytes >> 4) + t * 16), a_hi),
+                             halo_desc(dy_lo + (uint32_t)(t * 16), b_hi), idesc, 1u);
           }
-          accum = 1u;
-          ptx::umma_commit(&empty_bar[slot0]);
-          ptx::umma_commit(&dempty_bar[ds]);
-          if (++slot0 == R) slot0 = 0;
-          if (++ds == RD) { ds = 0; dpar ^= 1u; }
-        }
-        for (int t = 0; t < KH - 1; ++t) {
-          ptx::umma_commit(&empty_bar[slot0]);
-          if (++slot0 == R) slot0 = 0;
+          ptx::umma_commit(&empty_bar[xslot]);
+          if (++xslot == R) { xslot = 0; xpar ^= 1u; }
+          if (i >= KH - 1) {                                 // dY row i-KH+1 has met its last input row
+            ptx::umma_commit(&dempty_bar[dlo]);
+            if (++dlo == RD) dlo = 0;
+          }
         }
       }
       ptx::umma_commit(done_bar);
@@ -412,15 +420,21 @@ conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int kw = m >> 3, cil = m & 7;
+    for (int c0 = 0; c0 < ncols; c0 += 16) ptx::tmem_st_32x32b_x16_fill(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, 0u);
+    ptx::tmem_st_wait();
+    ptx::tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(zero_bar);
     ptx::mbar_wait(done_bar, 0);
     ptx::tcgen05_fence_after();
     if (q * 4 < P.KW) {                      // warps whose 4 pixel shifts include a real tap
-      for (int kh = 0; kh < P.KH; ++kh)
-        for (int p = 0; p < P.P; ++p) {
+      for (int p = 0; p < NP; ++p)
+        for (int b = 0; b < KH; ++b) {
+          const int kh = KH - 1 - b;
           const int ci = p * 8 + cil;
           for (int c0 = 0; c0 < P.Cout; c0 += 16) {
             uint32_t v[16];
-            ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((kh * P.P + p) * P.Cout + c0), v);
+            ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((p * KH + b) * P.Cout + c0), v);
             ptx::tmem_ld_wait();
             if (kw < P.KW) {
 #pragma unroll
@@ -580,24 +594,28 @@ static int32_t launch_halo_wgrad(const c3d_conv_desc* d, const void* x, const vo
   if (!enc) return set_error(C3D_ECUDA, "cuTensorMapEncodeTiled unavailable");
   HaloParams P;
   memset(&P, 0, sizeof(P));
-  int grid;
   const int cols = d->KH * (d->Cin / 8) * d->Cout;
   const uint32_t tcols = cols <= 128 ? 128u : (cols <= 256 ? 256u : 512u);
-  halo_chunking(d, &P, (int)(512u / tcols), &grid);           // co-resident CTAs are bounded by their TMEM blocks
   P.N = d->N; P.H = d->H; P.W = d->W; P.Cin = d->Cin; P.Cout = d->Cout; P.KH = d->KH; P.KW = d->KW; P.pad = d->pad;
   P.P = d->Cin / 8; P.PO = d->Cout / 8;
   P.BW = 144;
-  P.R = halo_ring_rows(d->KH, P.P * P.BW * 16, 32 * 1024);
-  P.RD = halo_ring_rows(0, P.PO * 128 * 16, 16 * 1024);
+  P.R = halo_ring_rows(0, P.P * P.BW * 16, 16 * 1024);             // input rows are a plain FIFO here
+  P.RD = halo_ring_rows(d->KH, P.PO * 128 * 16, 0);                // window of KH rows + 2 in flight
   P.dw = dw; P.oihw = oihw;
+  const size_t smem = 128 + (size_t)P.R * P.P * P.BW * 16 + (size_t)(P.RD + d->KH - 1) * P.PO * 128 * 16 +
+                      (size_t)(2 * P.R + 2 * P.RD + 2) * 8 + 16 + 64;
+  if (smem > 200 * 1024) return set_error(C3D_EINVAL, "halo wgrad: smem %zu too large", smem);
+  int ctas = (int)(512u / tcols);                                  // co-resident CTAs: TMEM blocks, shared memory
+  const int by_smem = (int)((227 * 1024) / (smem + 1024));
+  if (ctas > by_smem) ctas = by_smem;
+  if (ctas < 1) ctas = 1;
+  int grid;
+  halo_chunking(d, &P, ctas, &grid);
   CUtensorMap mx, mdy;
   CUresult r = halo_tensormap(enc, &mx, x, d->Cin, d->W, d->H, d->N, P.BW);
   if (r != CUDA_SUCCESS) return set_error(C3D_ECUDA, "encode halo x tensormap failed: %d", (int)r);
   r = halo_tensormap(enc, &mdy, dy, d->Cout, d->W, d->H, d->N, 128);
   if (r != CUDA_SUCCESS) return set_error(C3D_ECUDA, "encode halo dy tensormap failed: %d", (int)r);
-  const size_t smem = 128 + (size_t)P.R * P.P * P.BW * 16 + (size_t)P.RD * P.PO * 128 * 16 +
-                      (size_t)(2 * P.R + 2 * P.RD + 1) * 8 + 16 + 64;
-  if (smem > 200 * 1024) return set_error(C3D_EINVAL, "halo wgrad: smem %zu too large", smem);
   if (d->KH == 7 && d->Cin == 8) return launch_halo_wgrad_inst<7, 8>(mx, mdy, P, grid, smem, tcols, st);
   if (d->KH == 3 && d->Cin == 16) return launch_halo_wgrad_inst<3, 16>(mx, mdy, P, grid, smem, tcols, st);
   if (d->KH == 3 && d->Cin == 32) return launch_halo_wgrad_inst<3, 32>(mx, mdy, P, grid, smem, tcols, st);

@@ -117,6 +117,14 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+// 16 consecutive fp32 columns of this warp's 32 TMEM lanes <- one value (used to zero accumulators)
+__device__ __forceinline__ void tmem_st_32x32b_x16_fill(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(taddr),
+      "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 // ---- descriptors ------------------------------------------------------------------------------
 // Instruction descriptor, kind::f16: bf16 x bf16 -> f32 (cute::UMMA::InstrDescriptor bit layout):
