@@ -211,6 +211,22 @@ int32_t c3d_anchor_match(const float* anchors, int64_t A, const float* gt_boxes,
                          void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * RPN objectness + localisation losses over all B*A anchors, one pass forward and one backward
+ * (cubercnn/modeling/proposal_generator/rpn.py:108-218: IoU-ness objectness targets, both terms weighted by the target
+ * and restricted to positive anchors).  logits [B][A], deltas [B][A][4], labels int8 [B][A] in {-1,0,1},
+ * matched_idx int64 [B][A], gt_boxes [B][G][4], anchors [A][4], weights4_host = BBOX_REG_WEIGHTS.
+ *   fwd: acc6 = {sum cls, sum loc, #pos, #neg, sum sigmoid(pos), sum sigmoid(non-pos)} (un-normalised)
+ *   bwd: dlogits / ddeltas (dense, zero off the positives) scaled by the device scalars *g_cls / *g_loc
+ * ------------------------------------------------------------------------------------------ */
+int32_t c3d_rpn_loss_fwd(const float* logits, const float* deltas, const int8_t* labels, const int64_t* matched_idx,
+                         const float* gt_boxes, const float* anchors, int32_t B, int64_t A, int32_t G,
+                         const float* weights4_host, float* acc6, void* stream);
+int32_t c3d_rpn_loss_bwd(const float* logits, const float* deltas, const int8_t* labels, const int64_t* matched_idx,
+                         const float* gt_boxes, const float* anchors, int32_t B, int64_t A, int32_t G,
+                         const float* weights4_host, const float* g_cls, const float* g_loc, float* dlogits,
+                         float* ddeltas, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * CubeHead decode + disentangled 3D corner losses, fused forward / backward (one thread per RoI).
  * Replaces the ATen micro-kernels of cubercnn/modeling/roi_heads/roi_heads.py:409-525 (decode) and :527-740
  * (xy / z / dims L1 corner losses, chamfer pose + joint losses, sqrt(2)*exp(-u) weighting), with

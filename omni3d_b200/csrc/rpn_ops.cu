@@ -125,3 +125,123 @@ extern "C" int32_t c3d_anchor_match(const float* anchors, int64_t A, const float
                                               reinterpret_cast<signed char*>(labels), max_ioa, rowmax_ws, best_idx);
   return check_launch("anchor_match");
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// RPN losses over all B*A anchors in one pass each way (replaces ~80 ATen launches over (B,A[,4]) tensors):
+//   objectness: BCE-with-logits against the IoU-ness target of the matched GT, weighted by that target, positives only
+//   localisation: L1 between predicted and encoded GT deltas, weighted by the target, positives only
+// (cubercnn/modeling/proposal_generator/rpn.py:108-218 losses(); formulas as omni3d_b200/cubercnn/rpn.py RPNWithIgnore.losses).
+// acc[6] += {sum cls, sum loc, #pos, #neg, sum sigmoid over pos, sum sigmoid over non-pos}
+namespace c3d {
+
+struct RpnPos { float target; float gd[4]; };
+
+__device__ __forceinline__ RpnPos rpn_targets(const float4 a, const float4 g, float wx, float wy, float ww, float wh) {
+  RpnPos r;
+  const float iw = fmaxf(fminf(a.z, g.z) - fmaxf(a.x, g.x), 0.f), ih = fmaxf(fminf(a.w, g.w) - fmaxf(a.y, g.y), 0.f);
+  const float inter = iw * ih;
+  r.target = inter / ((a.z - a.x) * (a.w - a.y) + (g.z - g.x) * (g.w - g.y) - inter);
+  const float sw = a.z - a.x, sh = a.w - a.y, scx = a.x + 0.5f * sw, scy = a.y + 0.5f * sh;
+  const float tw = g.z - g.x, th = g.w - g.y, tcx = g.x + 0.5f * tw, tcy = g.y + 0.5f * th;
+  r.gd[0] = wx * (tcx - scx) / sw; r.gd[1] = wy * (tcy - scy) / sh;
+  r.gd[2] = ww * logf(tw / sw); r.gd[3] = wh * logf(th / sh);
+  return r;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+rpn_loss_kernel(const float* __restrict__ logits, const float4* __restrict__ deltas, const signed char* __restrict__ labels,
+                const long long* __restrict__ matched_idx, const float4* __restrict__ gt, const float4* __restrict__ anchors,
+                int B, int A, int G, float wx, float wy, float ww, float wh, float* __restrict__ acc,
+                const float* __restrict__ g_cls, const float* __restrict__ g_loc, float* __restrict__ dlogits,
+                float4* __restrict__ ddeltas) {
+  const long long total = (long long)B * A;
+  float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float gc = BWD ? *g_cls : 0.f, gl = BWD ? *g_loc : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int lab = labels[i];
+    const float x = logits[i];
+    const float sig = 1.f / (1.f + __expf(-x));
+    const bool pos = lab == 1;
+    float dl = 0.f;
+    float4 dd = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!BWD) {
+      s[2] += pos ? 1.f : 0.f; s[3] += lab == 0 ? 1.f : 0.f;
+      s[4] += pos ? sig : 0.f; s[5] += pos ? 0.f : sig;
+    }
+    if (pos) {
+      const int b = (int)(i / A), a = (int)(i - (long long)b * A);
+      const RpnPos t = rpn_targets(anchors[a], gt[(size_t)b * G + matched_idx[i]], wx, wy, ww, wh);
+      const float4 d = deltas[i];
+      const float e[4] = {d.x - t.gd[0], d.y - t.gd[1], d.z - t.gd[2], d.w - t.gd[3]};
+      if (!BWD) {
+        const float bce = fmaxf(x, 0.f) - x * t.target + log1pf(__expf(-fabsf(x)));
+        s[0] += bce * t.target;
+        s[1] += (fabsf(e[0]) + fabsf(e[1]) + fabsf(e[2]) + fabsf(e[3])) * t.target;
+      } else {
+        const float tt = t.target;
+        dl = gc * (sig - tt) * tt;
+        auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
+        dd = make_float4(gl * tt * sgn(e[0]), gl * tt * sgn(e[1]), gl * tt * sgn(e[2]), gl * tt * sgn(e[3]));
+      }
+    }
+    if (BWD) { dlogits[i] = dl; ddeltas[i] = dd; }
+  }
+  if (!BWD) {
+    __shared__ float sm[6][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      float v = s[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sm[k][w] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v += sm[threadIdx.x][j];
+      atomicAdd(acc + threadIdx.x, v);
+    }
+  }
+}
+
+}  // namespace c3d
+
+extern "C" int32_t c3d_rpn_loss_fwd(const float* logits, const float* deltas, const int8_t* labels, const int64_t* matched_idx,
+                                    const float* gt_boxes, const float* anchors, int32_t B, int64_t A, int32_t G,
+                                    const float* weights4_host, float* acc6, void* stream) {
+  if (!logits || !deltas || !labels || !matched_idx || !gt_boxes || !anchors || !weights4_host || !acc6)
+    return set_error(C3D_EINVAL, "rpn_loss: null pointer");
+  if (B < 1 || A < 1 || A > 0x7fffffffLL || G < 1) return set_error(C3D_EINVAL, "rpn_loss: bad sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(acc6, 0, 6 * sizeof(float), st);
+  if (e != cudaSuccess) return set_error(C3D_ECUDA, "rpn_loss memset: %s", cudaGetErrorString(e));
+  long long blocks = ((long long)B * A + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  rpn_loss_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(logits, reinterpret_cast<const float4*>(deltas),
+      reinterpret_cast<const signed char*>(labels), reinterpret_cast<const long long*>(matched_idx),
+      reinterpret_cast<const float4*>(gt_boxes), reinterpret_cast<const float4*>(anchors), B, (int)A, G, weights4_host[0],
+      weights4_host[1], weights4_host[2], weights4_host[3], acc6, nullptr, nullptr, nullptr, nullptr);
+  return check_launch("rpn_loss_fwd");
+}
+
+extern "C" int32_t c3d_rpn_loss_bwd(const float* logits, const float* deltas, const int8_t* labels, const int64_t* matched_idx,
+                                    const float* gt_boxes, const float* anchors, int32_t B, int64_t A, int32_t G,
+                                    const float* weights4_host, const float* g_cls, const float* g_loc, float* dlogits,
+                                    float* ddeltas, void* stream) {
+  if (!logits || !deltas || !labels || !matched_idx || !gt_boxes || !anchors || !weights4_host || !g_cls || !g_loc || !dlogits ||
+      !ddeltas)
+    return set_error(C3D_EINVAL, "rpn_loss_bwd: null pointer");
+  if (B < 1 || A < 1 || A > 0x7fffffffLL || G < 1) return set_error(C3D_EINVAL, "rpn_loss_bwd: bad sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long blocks = ((long long)B * A + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  rpn_loss_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(logits, reinterpret_cast<const float4*>(deltas),
+      reinterpret_cast<const signed char*>(labels), reinterpret_cast<const long long*>(matched_idx),
+      reinterpret_cast<const float4*>(gt_boxes), reinterpret_cast<const float4*>(anchors), B, (int)A, G, weights4_host[0],
+      weights4_host[1], weights4_host[2], weights4_host[3], nullptr, g_cls, g_loc, dlogits,
+      reinterpret_cast<float4*>(ddeltas));
+  return check_launch("rpn_loss_bwd");
+}

@@ -179,6 +179,7 @@ class RPNWithIgnore(nn.Module):
         # torchvision.ops.batched_nms switches from the coordinate trick to per-category NMS above this many
         # box coordinates (20000 on CUDA, 4000 on CPU); the reference runs on CUDA.
         self.nms_trick_max_numel = 20000
+        self.fused_loss = True                 # c3d_rpn_loss_fwd/bwd instead of the (B,A)-shaped torch formulation
         self.stats = {}
 
     # -- labels -----------------------------------------------------------------------------------
@@ -256,6 +257,16 @@ class RPNWithIgnore(nn.Module):
     # -- losses -----------------------------------------------------------------------------------
     def losses(self, anchors, logits, deltas, labels, matched_idx, gt_boxes):
         B = labels.shape[0]
+        norm = self.batch_size_per_image * B
+        if logits.is_cuda and self.fused_loss:
+            from ..nnfunc import RPNLossSums
+            acc = RPNLossSums.apply(logits, deltas, labels, matched_idx, gt_boxes, anchors, self.weights)
+            with torch.no_grad():
+                a = acc.detach()
+                npos, rest = a[2], labels.numel() - a[2]
+                self.stats = {"rpn/num_pos_anchors": npos / B, "rpn/num_neg_anchors": a[3] / B,
+                              "rpn/conf_pos_anchors": a[4] / npos.clamp(min=1), "rpn/conf_neg_anchors": a[5] / rest.clamp(min=1)}
+            return {"rpn/cls": acc[0] / norm, "rpn/loc": acc[1] / norm}
         pos = labels == 1
         matched = torch.gather(gt_boxes, 1, matched_idx[:, :, None].expand(-1, -1, 4))       # (B,A,4)
         a = anchors.unsqueeze(0).expand(B, -1, -1)

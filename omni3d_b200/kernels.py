@@ -44,6 +44,8 @@ def _bind():
     L.c3d_nms_workspace_bytes.restype = ctypes.c_size_t
     L.c3d_nms_workspace_bytes.argtypes = [i32, i32]
     sig["c3d_nms_batched"] = [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, ctypes.c_size_t, vp]
+    sig["c3d_rpn_loss_fwd"] = [vp, vp, vp, vp, vp, vp, i32, i64, i32, ctypes.POINTER(f32), vp, vp]
+    sig["c3d_rpn_loss_bwd"] = [vp, vp, vp, vp, vp, vp, i32, i64, i32, ctypes.POINTER(f32), vp, vp, vp, vp, vp]
     sig["c3d_anchor_match"] = [vp, i64, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp]
     sig["c3d_preprocess_image_u8"] = [vp, i32, i32, vp, i32, i32, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), vp]
     for name, args in sig.items():
@@ -221,6 +223,28 @@ def anchor_match(anchors, gt_boxes, gt_valid, gt_ign, fg_thresh):
     _lib.check(L.c3d_anchor_match(_p(anchors), A, _p(gt_boxes), _p(v8), _p(i8), B, G, float(fg_thresh), _p(idx), _p(iou),
                                   _p(lab), _p(ioa), _p(best), _p(ws), _st()), launches=3)
     return idx, iou, lab, ioa, best
+
+
+def rpn_loss_fwd(logits, deltas, labels, matched_idx, gt_boxes, anchors, weights):
+    """-> acc (6,) fp32: [sum cls, sum loc, #pos, #neg, sum sigmoid over positives, sum sigmoid over the rest]."""
+    L = _bind()
+    B, A = logits.shape
+    acc = torch.empty(6, dtype=torch.float32, device=logits.device)
+    w = (f32 * 4)(*[float(v) for v in weights])
+    _lib.check(L.c3d_rpn_loss_fwd(_p(logits), _p(deltas), _p(labels), _p(matched_idx), _p(gt_boxes), _p(anchors), B, A,
+                                  gt_boxes.shape[1], w, _p(acc), _st()))
+    return acc
+
+
+def rpn_loss_bwd(logits, deltas, labels, matched_idx, gt_boxes, anchors, weights, g_cls, g_loc):
+    L = _bind()
+    B, A = logits.shape
+    dl = torch.empty_like(logits)
+    dd = torch.empty_like(deltas)
+    w = (f32 * 4)(*[float(v) for v in weights])
+    _lib.check(L.c3d_rpn_loss_bwd(_p(logits), _p(deltas), _p(labels), _p(matched_idx), _p(gt_boxes), _p(anchors), B, A,
+                                  gt_boxes.shape[1], w, _p(g_cls), _p(g_loc), _p(dl), _p(dd), _st()))
+    return dl, dd
 
 
 def bias_act_bwd(dout, out, relu, dbias):

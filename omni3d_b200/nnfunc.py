@@ -219,3 +219,24 @@ class CubeLossRows(torch.autograd.Function):
     def backward(ctx, dout):
         raw, aux = ctx.saved_tensors
         return Kx.cube_loss_bwd(raw, aux, dout[:, :6].contiguous().float()), None
+
+
+class RPNLossSums(torch.autograd.Function):
+    """logits (B,A), deltas (B,A,4) fp32 + labels / matches -> (6,) [sum cls, sum loc, #pos, #neg, sum sig(pos),
+    sum sig(rest)]; gradients flow from the first two entries only (c3d_rpn_loss_fwd / _bwd, one launch each)."""
+
+    @staticmethod
+    def forward(ctx, logits, deltas, labels, matched_idx, gt_boxes, anchors, weights):
+        logits, deltas = logits.contiguous().float(), deltas.contiguous().float()
+        labels, matched_idx = labels.to(torch.int8).contiguous(), matched_idx.contiguous()
+        gt_boxes, anchors = gt_boxes.contiguous().float(), anchors.contiguous().float()
+        ctx.save_for_backward(logits, deltas, labels, matched_idx, gt_boxes, anchors)
+        ctx.weights = tuple(weights)
+        return Kx.rpn_loss_fwd(logits, deltas, labels, matched_idx, gt_boxes, anchors, weights)
+
+    @staticmethod
+    def backward(ctx, dacc):
+        logits, deltas, labels, matched_idx, gt_boxes, anchors = ctx.saved_tensors
+        dacc = dacc.contiguous().float()
+        dl, dd = Kx.rpn_loss_bwd(logits, deltas, labels, matched_idx, gt_boxes, anchors, ctx.weights, dacc[0:1], dacc[1:2])
+        return dl, dd, None, None, None, None, None

@@ -287,3 +287,35 @@ def test_anchor_match_kernel_equals_torch_formulation(B, G, thr):
             assert torch.equal(a.cpu(), b), n
         else:
             assert torch.equal(a.cpu(), b), n
+
+
+def test_fused_rpn_loss_matches_torch_formulation():
+    """c3d_rpn_loss_fwd/bwd == RPNWithIgnore.losses() written with torch ops (values, statistics and both gradients)."""
+    from omni3d_b200.cubercnn import rpn as prpn
+    ag = prpn.AnchorGenerator([[32], [64], [128], [256], [512]], [[0.5, 1.0, 2.0]], [4, 8, 16, 32, 64])
+    anchors = torch.cat(ag([(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)], torch.device("cuda")))
+    A, B, G = anchors.shape[0], 3, 5
+    g = torch.Generator(device="cuda").manual_seed(7)
+    xy = torch.rand(B, G, 2, device="cuda", generator=g) * torch.tensor([160.0, 110.0], device="cuda")
+    boxes = torch.cat([xy, xy + torch.rand(B, G, 2, device="cuda", generator=g) * 100 + 8], -1)
+    head = prpn.RPNWithIgnore.__new__(prpn.RPNWithIgnore)
+    head.iou_thresholds, head.weights, head.batch_size_per_image = [0.3, 0.3], (1.0, 1.0, 1.0, 1.0), 256
+    valid = torch.ones(B, G, dtype=torch.bool, device="cuda")
+    idx, _, lab, _, _ = head.match_anchors(anchors, boxes, valid)
+    lab = torch.where(torch.rand(B, A, device="cuda", generator=g) < 0.1, torch.full_like(lab, -1), lab)   # some ignored
+    out = {}
+    for fused in (False, True):
+        head.fused_loss = fused
+        logits = torch.randn(B, A, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)).requires_grad_(True)
+        deltas = (0.5 * torch.randn(B, A, 4, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))).requires_grad_(True)
+        losses = head.losses(anchors, logits, deltas, lab, idx, boxes)
+        (losses["rpn/cls"] * 1.7 + losses["rpn/loc"] * 0.6).backward()
+        out[fused] = (losses, dict(head.stats), logits.grad, deltas.grad)
+    for k in ("rpn/cls", "rpn/loc"):
+        a, b = float(out[True][0][k]), float(out[False][0][k])
+        assert abs(a - b) <= 1e-4 * abs(b) + 1e-6, (k, a, b)
+    for k, v in out[False][1].items():
+        assert abs(float(out[True][1][k]) - float(v)) <= 1e-4 * abs(float(v)) + 1e-5, k
+    for i in (2, 3):
+        ref = out[False][i]
+        assert (out[True][i] - ref).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-9
