@@ -86,9 +86,27 @@ def bn_apply(y, mean, rstd, gamma, beta, residual=None, relu=True, out=None):
     return out
 
 
+def pixel_stride(t):
+    """t (N,H,W,C) that is either dense or a channel slice of a dense NHWC buffer (what autograd hands back for the
+    inputs of a torch.cat over channels) -> its pixel stride in elements, or None if it needs a .contiguous() copy."""
+    if t.dim() != 4 or t.stride(3) != 1:
+        return None
+    N, H, W, C = t.shape
+    s = t.stride(2)
+    if s < C or s % 8 or (t.storage_offset() * t.element_size()) % 16:
+        return None
+    if (H > 1 and t.stride(1) != W * s) or (N > 1 and t.stride(0) != H * W * s):
+        return None
+    return s
+
+
 def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres, frozen=False):
-    """-> dy (bf16, like y), dres (bf16 or None); dgamma/dbeta (fp32 [C]) are accumulated in place."""
+    """-> dy (bf16, like y), dres (bf16 or None); dgamma/dbeta (fp32 [C]) are accumulated in place.  `dout` may be a
+    channel slice of a wider NHWC gradient (read in place through its pixel stride)."""
     L = _bind()
+    ds = pixel_stride(dout)
+    if ds is None:
+        dout, ds = dout.contiguous(), 0
     C = y.shape[-1]
     P = y.numel() // C
     blocks = L.c3d_bn_bwd_blocks(P, C)
@@ -98,7 +116,7 @@ def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres, froz
     dres = torch.empty_like(y) if want_dres else None
     scratch = torch.empty(128 * 2 * C, device=y.device, dtype=torch.float64)
     _lib.check(L.c3d_bn_bwd(_p(dout), _p(out), _p(y), _p(mean), _p(rstd), _p(gamma), int(relu), int(frozen), _p(partial), _p(coef),
-                            _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, 0, 0, 0, _p(scratch), _st()), launches=4)
+                            _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, ds, 0, 0, _p(scratch), _st()), launches=4)
     return dy, dres
 
 
@@ -113,8 +131,11 @@ def maxpool2_fwd(x):
 def maxpool2_bwd(x, dy):
     L = _bind()
     N, H, W, C = x.shape
+    ds = pixel_stride(dy)
+    if ds is None:
+        dy, ds = dy.contiguous(), 0
     dx = torch.empty_like(x)
-    _lib.check(L.c3d_maxpool2_bwd(_p(x), _p(dy), _p(dx), N, H, W, C, 0, 0, _st()))
+    _lib.check(L.c3d_maxpool2_bwd(_p(x), _p(dy), _p(dx), N, H, W, C, 0, ds, _st()))
     return dx
 
 

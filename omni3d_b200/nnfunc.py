@@ -136,7 +136,6 @@ class ConvBNAct(torch.autograd.Function):
     def backward(ctx, dout):
         x, w, gamma, y, mean, rstd, out, beta = ctx.saved_tensors
         stride, pad, relu, training, has_res = ctx.cfg
-        dout = dout.contiguous()
         dgamma, ret_g = _grad_slot(gamma)
         dbeta, ret_b = _grad_slot(beta)
         dy, dres = Kx.bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, has_res and ctx.needs_input_grad[6],
@@ -182,7 +181,7 @@ class MaxPool2(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
-        return Kx.maxpool2_bwd(x, dy.contiguous())
+        return Kx.maxpool2_bwd(x, dy)
 
 
 class ROIAlign(torch.autograd.Function):
