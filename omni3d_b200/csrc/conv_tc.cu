@@ -718,9 +718,7 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   if (Cout % 128 != 0) BN = (Cout % 64 == 0) ? 64 : (Cout % 32 == 0 ? 32 : 16);
   // persistent + double-buffered TMEM pays off for the tensor-bound shapes; the tiny-K / memory-bound ones
   // (Cin < 64, or 1x1 with Cin <= 64) run better as many short CTAs (measured, profiles/)
-  static const bool p1x1 = getenv("C3D_CONV_P1X1") != nullptr;       // experiment: persistent BN=256 for thin 1x1 layers
-  const bool persistent = !non_persistent && BK == 64 && BN >= 64 &&
-                          (!(d->KH == 1 && Cin <= 64) || (p1x1 && Cout % 256 == 0));
+  const bool persistent = !non_persistent && BK == 64 && BN >= 64 && !(d->KH == 1 && Cin <= 64);
   if (persistent && allow_n256 && Cout % 256 == 0) BN = 256;
   const int Ho = d->out_h > 0 ? d->out_h : (d->H + 2 * d->pad - d->KH) / d->stride + 1;
   const int Wo = d->out_w > 0 ? d->out_w : (d->W + 2 * d->pad - d->KW) / d->stride + 1;

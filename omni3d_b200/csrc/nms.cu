@@ -32,43 +32,36 @@ __device__ __forceinline__ float4 shift(float4 b, float off) {
 __global__ void nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ nvalid, int n, int words,
                                 float thr, const float* __restrict__ cats, const float* __restrict__ maxc,
                                 int trick_max_numel, unsigned long long* __restrict__ mask) {
-  // one block per (image, 64-row strip): walks the column tiles to the right of the diagonal (a block per tile was
-  // launch/drain bound: 64 iterations of work per 64-thread block)
-  const int b = blockIdx.y, row_blk = blockIdx.x;
+  const int b = blockIdx.z, row_blk = blockIdx.y, col_blk = blockIdx.x;
+  if (col_blk < row_blk) return;
   const int nv = nvalid[b];
-  const int row0 = row_blk * 64;
-  if (row0 >= nv) return;
-  __shared__ float4 cb[2][64];
-  __shared__ float cc[2][64];
+  const int row0 = row_blk * 64, col0 = col_blk * 64;
+  if (row0 >= nv || col0 >= nv) return;
+  __shared__ float4 cb[64];
+  __shared__ float cc[64];
   const int t = threadIdx.x;
   const float4* bx = boxes + (size_t)b * n;
   const float* cx = cats ? cats + (size_t)b * n : nullptr;
   const bool trick = cx && (4 * nv <= trick_max_numel);
   const float scale = trick ? (maxc[b] + 1.0f) : 0.f;
+  if (col0 + t < nv) {
+    float c = cx ? cx[col0 + t] : 0.f;
+    cc[t] = c;
+    cb[t] = trick ? shift(bx[col0 + t], c * scale) : bx[col0 + t];
+  }
+  __syncthreads();
   const int i = row0 + t;
-  const float myc = (cx && i < nv) ? cx[i] : 0.f;
-  float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i < nv) me = trick ? shift(bx[i], myc * scale) : bx[i];
-  const int last_blk = (nv - 1) / 64;
-  int buf = 0;
-  for (int col_blk = row_blk; col_blk <= last_blk; ++col_blk, buf ^= 1) {
-    const int col0 = col_blk * 64;
-    if (col0 + t < nv) {
-      const float c = cx ? cx[col0 + t] : 0.f;
-      cc[buf][t] = c;
-      cb[buf][t] = trick ? shift(bx[col0 + t], c * scale) : bx[col0 + t];
-    }
-    __syncthreads();                       // double-buffered tiles: one barrier per column tile
-    if (i < nv) {
-      unsigned long long bits = 0;
-      const int ncol = min(64, nv - col0);
-      const int start = (row_blk == col_blk) ? t + 1 : 0;
-      for (int j = start; j < ncol; ++j)
-        // different categories never suppress each other: per-category mode by definition, coordinate-trick mode
-        // because the shifted boxes are disjoint (IoU 0 <= thr) — skip the IoU arithmetic for those pairs
-        if (cc[buf][j] == myc && iou_gt(me, cb[buf][j], thr)) bits |= 1ULL << j;
-      mask[((size_t)b * n + i) * words + col_blk] = bits;
-    }
+  if (i < nv) {
+    const float myc = cx ? cx[i] : 0.f;
+    const float4 me = trick ? shift(bx[i], myc * scale) : bx[i];
+    unsigned long long bits = 0;
+    const int ncol = min(64, nv - col0);
+    const int start = (row_blk == col_blk) ? t + 1 : 0;
+    for (int j = start; j < ncol; ++j)
+      // different categories never suppress each other: per-category mode by definition, coordinate-trick mode because
+      // the shifted boxes are disjoint (IoU 0 <= thr) — skip the IoU arithmetic for ~(levels-1)/levels of the pairs
+      if (cc[j] == myc && iou_gt(me, cb[j], thr)) bits |= 1ULL << j;
+    mask[((size_t)b * n + i) * words + col_blk] = bits;
   }
 }
 
@@ -120,7 +113,7 @@ extern "C" int32_t c3d_nms_batched(const float* boxes, const int32_t* nvalid, co
   cudaStream_t st = (cudaStream_t)stream;
   // rows whose diagonal tile is skipped (beyond nvalid) are never read; no memset needed because the scan
   // only reads words >= i/64 of rows i < nvalid, all of which kernel 1 writes when col0 < nvalid.
-  dim3 grid(words, B);
+  dim3 grid(words, words, B);
   if (cats && !maxc) return set_error(C3D_EINVAL, "nms: cats given without maxc");
   nms_mask_kernel<<<grid, 64, 0, st>>>((const float4*)boxes, nvalid, n, words, iou_thresh, cats, maxc,
                                        trick_max_numel, (unsigned long long*)workspace);
