@@ -128,28 +128,27 @@ class FlatSGDTrainer:
         self.status_event = None
         self.iteration = 0
         self.stabilize = cfg.MODEL.STABILIZE > 0
-        # CUDA-graph replay of the step body (see step()).  Multi-GPU: opt-in (NCCL all-reduce inside the graph).
+        # CUDA-graph replay of the step body (see step() / _body()); C3D_TRAIN_GRAPH=0 disables it
         if use_graph is None:
-            env = os.environ.get("C3D_TRAIN_GRAPH")
-            use_graph = (env != "0") if self.world == 1 or env is not None else False
+            use_graph = os.environ.get("C3D_TRAIN_GRAPH") != "0"
         self.use_graph = bool(use_graph) and self.on_cuda and hasattr(model, "forward_staged")
         self.graph_warmup = 2
-        self.graph = self.static = self.graph_sig = self.graph_losses = None
+        self.graph = self.static = self.graph_sig = self.graph_losses = self.graph_vec = None
         self.graph_launches = 0
         self.lr_dev = torch.zeros(1, device=dev)
 
     # -------------------------------------------------------------------------------------------------
-    def _body(self, staged, lr):
-        """zero grads, forward, stabiliser, backward, all-reduce, finite check, SGD — device work only (no host reads),
-        so the whole body can be replayed from a CUDA graph.  `lr`: python float (eager) or 1-element device tensor."""
-        model, world = self.model, self.world
+    def _seg_forward(self, staged):
+        """segment A: zero the gradient arena, forward, the 10 local losses as one vector."""
+        model = self.model
         self.flat_g.zero_()
         loss_dict = model.forward_staged(staged) if hasattr(model, "forward_staged") else model(staged)
         vec = torch.stack([loss_dict[k].detach().float() if k in loss_dict else self.flat_g.new_zeros(())
                            for k in LOSS_KEYS])
-        if world > 1:                                   # allreduce_dict, train_net.py:471-498 (mean over ranks)
-            dist.all_reduce(vec)
-            vec /= world
+        return loss_dict, vec
+
+    def _seg_backward(self, loss_dict, vec):
+        """segment B (vec = losses already averaged over ranks): device-side stabiliser, backward."""
         total_reduced = vec.sum()
         st = self.state
         recent = torch.where(st[3] > 0, st[0], total_reduced * 2.0)
@@ -159,13 +158,16 @@ class FlatSGDTrainer:
         losses = sum(loss_dict.values())
         losses = torch.where(diverging, losses.clip(0, 1), losses)
         losses.backward()
-        if world > 1:                                   # C1: one gradient all-reduce (mean) over NVLink
-            dist.all_reduce(self.flat_g[:self.n_update])
+        return total_reduced, recent, diverging
+
+    def _seg_update(self, vec, total_reduced, recent, diverging, lr):
+        """segment C (gradients already summed over ranks): finite scan, fused SGD, controller state, status vector."""
+        st = self.state
         self.flag.copy_(diverging.to(torch.int32).reshape(1))
         if self.stabilize:
             Kx.grad_finite(self.flat_g[:self.n_update], self.flag)
         S = self.cfg.SOLVER
-        gs = 1.0 / world
+        gs = 1.0 / self.world
         d0, d1 = self.bounds["decay"]
         n0, n1 = self.bounds["nodecay"]
         Kx.sgd_momentum(self.flat_p[d0:d1], self.flat_g[d0:d1], self.flat_m[d0:d1], lr, S.MOMENTUM, S.WEIGHT_DECAY, gs,
@@ -176,6 +178,26 @@ class FlatSGDTrainer:
         new_recent = torch.where(diverging, recent, recent * (1 - GAMMA_ROLL) + total_reduced * GAMMA_ROLL)
         self.state.copy_(torch.stack([new_recent, st[1] + (1 - skipped), st[2] + skipped, torch.ones_like(st[3])]))
         self.status_dev.copy_(torch.cat([vec, self.state]))
+
+    def _reduce_losses(self, vec):
+        if self.world > 1:                              # allreduce_dict, train_net.py:471-498 (mean over ranks)
+            dist.all_reduce(vec)
+            vec /= self.world
+
+    def _reduce_grads(self):
+        if self.world > 1:                              # C1: one gradient all-reduce (sum; the update divides) over NVLink
+            dist.all_reduce(self.flat_g[:self.n_update])
+
+    def _body(self, staged, lr):
+        """zero grads, forward, loss all-reduce, stabiliser, backward, gradient all-reduce, finite check, SGD — device
+        work only (no host reads).  One GPU: the whole body is ONE CUDA graph.  Several GPUs: the three segments are
+        three graphs sharing a memory pool and the two NCCL all-reduces stay eager between them (no collective is ever
+        recorded, so a rank that falls back to eager execution still issues the same collective sequence)."""
+        loss_dict, vec = self._seg_forward(staged)
+        self._reduce_losses(vec)
+        tr, recent, div = self._seg_backward(loss_dict, vec)
+        self._reduce_grads()
+        self._seg_update(vec, tr, recent, div, lr)
         return loss_dict
 
     @staticmethod
@@ -213,7 +235,7 @@ class FlatSGDTrainer:
             else:
                 self._copy_into_static(staged)
                 self.lr_dev.fill_(lr)
-                self.graph.replay()
+                self._replay()
                 _lib.LAUNCHES["n"] += self.graph_launches
                 loss_dict = self.graph_losses
         if loss_dict is None:
@@ -228,19 +250,43 @@ class FlatSGDTrainer:
         self.iteration += 1
         return loss_dict
 
+    def _replay(self):
+        if len(self.graph) == 1:
+            self.graph[0].replay()
+            return
+        gA, gB, gC = self.graph
+        gA.replay()
+        self._reduce_losses(self.graph_vec)
+        gB.replay()
+        self._reduce_grads()
+        gC.replay()
+
     def _capture(self, staged, sig, lr):
         try:
             self.static = {"images": [im.clone() for im in staged["images"]], "sizes": staged["sizes"],
                            "meta": staged["meta"].clone(), "gt": {k: v.clone() for k, v in staged["gt"].items()}}
             self.lr_dev.fill_(lr)
-            graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             n0 = _lib.LAUNCHES["n"]
-            with torch.cuda.graph(graph):
-                losses = self._body(self.static, self.lr_dev)
+            mode = dict(capture_error_mode="thread_local")      # the NCCL watchdog thread may poll events meanwhile
+            if self.world == 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, **mode):
+                    losses = self._body(self.static, self.lr_dev)
+                graphs = [g]
+            else:
+                pool = torch.cuda.graph_pool_handle()
+                gA, gB, gC = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gA, pool=pool, **mode):
+                    losses, vec = self._seg_forward(self.static)
+                with torch.cuda.graph(gB, pool=pool, **mode):
+                    tr, recent, div = self._seg_backward(losses, vec)
+                with torch.cuda.graph(gC, pool=pool, **mode):
+                    self._seg_update(vec, tr, recent, div, self.lr_dev)
+                graphs, self.graph_vec = [gA, gB, gC], vec
             self.graph_launches = _lib.LAUNCHES["n"] - n0
-            self.graph, self.graph_sig, self.graph_losses = graph, sig, losses
-            graph.replay()          # recording does not execute: run the step that was just recorded
+            self.graph, self.graph_sig, self.graph_losses = graphs, sig, losses
+            self._replay()          # recording does not execute: run the step that was just recorded
             return losses
         except Exception as e:      # noqa: BLE001 — never silently: say so, then keep training eagerly
             import sys
