@@ -269,6 +269,9 @@ class FlatSGDTrainer:
             torch.cuda.synchronize()
             n0 = _lib.LAUNCHES["n"]
             mode = dict(capture_error_mode="thread_local")      # the NCCL watchdog thread may poll events meanwhile
+            quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+            if quiet is not None:                               # backward is recorded on the capture stream by design
+                quiet(False)
             if self.world == 1:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, **mode):
