@@ -193,6 +193,13 @@ int32_t c3d_nms_batched(const float* boxes, const int32_t* nvalid, const float* 
                         int32_t trick_max_numel, int32_t B, int32_t n, float iou_thresh,
                         int32_t max_keep, int32_t* keep_idx, int32_t* keep_cnt, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* same result when the caller knows the categories are the integers 0..ncat-1 (ncat <= 16; boxes with another value are
+ * dropped): candidates are split per category first, so suppression tiles and the greedy scans run inside a category
+ * only.  max_per_cat_hint (0 = unknown) sizes the tile grid (performance only). */
+int32_t c3d_nms_batched_grouped(const float* boxes, const int32_t* nvalid, const float* cats, const float* maxc,
+                                int32_t trick_max_numel, int32_t B, int32_t n, float iou_thresh, int32_t max_keep,
+                                int32_t ncat, int32_t max_per_cat_hint, int32_t* keep_idx, int32_t* keep_cnt,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * RPN anchor <-> ground-truth matching for a whole batch (two passes, GT boxes of an image in shared memory).

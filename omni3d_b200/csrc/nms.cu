@@ -8,6 +8,7 @@
 //   kernel 1: 64x64 tiles of the upper-triangular suppression bit matrix (one uint64 per row/tile);
 //   kernel 2: one warp per image walks the rows in score order keeping the live "removed" bitset in
 //             registers (4 words per lane, up to 8192 candidates), writes the first `max_keep` survivors.
+#include <stdlib.h>
 #include "c3d_common.cuh"
 
 namespace c3d {
@@ -92,18 +93,145 @@ __global__ void nms_scan_kernel(const unsigned long long* __restrict__ mask, con
   if (lane == 0) keep_cnt[b] = cnt;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Grouped variant: boxes of different categories never suppress each other, so the candidates of an image are first
+// split (stably, i.e. still in score order) into their categories and every category is solved on its own:
+//   G  one block per image: per-category counts, offsets and the permutation (category-major, score order inside)
+//   M  64x64 suppression tiles inside each category only   (5 levels x 2000 boxes: 3.4x fewer pairs than 8300^2 / 2)
+//   S  one warp per (image, category) greedy scan           (5x more warps, each over <= 2000 instead of 8300 rows)
+//   C  one warp per image: survivors back in global score order, first max_keep
+// Results are identical to the single-list kernels above (same IoU arithmetic, same coordinate-trick shifts).
+constexpr int kMaxCat = 16;
+
+__global__ void __launch_bounds__(32 * kMaxCat)
+nms_group_kernel(const float* __restrict__ cats, const int* __restrict__ nvalid, int n, int ncat, int* __restrict__ perm,
+                 int* __restrict__ cat_off /*[B][kMaxCat+1]*/, unsigned char* __restrict__ keepflag) {
+  const int b = blockIdx.x, c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = nvalid[b];
+  const float* cx = cats + (size_t)b * n;
+  __shared__ int cnt[kMaxCat + 1];
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) keepflag[(size_t)b * n + i] = 0;
+  int mine = 0;
+  if (c < ncat)
+    for (int i0 = 0; i0 < nv; i0 += 32) {
+      const int i = i0 + lane;
+      const bool f = i < nv && (int)cx[i] == c;
+      mine += __popc(__ballot_sync(0xffffffffu, f));
+    }
+  if (lane == 0) cnt[c] = c < ncat ? mine : 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k < kMaxCat; ++k) { const int v = cnt[k]; cnt[k] = acc; acc += v; }
+    cnt[kMaxCat] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x <= kMaxCat) cat_off[(size_t)b * (kMaxCat + 1) + threadIdx.x] = cnt[threadIdx.x];
+  if (c < ncat) {
+    int base = cnt[c];
+    for (int i0 = 0; i0 < nv; i0 += 32) {
+      const int i = i0 + lane;
+      const bool f = i < nv && (int)cx[i] == c;
+      const unsigned m = __ballot_sync(0xffffffffu, f);
+      if (f) perm[(size_t)b * n + base + __popc(m & ((1u << lane) - 1u))] = i;
+      base += __popc(m);
+    }
+  }
+}
+
+__global__ void nms_mask_grouped_kernel(const float4* __restrict__ boxes, const int* __restrict__ nvalid, int n, int words,
+                                        float thr, const float* __restrict__ maxc, int trick_max_numel,
+                                        const int* __restrict__ perm, const int* __restrict__ cat_off, int ncat,
+                                        unsigned long long* __restrict__ mask) {
+  const int b = blockIdx.z / ncat, c = blockIdx.z % ncat;
+  const int off = cat_off[(size_t)b * (kMaxCat + 1) + c], m = cat_off[(size_t)b * (kMaxCat + 1) + c + 1] - off;
+  if (m <= 0) return;
+  const int nv = nvalid[b];
+  const bool trick = 4 * nv <= trick_max_numel;
+  const float sh = trick ? (float)c * (maxc[b] + 1.0f) : 0.f;
+  const float4* bx = boxes + (size_t)b * n;
+  const int* pm = perm + (size_t)b * n + off;
+  const int tiles = (m + 63) / 64;
+  __shared__ float4 cb[64];
+  const int t = threadIdx.x;
+  for (int row_blk = blockIdx.y; row_blk < tiles; row_blk += gridDim.y)
+    for (int col_blk = blockIdx.x; col_blk < tiles; col_blk += gridDim.x) {
+      if (col_blk < row_blk) continue;
+      const int row0 = row_blk * 64, col0 = col_blk * 64;
+      __syncthreads();
+      if (col0 + t < m) cb[t] = trick ? shift(bx[pm[col0 + t]], sh) : bx[pm[col0 + t]];
+      __syncthreads();
+      const int i = row0 + t;
+      if (i < m) {
+        const float4 me = trick ? shift(bx[pm[i]], sh) : bx[pm[i]];
+        unsigned long long bits = 0;
+        const int ncol = min(64, m - col0);
+        const int start = (row_blk == col_blk) ? t + 1 : 0;
+        for (int j = start; j < ncol; ++j)
+          if (iou_gt(me, cb[j], thr)) bits |= 1ULL << j;
+        mask[((size_t)b * n + off + i) * words + col_blk] = bits;
+      }
+    }
+}
+
+__global__ void nms_scan_grouped_kernel(const unsigned long long* __restrict__ mask, int n, int words, int max_keep,
+                                        const int* __restrict__ perm, const int* __restrict__ cat_off, int ncat,
+                                        unsigned char* __restrict__ keepflag) {
+  const int b = blockIdx.x / ncat, c = blockIdx.x % ncat, lane = threadIdx.x;
+  const int off = cat_off[(size_t)b * (kMaxCat + 1) + c], m = cat_off[(size_t)b * (kMaxCat + 1) + c + 1] - off;
+  if (m <= 0) return;
+  const int wc = (m + 63) / 64;
+  unsigned long long r0 = 0, r1 = 0, r2 = 0, r3 = 0;     // removed bits: word w lives on lane w%32, slot w/32
+  int cnt = 0;
+  for (int i = 0; i < m && cnt < max_keep; ++i) {
+    const int w = i >> 6, slot = w >> 5, owner = w & 31;
+    unsigned long long word = slot == 0 ? r0 : (slot == 1 ? r1 : (slot == 2 ? r2 : r3));
+    word = __shfl_sync(0xffffffffu, word, owner);
+    if (!((word >> (i & 63)) & 1ULL)) {
+      if (lane == 0) keepflag[(size_t)b * n + perm[(size_t)b * n + off + i]] = 1;
+      ++cnt;
+      const unsigned long long* row = mask + ((size_t)b * n + off + i) * words;
+      int ww = lane;
+      if (ww >= w && ww < wc) r0 |= row[ww];
+      ww = lane + 32; if (ww >= w && ww < wc) r1 |= row[ww];
+      ww = lane + 64; if (ww >= w && ww < wc) r2 |= row[ww];
+      ww = lane + 96; if (ww >= w && ww < wc) r3 |= row[ww];
+    }
+  }
+}
+
+__global__ void nms_compact_kernel(const unsigned char* __restrict__ keepflag, const int* __restrict__ nvalid, int n,
+                                   int max_keep, int* __restrict__ keep_idx, int* __restrict__ keep_cnt) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int nv = nvalid[b];
+  int* out = keep_idx + (size_t)b * max_keep;
+  int cnt = 0;
+  for (int i0 = 0; i0 < nv && cnt < max_keep; i0 += 32) {
+    const int i = i0 + lane;
+    const bool f = i < nv && keepflag[(size_t)b * n + i];
+    const unsigned mk = __ballot_sync(0xffffffffu, f);
+    const int pos = cnt + __popc(mk & ((1u << lane) - 1u));
+    if (f && pos < max_keep) out[pos] = i;
+    cnt += __popc(mk);
+  }
+  if (cnt > max_keep) cnt = max_keep;
+  for (int k = cnt + lane; k < max_keep; k += 32) out[k] = -1;
+  if (lane == 0) keep_cnt[b] = cnt;
+}
+
 }  // namespace c3d
 
 extern "C" size_t c3d_nms_workspace_bytes(int32_t B, int32_t n) {
   if (B < 0 || n < 0) return 0;
   size_t words = (size_t)(n + 63) / 64;
-  return (size_t)B * n * words * 8 + 256;
+  // suppression bit matrix + (grouped path) permutation, keep flags and per-category offsets
+  return (size_t)B * n * words * 8 + 256 + (size_t)B * n * 4 + (size_t)B * n + (size_t)B * (c3d::kMaxCat + 1) * 4 + 256;
 }
 
-extern "C" int32_t c3d_nms_batched(const float* boxes, const int32_t* nvalid, const float* cats, const float* maxc,
-                                   int32_t trick_max_numel, int32_t B, int32_t n, float iou_thresh,
-                                   int32_t max_keep, int32_t* keep_idx, int32_t* keep_cnt, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+static int32_t nms_impl(const float* boxes, const int32_t* nvalid, const float* cats, const float* maxc,
+                        int32_t trick_max_numel, int32_t B, int32_t n, float iou_thresh, int32_t max_keep,
+                        int32_t* keep_idx, int32_t* keep_cnt, void* workspace, size_t workspace_bytes, void* stream,
+                        int ncat, int max_per_cat) {
   using namespace c3d;
   if (B == 0 || n == 0) return C3D_OK;
   if (!boxes || !nvalid || !keep_idx || !keep_cnt || !workspace) return set_error(C3D_EINVAL, "nms: null pointer");
@@ -113,11 +241,46 @@ extern "C" int32_t c3d_nms_batched(const float* boxes, const int32_t* nvalid, co
   cudaStream_t st = (cudaStream_t)stream;
   // rows whose diagonal tile is skipped (beyond nvalid) are never read; no memset needed because the scan
   // only reads words >= i/64 of rows i < nvalid, all of which kernel 1 writes when col0 < nvalid.
-  dim3 grid(words, words, B);
   if (cats && !maxc) return set_error(C3D_EINVAL, "nms: cats given without maxc");
+  static const bool single_list = getenv("C3D_NMS_SINGLE_LIST") != nullptr;
+  if (cats && ncat > 0 && ncat <= kMaxCat && !single_list) {
+    // workspace: [mask][perm int32 B*n][cat_off int32 B*(kMaxCat+1)][keepflag u8 B*n]
+    uint8_t* base = (uint8_t*)workspace + (((size_t)B * n * words * 8 + 255) & ~(size_t)255);
+    int* perm = (int*)base;
+    int* cat_off = perm + (size_t)B * n;
+    unsigned char* keepflag = (unsigned char*)(cat_off + (size_t)B * (kMaxCat + 1));
+    nms_group_kernel<<<B, 32 * kMaxCat, 0, st>>>(cats, nvalid, n, ncat, perm, cat_off, keepflag);
+    int tiles = ((max_per_cat > 0 ? (max_per_cat < n ? max_per_cat : n) : n) + 63) / 64;
+    if (tiles > 64) tiles = 64;                          // the kernel strides over further tiles if a category is larger
+    dim3 gm(tiles, tiles, B * ncat);
+    nms_mask_grouped_kernel<<<gm, 64, 0, st>>>((const float4*)boxes, nvalid, n, words, iou_thresh, maxc, trick_max_numel,
+                                               perm, cat_off, ncat, (unsigned long long*)workspace);
+    nms_scan_grouped_kernel<<<B * ncat, 32, 0, st>>>((const unsigned long long*)workspace, n, words, max_keep, perm,
+                                                     cat_off, ncat, keepflag);
+    nms_compact_kernel<<<B, 32, 0, st>>>(keepflag, nvalid, n, max_keep, keep_idx, keep_cnt);
+    return check_launch("nms_batched (grouped)");
+  }
+  dim3 grid(words, words, B);
   nms_mask_kernel<<<grid, 64, 0, st>>>((const float4*)boxes, nvalid, n, words, iou_thresh, cats, maxc,
                                        trick_max_numel, (unsigned long long*)workspace);
   nms_scan_kernel<<<B, 32, 0, st>>>((const unsigned long long*)workspace, nvalid, n, words, max_keep, keep_idx,
                                     keep_cnt);
   return check_launch("nms_batched");
+}
+
+extern "C" int32_t c3d_nms_batched(const float* boxes, const int32_t* nvalid, const float* cats, const float* maxc,
+                                   int32_t trick_max_numel, int32_t B, int32_t n, float iou_thresh,
+                                   int32_t max_keep, int32_t* keep_idx, int32_t* keep_cnt, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  return nms_impl(boxes, nvalid, cats, maxc, trick_max_numel, B, n, iou_thresh, max_keep, keep_idx, keep_cnt, workspace,
+                  workspace_bytes, stream, 0, 0);
+}
+extern "C" int32_t c3d_nms_batched_grouped(const float* boxes, const int32_t* nvalid, const float* cats, const float* maxc,
+                                           int32_t trick_max_numel, int32_t B, int32_t n, float iou_thresh,
+                                           int32_t max_keep, int32_t ncat, int32_t max_per_cat_hint, int32_t* keep_idx,
+                                           int32_t* keep_cnt, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!cats) return c3d::set_error(C3D_EINVAL, "nms grouped: cats missing");
+  if (ncat < 1 || ncat > c3d::kMaxCat) return c3d::set_error(C3D_EINVAL, "nms grouped: ncat=%d outside [1, %d]", ncat, c3d::kMaxCat);
+  return nms_impl(boxes, nvalid, cats, maxc, trick_max_numel, B, n, iou_thresh, max_keep, keep_idx, keep_cnt, workspace,
+                  workspace_bytes, stream, ncat, max_per_cat_hint);
 }

@@ -321,7 +321,8 @@ class RPNWithIgnore(nn.Module):
         maxc = torch.where(keep_sorted[:, :, None], boxes, torch.full_like(boxes, -float("inf"))).amax(dim=(1, 2))
         post = self.post_nms_topk[training]
         kidx, kcnt = Kx.nms_batched(boxes, nvalid, self.nms_thresh, post, cats=lvl.contiguous(), maxc=maxc,
-                                    trick_max_numel=self.nms_trick_max_numel)
+                                    trick_max_numel=self.nms_trick_max_numel, ncat=len(anchors_per_level),
+                                    max_per_cat=self.pre_nms_topk[training])
         safe = kidx.clamp(min=0).long()
         out_b = torch.gather(boxes, 1, safe[:, :, None].expand(-1, -1, 4))
         out_s = torch.gather(key, 1, safe)

@@ -44,6 +44,7 @@ def _bind():
     L.c3d_nms_workspace_bytes.restype = ctypes.c_size_t
     L.c3d_nms_workspace_bytes.argtypes = [i32, i32]
     sig["c3d_nms_batched"] = [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, ctypes.c_size_t, vp]
+    sig["c3d_nms_batched_grouped"] = [vp, vp, vp, vp, i32, i32, i32, f32, i32, i32, i32, vp, vp, vp, ctypes.c_size_t, vp]
     sig["c3d_rpn_loss_fwd"] = [vp, vp, vp, vp, vp, vp, i32, i64, i32, ctypes.POINTER(f32), vp, vp]
     sig["c3d_rpn_loss_bwd"] = [vp, vp, vp, vp, vp, vp, i32, i64, i32, ctypes.POINTER(f32), vp, vp, vp, vp, vp]
     sig["c3d_anchor_match"] = [vp, i64, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp]
@@ -207,9 +208,10 @@ def sgd_momentum(p, g, mom, lr, momentum, weight_decay, grad_scale=1.0, skip_fla
 _nms_ws = {}
 
 
-def nms_batched(boxes, nvalid, iou_thresh, max_keep, cats=None, maxc=None, trick_max_numel=20000):
+def nms_batched(boxes, nvalid, iou_thresh, max_keep, cats=None, maxc=None, trick_max_numel=20000, ncat=0, max_per_cat=0):
     """boxes (B,n,4) fp32 sorted by score desc, nvalid (B,) int32, cats (B,n) fp32 categories, maxc (B,) fp32
-    -> keep_idx (B,max_keep) int32 (-1 padded, score order), keep_cnt (B,) int32.  No host sync."""
+    -> keep_idx (B,max_keep) int32 (-1 padded, score order), keep_cnt (B,) int32.  No host sync.
+    ncat > 0: the categories are exactly the integers 0..ncat-1 -> per-category kernels (same result, less work)."""
     L = _bind()
     B, n, _ = boxes.shape
     boxes = boxes.contiguous()
@@ -221,6 +223,11 @@ def nms_batched(boxes, nvalid, iou_thresh, max_keep, cats=None, maxc=None, trick
         _nms_ws[key] = ws
     keep = torch.empty((B, max_keep), dtype=torch.int32, device=boxes.device)
     cnt = torch.empty((B,), dtype=torch.int32, device=boxes.device)
+    if ncat > 0 and cats is not None:
+        _lib.check(L.c3d_nms_batched_grouped(_p(boxes), _p(nvalid), _p(cats), _p(maxc), trick_max_numel, B, n, iou_thresh,
+                                             max_keep, ncat, max_per_cat, _p(keep), _p(cnt), _p(ws), ws.numel(), _st()),
+                   launches=4)
+        return keep, cnt
     _lib.check(L.c3d_nms_batched(_p(boxes), _p(nvalid), _p(cats), _p(maxc), trick_max_numel, B, n, iou_thresh,
                                  max_keep, _p(keep), _p(cnt), _p(ws), ws.numel(), _st()), launches=2)
     return keep, cnt

@@ -186,20 +186,20 @@ def test_nms_batched_exact_vs_torchvision(n, trick):
     b_sorted = torch.gather(boxes, 1, order[:, :, None].expand(-1, -1, 4))
     c_sorted = torch.gather(cats, 1, order)
     maxc = torch.stack([b_sorted[i, :nvalid[i]].max() for i in range(B)])
-    keep, cnt = Kx.nms_batched(b_sorted.cuda(), nvalid.cuda(), 0.7, 1000, cats=c_sorted.cuda().contiguous(),
-                               maxc=maxc.cuda(), trick_max_numel=trick)
     import torchvision
-    for i in range(B):
-        nv = int(nvalid[i])
-        bb, ss, cc = b_sorted[i, :nv], s_sorted[i, :nv], c_sorted[i, :nv].long()
-        if bb.numel() > trick:      # torchvision's per-category path
-            ref = torchvision.ops.boxes._batched_nms_vanilla(bb, ss, cc, 0.7)
-        else:
-            ref = torchvision.ops.boxes._batched_nms_coordinate_trick(bb, ss, cc, 0.7)
-        ref = ref[:1000]
-        got = keep[i, :int(cnt[i])].cpu().long()
-        assert torch.equal(got, ref), (i, len(got), len(ref))
-
+    for grouped in (0, 5):                  # single sorted list vs per-category kernels: both == torchvision
+        keep, cnt = Kx.nms_batched(b_sorted.cuda(), nvalid.cuda(), 0.7, 1000, cats=c_sorted.cuda().contiguous(),
+                                   maxc=maxc.cuda(), trick_max_numel=trick, ncat=grouped, max_per_cat=n // 8)
+        for i in range(B):
+            nv = int(nvalid[i])
+            bb, ss, cc = b_sorted[i, :nv], s_sorted[i, :nv], c_sorted[i, :nv].long()
+            if bb.numel() > trick:      # torchvision's per-category path
+                ref = torchvision.ops.boxes._batched_nms_vanilla(bb, ss, cc, 0.7)
+            else:
+                ref = torchvision.ops.boxes._batched_nms_coordinate_trick(bb, ss, cc, 0.7)
+            ref = ref[:1000]
+            got = keep[i, :int(cnt[i])].cpu().long()
+            assert torch.equal(got, ref), (grouped, i, len(got), len(ref))
 
 def test_sgd_and_finite_flag():
     from omni3d_b200 import kernels as Kx
