@@ -233,6 +233,16 @@ int32_t c3d_rpn_loss_bwd(const float* logits, const float* deltas, const int8_t*
                          const float* weights4_host, const float* g_cls, const float* g_loc, float* dlogits,
                          float* ddeltas, void* stream);
 
+/* RPN proposal decoding of one FPN level's top-k candidates for all images (apply_deltas, clip, finite / min-size
+ * filter; detectron2 find_top_rpn_proposals via rpn.py:221-284).  topk_idx / topk_score [B][K] index the level's
+ * anchors [A][4] and deltas [B][A][4]; image_hw [B][2] = (h, w).  Results go to columns col0..col0+K-1 of the
+ * concatenated [B][Ktot] arrays: boxes (xyxy), key (score, or -inf when filtered), lvl (= level as float); nvalid[b] and
+ * maxc[b] (max kept coordinate, fp32 bits; both zero-initialised by the caller) are accumulated with atomics. */
+int32_t c3d_rpn_decode_level(const int64_t* topk_idx, const float* topk_score, const float* deltas, const float* anchors,
+                             const float* image_hw, int32_t B, int32_t K, int64_t A, const float* weights4_host,
+                             float scale_clamp, float min_size, int32_t level, int32_t col0, int32_t Ktot, float* boxes,
+                             float* key, float* lvl, int32_t* nvalid, float* maxc, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * CubeHead decode + disentangled 3D corner losses, fused forward / backward (one thread per RoI).
  * Replaces the ATen micro-kernels of cubercnn/modeling/roi_heads/roi_heads.py:409-525 (decode) and :527-740

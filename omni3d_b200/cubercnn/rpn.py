@@ -180,6 +180,7 @@ class RPNWithIgnore(nn.Module):
         # box coordinates (20000 on CUDA, 4000 on CPU); the reference runs on CUDA.
         self.nms_trick_max_numel = 20000
         self.fused_loss = True                 # c3d_rpn_loss_fwd/bwd instead of the (B,A)-shaped torch formulation
+        self.fused_decode = True               # c3d_rpn_decode_level instead of ~35 torch ops per level
         self.stats = {}
 
     # -- labels -----------------------------------------------------------------------------------
@@ -294,31 +295,51 @@ class RPNWithIgnore(nn.Module):
         training = self.training
         B = logits_per_level[0].shape[0]
         dev = logits_per_level[0].device
-        cand_b, cand_s, cand_l = [], [], []
-        for lvl, (anc, lg, dl) in enumerate(zip(anchors_per_level, logits_per_level, deltas_per_level)):
-            k = min(lg.shape[1], self.pre_nms_topk[training])
-            s, i = lg.topk(k, dim=1)
-            d = torch.gather(dl, 1, i[:, :, None].expand(-1, -1, 4))
-            cand_b.append(apply_deltas(d, anc[i], self.weights))
-            cand_s.append(s)
-            cand_l.append(torch.full((k,), lvl, dtype=torch.float32, device=dev))
-        boxes, scores = torch.cat(cand_b, 1), torch.cat(cand_s, 1)
-        lvl = torch.cat(cand_l)[None].expand(B, -1)
         hw = sizes_dev if sizes_dev is not None else torch.as_tensor(image_sizes, dtype=torch.float32, device=dev)  # (B,2) = (h,w)
-        lim = torch.stack((hw[:, 1], hw[:, 0], hw[:, 1], hw[:, 0]), 1)[:, None, :]
-        finite = torch.isfinite(boxes).all(-1) & torch.isfinite(scores)
-        boxes = torch.minimum(boxes.clamp(min=0), lim)
-        keep = finite & ((boxes[..., 2] - boxes[..., 0]) > self.min_box_size) & \
-            ((boxes[..., 3] - boxes[..., 1]) > self.min_box_size)
-        key = torch.where(keep, scores, torch.full_like(scores, -float("inf")))
-        key, order = key.sort(dim=1, descending=True)
-        boxes = torch.gather(boxes, 1, order[:, :, None].expand(-1, -1, 4))
-        lvl = torch.gather(lvl, 1, order)
-        nvalid = keep.sum(1).to(torch.int32)
+        ks = [min(lg.shape[1], self.pre_nms_topk[training]) for lg in logits_per_level]
+        if dev.type == "cuda" and self.fused_decode:
+            # one c3d_rpn_decode_level launch per level: apply_deltas + clip + finite/min-size filter, straight into the
+            # concatenated candidate arrays (plus per-image valid count and max kept coordinate)
+            Ktot = sum(ks)
+            boxes = torch.empty((B, Ktot, 4), device=dev)
+            key = torch.empty((B, Ktot), device=dev)
+            lvl = torch.empty((B, Ktot), device=dev)
+            nvalid = torch.zeros((B,), dtype=torch.int32, device=dev)
+            maxc = torch.zeros((B,), device=dev)
+            hw = hw.contiguous().float()
+            col = 0
+            for li, (anc, lg, dl, k) in enumerate(zip(anchors_per_level, logits_per_level, deltas_per_level, ks)):
+                s, i = lg.topk(k, dim=1)
+                Kx.rpn_decode_level(i, s, dl.contiguous(), anc, hw, self.weights, SCALE_CLAMP, self.min_box_size, li, col,
+                                    boxes, key, lvl, nvalid, maxc)
+                col += k
+            key, order = key.sort(dim=1, descending=True)
+            boxes = torch.gather(boxes, 1, order[:, :, None].expand(-1, -1, 4))
+            lvl = torch.gather(lvl, 1, order)
+        else:
+            cand_b, cand_s, cand_l = [], [], []
+            for li, (anc, lg, dl, k) in enumerate(zip(anchors_per_level, logits_per_level, deltas_per_level, ks)):
+                s, i = lg.topk(k, dim=1)
+                d = torch.gather(dl, 1, i[:, :, None].expand(-1, -1, 4))
+                cand_b.append(apply_deltas(d, anc[i], self.weights))
+                cand_s.append(s)
+                cand_l.append(torch.full((k,), li, dtype=torch.float32, device=dev))
+            boxes, scores = torch.cat(cand_b, 1), torch.cat(cand_s, 1)
+            lvl = torch.cat(cand_l)[None].expand(B, -1)
+            lim = torch.stack((hw[:, 1], hw[:, 0], hw[:, 1], hw[:, 0]), 1)[:, None, :]
+            finite = torch.isfinite(boxes).all(-1) & torch.isfinite(scores)
+            boxes = torch.minimum(boxes.clamp(min=0), lim)
+            keep = finite & ((boxes[..., 2] - boxes[..., 0]) > self.min_box_size) & \
+                ((boxes[..., 3] - boxes[..., 1]) > self.min_box_size)
+            key = torch.where(keep, scores, torch.full_like(scores, -float("inf")))
+            key, order = key.sort(dim=1, descending=True)
+            boxes = torch.gather(boxes, 1, order[:, :, None].expand(-1, -1, 4))
+            lvl = torch.gather(lvl, 1, order)
+            nvalid = keep.sum(1).to(torch.int32)
+            keep_sorted = torch.gather(keep, 1, order)
+            maxc = torch.where(keep_sorted[:, :, None], boxes, torch.full_like(boxes, -float("inf"))).amax(dim=(1, 2))
         # torchvision batched_nms: per-level NMS; for small inputs it uses the "coordinate trick" (shift every
         # level by level * (max coordinate + 1)) — the kernel reproduces either form per image.
-        keep_sorted = torch.gather(keep, 1, order)
-        maxc = torch.where(keep_sorted[:, :, None], boxes, torch.full_like(boxes, -float("inf"))).amax(dim=(1, 2))
         post = self.post_nms_topk[training]
         kidx, kcnt = Kx.nms_batched(boxes, nvalid, self.nms_thresh, post, cats=lvl.contiguous(), maxc=maxc,
                                     trick_max_numel=self.nms_trick_max_numel, ncat=len(anchors_per_level),

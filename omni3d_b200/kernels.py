@@ -47,6 +47,8 @@ def _bind():
     sig["c3d_nms_batched_grouped"] = [vp, vp, vp, vp, i32, i32, i32, f32, i32, i32, i32, vp, vp, vp, ctypes.c_size_t, vp]
     sig["c3d_rpn_loss_fwd"] = [vp, vp, vp, vp, vp, vp, i32, i64, i32, ctypes.POINTER(f32), vp, vp]
     sig["c3d_rpn_loss_bwd"] = [vp, vp, vp, vp, vp, vp, i32, i64, i32, ctypes.POINTER(f32), vp, vp, vp, vp, vp]
+    sig["c3d_rpn_decode_level"] = [vp, vp, vp, vp, vp, i32, i32, i64, ctypes.POINTER(f32), f32, f32, i32, i32, i32, vp, vp, vp,
+                                   vp, vp, vp]
     sig["c3d_anchor_match"] = [vp, i64, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp]
     sig["c3d_preprocess_image_u8"] = [vp, i32, i32, vp, i32, i32, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), vp]
     for name, args in sig.items():
@@ -251,6 +253,18 @@ def anchor_match(anchors, gt_boxes, gt_valid, gt_ign, fg_thresh):
     _lib.check(L.c3d_anchor_match(_p(anchors), A, _p(gt_boxes), _p(v8), _p(i8), B, G, float(fg_thresh), _p(idx), _p(iou),
                                   _p(lab), _p(ioa), _p(best), _p(ws), _st()), launches=3)
     return idx, iou, lab, ioa, best
+
+
+def rpn_decode_level(topk_idx, topk_score, deltas, anchors, image_hw, weights, scale_clamp, min_size, level, col0, boxes,
+                     key, lvl, nvalid, maxc):
+    """decode one level's top-k candidates into columns col0.. of boxes (B,Ktot,4) / key / lvl (B,Ktot); nvalid (B,) int32
+    and maxc (B,) fp32 accumulate (zero them first)."""
+    L = _bind()
+    B, K = topk_idx.shape
+    w = (f32 * 4)(*[float(v) for v in weights])
+    _lib.check(L.c3d_rpn_decode_level(_p(topk_idx), _p(topk_score), _p(deltas), _p(anchors), _p(image_hw), B, K,
+                                      deltas.shape[1], w, float(scale_clamp), float(min_size), int(level), int(col0),
+                                      boxes.shape[1], _p(boxes), _p(key), _p(lvl), _p(nvalid), _p(maxc), _st()))
 
 
 def rpn_loss_fwd(logits, deltas, labels, matched_idx, gt_boxes, anchors, weights):

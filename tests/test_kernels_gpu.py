@@ -319,3 +319,28 @@ def test_fused_rpn_loss_matches_torch_formulation():
     for i in (2, 3):
         ref = out[False][i]
         assert (out[True][i] - ref).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-9
+
+
+def test_fused_proposal_decode_matches_torch_formulation():
+    """RPNWithIgnore.predict_proposals with c3d_rpn_decode_level + grouped NMS == the torch-op formulation + single-list
+    NMS: identical proposal boxes, scores and counts (bit for bit), incl. non-finite deltas and tiny boxes."""
+    from omni3d_b200 import cubercnn as pc
+    cfg = pc.load_cfg("cubercnn_DLA34_FPN.yaml", ["MODEL.WEIGHTS_PRETRAIN", "none"])
+    torch.manual_seed(0)
+    rpn = pc.build_model(cfg).proposal_generator.train()
+    shapes = [(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)]
+    anchors_l = rpn.anchor_generator(shapes, torch.device("cuda"))
+    B = 3
+    g = torch.Generator(device="cuda").manual_seed(5)
+    logits = [torch.randn(B, a.shape[0], device="cuda", generator=g) for a in anchors_l]
+    deltas = [0.7 * torch.randn(B, a.shape[0], 4, device="cuda", generator=g) for a in anchors_l]
+    deltas[0][0, :50, 2] = float("nan"); deltas[1][1, :20, 0] = float("inf"); deltas[2][2, :10, 2:] = -20.0
+    sizes = [(160, 224), (150, 200), (160, 224)]
+    out = {}
+    for fused in (False, True):
+        rpn.fused_decode = fused
+        out[fused] = rpn.predict_proposals(anchors_l, logits, deltas, sizes)
+    rpn.fused_decode = True
+    for a, b, name in zip(out[True], out[False], ("boxes", "scores", "count")):
+        assert torch.equal(a, b), name
+    assert int(out[True][2].min()) > 100
