@@ -51,3 +51,31 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|#include\s+\".*oracle", s, flags=re.M):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_host_side_entry_points_without_gpu():
+    """entry points that do host arithmetic or argument checking only: tile query (incl. the rolling-halo path's
+    one-row-per-CTA statistics layout), workspace sizes, EINVAL + c3d_last_error on bad arguments (no CUDA call)."""
+    from omni3d_b200 import _lib, conv
+    L = conv._bind()
+    d = conv.ConvDesc(32, 640, 640, 16, 16, 3, 3, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)       # DLA level0: halo path
+    t, th, tw = conv.num_tiles(d)
+    if os.environ.get("C3D_CONV_NO_HALO"):
+        assert t == 32 * 640 * 640 // (th * tw)
+    else:
+        assert (t, th, tw) == (148 * 3, 1, 128)
+    d = conv.ConvDesc(32, 160, 160, 256, 256, 3, 3, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)     # FPN output conv
+    t, th, tw = conv.num_tiles(d)
+    assert th * tw <= 128 and t == 32 * -(-160 // th) * -(-160 // tw)
+    L.c3d_nms_workspace_bytes.restype = ctypes.c_size_t
+    L.c3d_nms_workspace_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    assert L.c3d_nms_workspace_bytes(32, 8192) > L.c3d_nms_workspace_bytes(32, 4096) > 32 * 4096 * 64 * 8
+    L.c3d_anchor_match.restype = ctypes.c_int32
+    L.c3d_last_error.restype = ctypes.c_char_p
+    null = ctypes.c_void_p(None)
+    L.c3d_anchor_match.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_int32, ctypes.c_int32, ctypes.c_float] + [ctypes.c_void_p] * 7
+    rc = L.c3d_anchor_match(null, 10, null, null, null, 1, 1, 0.7, null, null, null, null, null, null, null)
+    assert rc != 0 and b"anchor_match" in L.c3d_last_error()
+    with pytest.raises(_lib.C3DError):
+        _lib.check(rc)

@@ -98,3 +98,16 @@ def test_product_refuses_cpu_forward():
     m = pc.build_model(pcfg)
     with pytest.raises(_lib.C3DError):
         m(synth.make_batch(1, 64, 64))
+
+
+def test_pixel_stride_of_channel_slices():
+    """gradients of torch.cat inputs arrive as channel slices of a dense NHWC buffer: the BatchNorm / max-pool backward
+    kernels read them in place when 16-byte aligned, and fall back to a copy otherwise."""
+    from omni3d_b200.kernels import pixel_stride
+    big = torch.zeros(2, 5, 7, 448, dtype=torch.bfloat16)
+    assert pixel_stride(big) == 448
+    assert pixel_stride(big[..., 128:256]) == 448
+    assert pixel_stride(big[..., 4:132]) is None                 # 8-byte offset: not vector aligned
+    assert pixel_stride(big[:, :, 1:4, :128]) is None            # not a plain channel slice
+    assert pixel_stride(big.permute(0, 3, 1, 2)) is None
+    assert pixel_stride(torch.zeros(1, 1, 1, 64, dtype=torch.bfloat16)) == 64
