@@ -135,6 +135,7 @@ class FlatSGDTrainer:
         self.graph_warmup = 2
         self.graph = self.static = self.graph_sig = self.graph_losses = self.graph_vec = None
         self.graph_launches = 0
+        self.recaptures = 0
         self.lr_dev = torch.zeros(1, device=dev)
 
     # -------------------------------------------------------------------------------------------------
@@ -230,7 +231,15 @@ class FlatSGDTrainer:
             sig = self._signature(staged)
             if self.graph is not None and (sig[0] != self.graph_sig[0] or sig[1] > self.graph_sig[1]):
                 self.graph, self.static = None, None     # other shapes: record again
-            if self.graph is None:
+                self.recaptures += 1
+                if self.recaptures > 3:                  # shapes keep changing (real loaders): recording does not pay
+                    import sys
+                    print("omni3d_b200: input shapes changed %d times; train step continues without CUDA graphs"
+                          % self.recaptures, file=sys.stderr)
+                    self.use_graph = False
+            if not self.use_graph:
+                pass
+            elif self.graph is None:
                 loss_dict = self._capture(staged, sig, lr)
             else:
                 self._copy_into_static(staged)
