@@ -111,3 +111,24 @@ def test_pixel_stride_of_channel_slices():
     assert pixel_stride(big[:, :, 1:4, :128]) is None            # not a plain channel slice
     assert pixel_stride(big.permute(0, 3, 1, 2)) is None
     assert pixel_stride(torch.zeros(1, 1, 1, 64, dtype=torch.bfloat16)) == 64
+
+
+def test_stage_inputs_is_the_only_host_interface():
+    """RCNN3D.stage_inputs: images keep their dtype (uint8 as the mapper emits them, or float), one (B,12) row of
+    per-image scalars [h, w, height/h, K row-major], padded GT with the collate conventions."""
+    from omni3d_b200 import cubercnn as pc
+    cfg = pc.load_cfg("cubercnn_DLA34_FPN.yaml", ["MODEL.WEIGHTS_PRETRAIN", "none", "MODEL.DEVICE", "cpu"])
+    model = pc.build_model(cfg).train()
+    items = synth.make_batch(2, 96, 128, num_gt=3, seed=3, image_dtype=torch.uint8)
+    items[1]["gt"] = {k: v[:2] for k, v in items[1]["gt"].items()}            # ragged GT counts
+    items[0]["height"] = 192                                                   # original image was 2x larger
+    st = model.stage_inputs(items)
+    assert [im.dtype for im in st["images"]] == [torch.uint8, torch.uint8] and st["sizes"] == [(96, 128), (96, 128)]
+    meta = st["meta"]
+    assert meta.shape == (2, 12) and meta[0, :3].tolist() == [96.0, 128.0, 2.0] and meta[1, 2].item() == 1.0
+    assert torch.equal(meta[0, 3:].reshape(3, 3), torch.tensor(items[0]["K"], dtype=torch.float32))
+    gt = st["gt"]
+    assert gt["boxes"].shape == (2, 3, 4) and gt["present"].tolist() == [[True, True, True], [True, True, False]]
+    assert gt["classes"][1, 2].item() == -2 and torch.equal(gt["poses"][1, 2], torch.eye(3))
+    f = synth.make_batch(1, 64, 64, num_gt=2, seed=4)
+    assert model.stage_inputs(f)["images"][0].dtype == torch.float32
