@@ -20,11 +20,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "images/sec DLA34 Cube R-CNN train step"
 UNIT = "images/s"
-CONFIG_FILE = "cubercnn_DLA34_FPN.yaml"
-# algorithmic work per image (SURVEY.md section 8d / BASELINE.md section 3)
-GFLOP_TRAIN_PER_IMAGE = 452.0
+# per backbone: config file, metric name, algorithmic train GFLOP / image and conv-family forward GMAC / image
+# (SURVEY.md section 8d / BASELINE.md section 3: bottom-up + FPN 20.913 + RPN head 20.244; 0.963 = the stem, which has no dgrad)
+CONFIGS = {
+    "dla34": {"file": "cubercnn_DLA34_FPN.yaml", "metric": "images/sec DLA34 Cube R-CNN train step", "name": "DLA34_FPN",
+              "train_gflop": 452.0, "conv_fwd_gmac": 25.081 + 20.913 + 20.244, "baseline_cfg": "configs[1]"},
+    "resnet34": {"file": "cubercnn_ResNet34_FPN.yaml", "metric": "images/sec ResNet34 Cube R-CNN train step",
+                 "name": "ResNet34_FPN", "train_gflop": 3 * 2 * 80.17 - 1.9, "conv_fwd_gmac": 29.904 + 20.913 + 20.244,
+                 "baseline_cfg": "configs[3]"},
+}
 
 
 def parse():
@@ -36,8 +41,11 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU (BASELINE configs[1]: 32)")
     ap.add_argument("--size", type=int, default=640)
     ap.add_argument("--cpu-batch", type=int, default=2, help="images per CPU step (bounded sample of the workload)")
+    ap.add_argument("--config", default="dla34", choices=sorted(CONFIGS), help="backbone (BASELINE configs[1] / configs[3])")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-iou", action="store_true")
+    ap.add_argument("--skip-torch-baseline", action="store_true",
+                    help="do not time the oracle model in stock PyTorch eager on the GPU (baseline_torch_gpu)")
     return ap.parse_args()
 
 
@@ -85,9 +93,22 @@ def peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_train_images_per_s(batch, size, steps, warmup, threads):
+def physical_cores():
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:      # noqa: BLE001
+        pass
+    return os.cpu_count() or 1
+
+
+def cpu_train_images_per_s(config_file, batch, size, steps, warmup, threads):
     """The reference's CPU path for this metric = the oracle port (fp32, MODEL.DEVICE=cpu) doing
-    forward + backward + SGD on a bounded sample (batch `batch`) of the same synthetic workload."""
+    forward + backward + SGD on a bounded sample (batch `batch`) of the same synthetic workload.
+    -> (images/s from the MEDIAN step, median s, min s, all step times)."""
+    import statistics
     import torch
     from omni3d_b200 import synth
     from oracle import cubercnn_oracle as co
@@ -95,7 +116,7 @@ def cpu_train_images_per_s(batch, size, steps, warmup, threads):
     from detectron2.utils.events import EventStorage
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    cfg = co.load_cfg(CONFIG_FILE)
+    cfg = co.load_cfg(config_file)
     model = co.build_model(cfg)
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
@@ -111,26 +132,78 @@ def cpu_train_images_per_s(batch, size, steps, warmup, threads):
             opt.step()
             if it >= warmup:
                 times.append(time.perf_counter() - t0)
-    sec = sum(times) / len(times)
-    return batch / sec, sec
+    med = statistics.median(times)
+    return batch / med, med, min(times), times
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
-    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    ips, sec = cpu_train_images_per_s(args.cpu_batch, args.size, steps, warm, cores)
-    sample = f"oracle port fwd+bwd+SGD, fp32, batch {args.cpu_batch} x {args.size}x{args.size}, {steps} timed steps"
+    C = CONFIGS[args.config]
+    cores = physical_cores()
+    steps, warm = max(3, min(args.steps, 5)), max(2, min(args.warmup, 3))
+    ips, med, best, times = cpu_train_images_per_s(C["file"], args.cpu_batch, args.size, steps, warm, cores)
+    sample = (f"oracle port fwd+bwd+SGD, fp32, batch {args.cpu_batch} x {args.size}x{args.size}, {steps} timed steps after "
+              f"{warm} warm-up, {cores} threads (= physical cores); value from the median step ({med:.2f} s, min {best:.2f} s)")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": C["metric"], "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Cube R-CNN DLA34_FPN train step, synthetic {args.size}x{args.size}, CPU sample batch {args.cpu_batch}"},
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": f"Cube R-CNN {C['name']} train step, synthetic {args.size}x{args.size}, CPU sample batch {args.cpu_batch}"},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "step_seconds": times, "value_from_min_step": args.cpu_batch / best},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def torch_gpu_baseline(config_file, batch, size, steps=5, warmup=2):
+    """SURVEY 8d 'baseline_torch_gpu': the oracle restatement of the reference graph (fp32 NCHW nn.Modules, per-image
+    Python loops, detectron2 semantics) executed by stock PyTorch eager on this GPU — cuDNN / cuBLAS sm_100 kernels,
+    torchvision ROIAlign / NMS — doing forward + backward + SGD on the SAME batch shape.  fp32 (the reference trains in
+    fp32, TF32 off) and bf16 autocast.  This is the library path our kernels have to beat on this box."""
+    import statistics
+    import torch
+    from omni3d_b200 import synth
+    from oracle import cubercnn_oracle as co
+    from oracle import model_io
+    from detectron2.utils.events import EventStorage
+    out = {}
+    items = synth.make_batch(batch, size, size, num_gt=8, seed=0)
+    dev_items = [{**it, "image": it["image"].cuda(), "gt": {k: v.cuda() for k, v in it["gt"].items()}} for it in items]
+    for name, autocast in (("bf16_autocast", True), ("fp32", False)):
+        model = opt = None
+        try:
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.manual_seed(0)
+            model = co.build_model(co.load_cfg(config_file)).cuda().train()
+            params = [p for p in model.parameters() if p.requires_grad]
+            opt = torch.optim.SGD(params, lr=1e-4, momentum=0.9, weight_decay=1e-4)
+            ts = []
+            with EventStorage(0):
+                for it in range(warmup + steps):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                        losses = model(model_io.to_d2_inputs(dev_items))
+                    opt.zero_grad(set_to_none=True)
+                    sum(losses.values()).backward()
+                    opt.step()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if it >= warmup:
+                        ts.append(e0.elapsed_time(e1))
+            med = statistics.median(ts)
+            out[name] = {"value": batch / (med * 1e-3), "unit": UNIT, "ms_per_step": med, "ms_min": min(ts), "steps": steps,
+                         "warmup": warmup}
+        except Exception as e:      # noqa: BLE001 — a baseline that cannot run is reported, never fatal for the bench line
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        del model, opt
+        torch.cuda.empty_cache()
+    out["what"] = (f"oracle restatement of the reference model, stock PyTorch {torch.__version__} eager on this GPU (cuDNN/cuBLAS/"
+                   f"torchvision ops), fwd+bwd+SGD, batch {batch} x {size}x{size}, inputs resident in HBM, TF32 off")
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -144,7 +217,7 @@ def _top_kernel_traffic():
         return None
 
 
-def conv_roofline(trainer, items, peak_tflops, peak_src):
+def conv_roofline(trainer, items, peak_tflops, peak_src, conv_fwd_gmac):
     """One instrumented step: CUDA events around every conv_tc launch (on the launching stream) ->
     algorithmic FLOPs / summed duration for the dominant kernel family."""
     import torch
@@ -182,11 +255,11 @@ def conv_roofline(trainer, items, peak_tflops, peak_src):
         K.conv2d_fwd, K.conv2d_wgrad = o_f, o_w
         trainer.use_graph = graph_mode
     ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
-    # ALGORITHMIC conv FLOPs of one train step: DLA34 25.081 + FPN 20.913 + RPN head 20.244
-    # GMAC/img forward; backward = dgrad (no dgrad for the 0.963-GMAC stem) + wgrad.  Executed FLOPs are higher
+    # ALGORITHMIC conv FLOPs of one train step: bottom-up (DLA34 25.081 | ResNet34 29.904) + FPN 20.913 +
+    # RPN head 20.244 GMAC/img forward; backward = dgrad (no dgrad for the 0.963-GMAC stem) + wgrad.  Executed FLOPs are higher
     # (stem Cin 3 padded to 16, zero-stuffed stride-2 dgrad) and are NOT what is credited here.
     n_img = items[0]["image"].shape[0] if hasattr(items[0]["image"], "shape") and items[0]["image"].dim() == 4 else len(items)
-    fl = n_img * 2.0 * (3 * 66.238e9 - 0.963e9)
+    fl = n_img * 2.0 * (3 * conv_fwd_gmac * 1e9 - 0.963e9)
     ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
     by = {}
     for a, b, f, kind in rec:
@@ -201,25 +274,79 @@ def conv_roofline(trainer, items, peak_tflops, peak_src):
                           for k, v in by.items()}}
 
 
-def iou_block():
+def _ncu_iou_issue_pct():
+    """issue-slot utilisation of the dense IoU kernel from the committed `ncu --set full` summary (profiles/): the number
+    is evidence from a profiler run, never a timing; None when the summary file is absent."""
+    p = os.path.join(ROOT, "profiles", "iou3d_ncu.json")
+    try:
+        return json.load(open(p))
+    except Exception:      # noqa: BLE001
+        return None
+
+
+def iou_cpu_baseline(n=100, threads_all=None):
+    """pytorch3d's serial CPU algorithm as the reference calls it (omni3d_evaluation.py:1404-1412) = oracle/iou3d_oracle.c,
+    on a bounded n x n cross sample of the same box distributions: 1 thread (faithful) and all physical cores (pthreads)."""
+    import boxgen
+    from oracle import iou3d as oracle
+    threads_all = threads_all or physical_cores()
+    out = {}
+    for regime, L in (("dense", 1.0), ("sparse", 10.0)):
+        a = boxgen.inject_degenerate(boxgen.random_boxes(n, L, 0), 0.01, 1)[0]
+        b = boxgen.random_boxes(n, L, 5)
+        rec = {}
+        for label, th in (("serial", 1), ("threaded", threads_all)):
+            oracle.iou_box3d(a[:8], b[:8], threads=th)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                oracle.iou_box3d(a, b, threads=th)
+                ts.append(time.perf_counter() - t0)
+            ts.sort()
+            rec[label] = {"pairs_per_s": n * n / ts[1], "cores": th, "seconds_median": ts[1]}
+        out[regime] = rec
+    out["kind"] = "port"
+    out["sample"] = f"{n} x {n} cross pairs per regime, C restatement of iou_box3d_cpu (oracle/iou3d_oracle.c), median of 3"
+    return out
+
+
+def iou_block(peak_hbm, peak_src):
+    """BASELINE configs[4]: box3d_overlap pairs/s.  Cross 1000 x 1000 (the reference API) dense / sparse, plus 1 M PAIRED
+    sparse pairs — the regime where HBM is the roofline (200 algorithmic B / pair, almost every pair rejected by the
+    bounding-sphere test)."""
     import numpy as np
     import torch
     import boxgen
     from omni3d_b200 import box3d
+
+    def med_ms(fn, iters=10):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
     out = {}
     for regime, L in (("dense", 1.0), ("sparse", 10.0)):
         a = torch.from_numpy(boxgen.inject_degenerate(boxgen.random_boxes(1000, L, 0), 0.01, 1)[0]).cuda()
         b = torch.from_numpy(boxgen.random_boxes(1000, L, 5)).cuda()
-        for _ in range(3):
-            box3d.iou_box3d(a, b)
-        ts = []
-        for _ in range(10):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); box3d.iou_box3d(a, b); e1.record(); torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = float(np.median(ts))
+        ms = med_ms(lambda: box3d.iou_box3d(a, b))
         out[regime] = {"pairs": 1_000_000, "ms": ms, "pairs_per_s": 1e6 / (ms * 1e-3),
                        "alg_GBps": (96 * 2000 + 8e6) / (ms * 1e-3) / 1e9}
+    n = 1_000_000
+    a = torch.from_numpy(boxgen.random_boxes(n, 10.0, 0)).cuda()
+    b = torch.from_numpy(boxgen.random_boxes(n, 10.0, 5)).cuda()
+    ms = med_ms(lambda: box3d.iou_box3d_paired(a, b), iters=5)
+    gbs = 200.0 * n / (ms * 1e-3) / 1e9
+    out["sparse_paired"] = {"pairs": n, "ms": ms, "pairs_per_s": n / (ms * 1e-3), "alg_GBps": gbs}
+    out["roofline"] = {"bound": "hbm", "kernel": "iou3d_pair_kernel, 1e6 paired sparse pairs (200 algorithmic B / pair)",
+                       "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm, "traffic": None,
+                       "peak_source": peak_src + ", hbm copy",
+                       "dense_note": "dense (overlapping) pairs are issue-slot bound, not HBM bound (8 B / pair in cross mode): "
+                                     "see `ncu` for the committed issue-slot / lane-utilisation figures",
+                       "ncu": _ncu_iou_issue_pct()}
     return out
 
 
@@ -236,7 +363,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    cfg = pc.load_cfg(CONFIG_FILE, ["MODEL.WEIGHTS_PRETRAIN", "none", "MODEL.DEVICE", "cuda", "SOLVER.IMS_PER_BATCH", args.batch * world,
+    C = CONFIGS[args.config]
+    cfg = pc.load_cfg(C["file"], ["MODEL.WEIGHTS_PRETRAIN", "none", "MODEL.DEVICE", "cuda", "SOLVER.IMS_PER_BATCH", args.batch * world,
                                     "SOLVER.BASE_LR", 0.0025])
     torch.manual_seed(0)
     model = pc.build_model(cfg)
@@ -288,7 +416,7 @@ def run_ours(args):
     status = trainer.status()
     peak_tf, peak_hbm, peak_src = peaks()
     # the instrumented step runs on EVERY rank (it contains the same collectives as any other step)
-    roof = conv_roofline(trainer, resident[0], peak_tf, peak_src)
+    roof = conv_roofline(trainer, resident[0], peak_tf, peak_src, C["conv_fwd_gmac"])
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -298,33 +426,45 @@ def run_ours(args):
     ips = B * world * args.steps / (ms * 1e-3)
     ips_e2e = B * world * args.steps / (ms_e2e * 1e-3)
     line = {
-        "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": C["metric"], "value": ips, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": f"Cube R-CNN DLA34_FPN train step, batch {B}/GPU synthetic {S}x{S}, K=50, G=8 GT/img "
-                               "(BASELINE configs[1]; weak scaling, global batch %d)" % (B * world),
+        "config": {"workload": f"Cube R-CNN {C['name']} train step, batch {B}/GPU synthetic {S}x{S}, K=50, G=8 GT/img "
+                               f"(BASELINE {C['baseline_cfg']}; weak scaling, global batch {B * world})",
                    "parallelism": f"dp{world}", "l2": "two alternating input batches (39 MB uint8 images each) + ~10 GB of "
                                                       "activations per step: working set >> 126 MB L2",
                    "cuda_graph": bool(trainer.graph is not None),
                    "images": "uint8 (3,H,W), as cubercnn/data/dataset_mapper.py:35 emits them",
-                   "train_gflop_per_image": GFLOP_TRAIN_PER_IMAGE},
+                   "train_gflop_per_image": C["train_gflop"]},
         "clocks": clocks,
         "e2e": {"value": ips_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 56,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
-        "step_tflops_model": ips / world * GFLOP_TRAIN_PER_IMAGE / 1e3,
+        "step_tflops_model": ips / world * C["train_gflop"] / 1e3,
+        "step_frac_of_peak": ips / world * C["train_gflop"] / 1e3 / peak_tf,
         "roofline": roof,
         "final_losses": status["losses"] if status else None,
         "iterations_skipped": status["iterations_explode"] if status else None,
     }
-    if not args.skip_iou:
-        line["box3d_overlap"] = iou_block()
+    if not args.skip_iou and world == 1:
+        line["box3d_overlap"] = iou_block(peak_hbm, peak_src)
+        if not args.skip_cpu_baseline:
+            line["box3d_overlap"]["cpu_baseline"] = iou_cpu_baseline()
+    if not args.skip_torch_baseline and world == 1:
+        del trainer, model
+        torch.cuda.empty_cache()
+        line["baseline_torch_gpu"] = torch_gpu_baseline(C["file"], B, S)
+        for k in ("bf16_autocast", "fp32"):
+            v = line["baseline_torch_gpu"].get(k, {})
+            if "value" in v:
+                v["ours_over_this"] = ips / v["value"]
     if not args.skip_cpu_baseline and world == 1:
-        cores = os.cpu_count()
-        cb, secs = cpu_train_images_per_s(args.cpu_batch, S, 1, 1, cores)
+        cores = physical_cores()
+        cb, med, best, times = cpu_train_images_per_s(C["file"], args.cpu_batch, S, 3, 1, cores)
         line["cpu_baseline"] = {"value": cb, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"oracle port fwd+bwd+SGD fp32, batch {args.cpu_batch} x {S}x{S}, 1 timed step "
-                                          f"({secs:.1f} s) after 1 warm-up"}
+                                "sample": f"oracle port fwd+bwd+SGD fp32, batch {args.cpu_batch} x {S}x{S}, 3 timed steps after 1 "
+                                          f"warm-up, {cores} threads (= physical cores), value from the median step "
+                                          f"({med:.1f} s; min {best:.1f} s)", "step_seconds": times}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -132,9 +132,9 @@ int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, const float
                    void* dy, void* dres, int64_t P, int32_t C, int64_t dout_stride, int64_t out_stride,
                    int64_t dres_stride, void* scratch, void* stream);
 /* backward of the bias(+ReLU) epilogue of the bias convs (FPN / RPN head): dz (bf16) = dout * (out > 0 if relu),
- * dbias (fp32 [C]) += sum over pixels.  dout/out are bf16, or fp32 when dout_fp32 != 0.
+ * dbias (fp32 [C]) += sum over pixels.  dtype_flags: bit 0 = dout is fp32 (else bf16), bit 1 = out is fp32 (else bf16).
  * partial: fp32 [c3d_bn_bwd_blocks(P,C)][C]; scratch: c3d_bn_scratch_bytes(C). */
-int32_t c3d_bias_act_bwd(const void* dout, const void* out, int32_t relu, int32_t dout_fp32, void* dz, float* partial,
+int32_t c3d_bias_act_bwd(const void* dout, const void* out, int32_t relu, int32_t dtype_flags, void* dz, float* partial,
                          float* dbias, int64_t P, int32_t C, void* scratch, void* stream);
 /* y (N,H/2,W/2,C) = 2x2 block sums of x: gradient of the FPN nearest-x2 upsampling */
 int32_t c3d_sumpool2(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
@@ -145,6 +145,11 @@ int32_t c3d_maxpool2_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W
                          int64_t y_stride, void* stream);
 int32_t c3d_maxpool2_bwd(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C,
                          int64_t x_stride, int64_t dy_stride, void* stream);
+/* 3x3 / stride 2 / pad 1 max pool of the torchvision ResNet stem (cubercnn/modeling/backbone/resnet.py:17-27,45-50):
+ * y (N,(H-1)/2+1,(W-1)/2+1,C); the backward routes dy to the first maximal element of every window (ATen tie order). */
+int32_t c3d_maxpool3s2_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+int32_t c3d_maxpool3s2_bwd(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C,
+                           int64_t dy_stride, void* stream);
 /* (3,H,W) fp32 BGR image -> (Hp,Wp,Cp) bf16 NHWC slot: (x-mean)/std in channels 0..2, zeros elsewhere */
 int32_t c3d_preprocess_image(const float* img, int32_t H, int32_t W, void* out_slot, int32_t Hp, int32_t Wp,
                              int32_t Cp, const float* mean3_host, const float* std3_host, void* stream);
@@ -165,6 +170,8 @@ int32_t c3d_sgd_momentum_dev(float* p, const float* g, float* mom, int64_t n, co
  * Multi-level ROIAlign (aligned=True, sampling_ratio 0) on NHWC bf16 FPN maps.
  * Replaces detectron2 ROIPooler/ROIAlignV2 at cubercnn/modeling/roi_heads/roi_heads.py:267,362.
  * rois: fp32 [R][6] = (batch index, level index, x1, y1, x2, y2).  out: bf16 [R][ph][pw][C].
+ * RoIs with a non-finite coordinate, a level outside [0, num_levels) or (when num_images > 0) an image index
+ * outside [0, num_images) pool zeros / contribute no gradient instead of indexing out of bounds.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   const void* feat[5];   /* level l: bf16 (N,H[l],W[l],C) */
@@ -172,6 +179,7 @@ typedef struct {
   int32_t H[5], W[5];
   float scale[5];
   int32_t num_levels;
+  int32_t num_images;    /* N of the maps (0 = do not check the image index) */
 } c3d_roi_levels;
 int32_t c3d_roi_align_fwd(const c3d_roi_levels* levels, const float* rois, int32_t R, int32_t C, int32_t pooled_h,
                           int32_t pooled_w, void* out, void* stream);

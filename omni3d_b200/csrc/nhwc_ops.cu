@@ -247,8 +247,8 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out,
 
 // ---- bias / ReLU backward for the bias convs (FPN, RPN head) -----------------------------------------
 // dz = dout * (out > 0 if relu) written as bf16; partial[block][c] = sum over the block's pixels of dz (dbias)
-template <int THREADS, typename TIN>
-__global__ void bias_act_bwd_kernel(const TIN* __restrict__ dout, const TIN* __restrict__ out, int relu,
+template <int THREADS, typename TIN, typename TOUT>
+__global__ void bias_act_bwd_kernel(const TIN* __restrict__ dout, const TOUT* __restrict__ out, int relu,
                                     bf16* __restrict__ dz, float* __restrict__ partial, long long P, int C) {
   const int cv = C >> 3;
   const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
@@ -257,9 +257,9 @@ __global__ void bias_act_bwd_kernel(const TIN* __restrict__ dout, const TIN* __r
   float s[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s[k] = 0.f;
-  auto load = [&](const TIN* p) {
+  auto load = [&](const auto* p) {
     V8 r;
-    if constexpr (sizeof(TIN) == 2) { r = ld8(reinterpret_cast<const bf16*>(p)); }
+    if constexpr (sizeof(*p) == 2) { r = ld8(reinterpret_cast<const bf16*>(p)); }
     else {
       const float4* q = reinterpret_cast<const float4*>(p);
       float4 a = q[0], b = q[1];
@@ -391,6 +391,88 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) st8(dx + off[j] * C + c, o[j]);
+  }
+}
+
+// ---- 3x3 stride-2 pad-1 max pool (NHWC): the torchvision ResNet stem pool (resnet.py:17-27 -> nn.MaxPool2d(3,2,1)) ----
+__device__ __forceinline__ int pool3_out(int n) { return (n - 1) / 2 + 1; }      // floor((n + 2 - 3) / 2) + 1
+__global__ void maxpool3s2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C) {
+  const int Ho = pool3_out(H), Wo = pool3_out(W), cv = C >> 3;
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) << 3;
+    long long p = i / cv;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    V8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = -INFINITY;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = 2 * ho - 1 + kh;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = 2 * wo - 1 + kw;
+        if (w < 0 || w >= W) continue;
+        V8 a = ld8(x + (((long long)n * H + h) * W + w) * C + c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(o.v[k], a.v[k]);
+      }
+    }
+    st8(y + (((long long)n * Ho + ho) * Wo + wo) * C + c, o);
+  }
+}
+// dx[h,w] = sum over the (<= 4) windows containing (h,w) whose FIRST maximal element (row-major window order, the
+// order ATen's max_pool2d resolves ties in) is (h,w), of dy[window].  Gather form: no atomics, no saved indices.
+__global__ void maxpool3s2_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx,
+                                      int N, int H, int W, int C, long long dy_stride) {
+  const int Ho = pool3_out(H), Wo = pool3_out(W), cv = C >> 3;
+  const long long total = (long long)N * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) << 3;
+    long long p = i / cv;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H);
+    const int n = (int)(p / H);
+    const bf16* xn = x + (long long)n * H * W * C + c;
+    const V8 me = ld8(xn + ((long long)h * W + w) * C);
+    V8 acc;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc.v[k] = 0.f;
+    // windows ho with 2*ho-1 <= h <= 2*ho+1
+    for (int ho = h >> 1; ho <= (h + 1) >> 1; ++ho) {
+      if (ho >= Ho) continue;
+      for (int wo = w >> 1; wo <= (w + 1) >> 1; ++wo) {
+        if (wo >= Wo) continue;
+        const int my = (h - (2 * ho - 1)) * 3 + (w - (2 * wo - 1));      // my position in that window's scan order
+        bool win[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) win[k] = true;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const int hh = 2 * ho - 1 + kh;
+          if (hh < 0 || hh >= H) continue;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int ww = 2 * wo - 1 + kw;
+            const int pos = kh * 3 + kw;
+            if (ww < 0 || ww >= W || pos == my) continue;
+            const V8 o = ld8(xn + ((long long)hh * W + ww) * C);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)       // an earlier element wins ties, a later one must be strictly larger
+              if (pos < my ? (o.v[k] >= me.v[k]) : (o.v[k] > me.v[k])) win[k] = false;
+          }
+        }
+        const V8 g = ld8(dy + (((long long)n * Ho + ho) * Wo + wo) * dy_stride + c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (win[k]) acc.v[k] += g.v[k];
+      }
+    }
+    st8(dx + (((long long)n * H + h) * W + w) * C + c, acc);
   }
 }
 
@@ -550,6 +632,22 @@ extern "C" int32_t c3d_maxpool2_bwd(const void* x, const void* dy, void* dx, int
       (const bf16*)x, (const bf16*)dy, (bf16*)dx, N, H, W, C, x_stride ? x_stride : C, dy_stride ? dy_stride : C);
   return check_launch("maxpool2_bwd");
 }
+extern "C" int32_t c3d_maxpool3s2_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+  C3D_REQ(x && y && C % 8 == 0 && H >= 1 && W >= 1, "maxpool3s2: bad args");
+  long long work = (long long)N * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * (C / 8);
+  if (work == 0) return C3D_OK;
+  maxpool3s2_fwd_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, N, H, W, C);
+  return check_launch("maxpool3s2_fwd");
+}
+extern "C" int32_t c3d_maxpool3s2_bwd(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W,
+                                      int32_t C, int64_t dy_stride, void* stream) {
+  C3D_REQ(x && dy && dx && C % 8 == 0 && H >= 1 && W >= 1, "maxpool3s2_bwd: bad args");
+  long long work = (long long)N * H * W * (C / 8);
+  if (work == 0) return C3D_OK;
+  maxpool3s2_bwd_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx,
+                                                                               N, H, W, C, dy_stride ? dy_stride : C);
+  return check_launch("maxpool3s2_bwd");
+}
 extern "C" int32_t c3d_preprocess_image(const float* img, int32_t H, int32_t W, void* out_slot, int32_t Hp,
                                         int32_t Wp, int32_t Cp, const float* mean3_host, const float* std3_host,
                                         void* stream) {
@@ -592,7 +690,7 @@ extern "C" int32_t c3d_sgd_momentum_dev(float* p, const float* g, float* mom, in
   return check_launch("sgd");
 }
 
-extern "C" int32_t c3d_bias_act_bwd(const void* dout, const void* out, int32_t relu, int32_t dout_fp32, void* dz,
+extern "C" int32_t c3d_bias_act_bwd(const void* dout, const void* out, int32_t relu, int32_t dtype_flags, void* dz,
                                     float* partial /*[c3d_bn_bwd_blocks(P,C)][C]*/, float* dbias, int64_t P, int32_t C,
                                     void* scratch, void* stream) {
   C3D_REQ(dout && dz && partial && scratch && C % 8 == 0 && C <= 2048, "bias_act_bwd: bad args");
@@ -600,12 +698,16 @@ extern "C" int32_t c3d_bias_act_bwd(const void* dout, const void* out, int32_t r
   if (P == 0) return C3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = c3d_bn_bwd_blocks(P, C);
-  if (dout_fp32)
-    bias_act_bwd_kernel<256, float><<<blocks, 256, 0, st>>>((const float*)dout, (const float*)out, relu, (bf16*)dz,
-                                                           partial, P, C);
-  else
-    bias_act_bwd_kernel<256, bf16><<<blocks, 256, 0, st>>>((const bf16*)dout, (const bf16*)out, relu, (bf16*)dz,
-                                                          partial, P, C);
+  // dtype_flags: bit 0 = dout is fp32, bit 1 = out is fp32 (the forward output keeps its own dtype: a ReLU conv saves
+  // a bf16 `out` even when its consumer hands back an fp32 gradient)
+  const bool din32 = dtype_flags & 1, out32 = dtype_flags & 2;
+#define C3D_BAB(TI, TO) bias_act_bwd_kernel<256, TI, TO><<<blocks, 256, 0, st>>>((const TI*)dout, (const TO*)out, relu, \
+                                                                                 (bf16*)dz, partial, P, C)
+  if (din32 && out32) C3D_BAB(float, float);
+  else if (din32) C3D_BAB(float, bf16);
+  else if (out32) C3D_BAB(bf16, float);
+  else C3D_BAB(bf16, bf16);
+#undef C3D_BAB
   if (dbias) {
     int slabs;
     launch_colsum(partial, blocks, C, (double*)scratch, &slabs, st);

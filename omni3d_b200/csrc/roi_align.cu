@@ -19,6 +19,7 @@ struct RoiLevels {
   int H[5], W[5];
   float scale[5];
   int num_levels;
+  int num_images;
 };
 
 struct Tap { int y0, y1, x0, x1; float w1, w2, w3, w4; bool valid; };
@@ -55,7 +56,16 @@ __global__ void roi_align_kernel(RoiLevels L, const float* __restrict__ rois, in
        bin += (long long)gridDim.x * warps_per_block) {
     const int pw = (int)(bin % PW), ph = (int)((bin / PW) % PH), r = (int)(bin / ((long long)PW * PH));
     const float* roi = rois + (size_t)r * 6;
-    const int b = (int)roi[0], lvl = (int)roi[1];
+    // a NaN / Inf box (diverging step) must not become an out-of-range level or image index: such RoIs pool zeros
+    const float fb = roi[0], fl = roi[1];
+    const bool sane = fb >= 0.f && (L.num_images <= 0 || fb < (float)L.num_images) && fl >= 0.f && fl < (float)L.num_levels &&
+                      isfinite(roi[2]) && isfinite(roi[3]) && isfinite(roi[4]) && isfinite(roi[5]);
+    if (!sane) {
+      if (!BWD)
+        for (int c = lane * 8; c < C; c += 256) *reinterpret_cast<uint4*>(out + (size_t)bin * C + c) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const int b = (int)fb, lvl = (int)fl;
     const float sc = L.scale[lvl];
     const int H = L.H[lvl], W = L.W[lvl];
     const float sw = roi[2] * sc - 0.5f, sh = roi[3] * sc - 0.5f;
@@ -134,7 +144,12 @@ __global__ void roi_align_bwd_sep_kernel(RoiLevels L, const float* __restrict__ 
        bin += (long long)gridDim.x * warps_per_block) {
     const int pw = (int)(bin % PW), ph = (int)((bin / PW) % PH), r = (int)(bin / ((long long)PW * PH));
     const float* roi = rois + (size_t)r * 6;
-    const int b = (int)roi[0], lvl = (int)roi[1];
+    // a NaN / Inf box (diverging step) must not become an out-of-range level or image index: such RoIs pool zeros
+    const float fb = roi[0], fl = roi[1];
+    const bool sane = fb >= 0.f && (L.num_images <= 0 || fb < (float)L.num_images) && fl >= 0.f && fl < (float)L.num_levels &&
+                      isfinite(roi[2]) && isfinite(roi[3]) && isfinite(roi[4]) && isfinite(roi[5]);
+    if (!sane) continue;
+    const int b = (int)fb, lvl = (int)fl;
     const float sc = L.scale[lvl];
     const int H = L.H[lvl], W = L.W[lvl];
     const float sw = roi[2] * sc - 0.5f, sh = roi[3] * sc - 0.5f;
@@ -219,6 +234,7 @@ static int32_t run(bool bwd, const c3d_roi_levels* lv, const float* rois, int R,
   if (R == 0) return C3D_OK;
   RoiLevels L;
   L.num_levels = lv->num_levels;
+  L.num_images = lv->num_images;
   for (int i = 0; i < 5; ++i) {
     L.feat[i] = (const bf16*)lv->feat[i]; L.grad[i] = (float*)lv->grad[i];
     L.H[i] = lv->H[i]; L.W[i] = lv->W[i]; L.scale[i] = lv->scale[i];

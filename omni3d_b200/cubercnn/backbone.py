@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from ..nnfunc import ConvBias, ConvBNAct, MaxPool2
+from ..nnfunc import ConvBias, ConvBNAct, MaxPool2, MaxPool3s2
 from .registry import BACKBONE_REGISTRY
 
 
@@ -141,8 +141,7 @@ class TVResNet(nn.Module):
 
     def forward(self, x):
         x = conv_bn(x, self.conv1, self.bn1)
-        # 3x3 stride-2 pad-1 max pool of the torchvision stem (channels-last view, no copy of the big tensor)
-        x = F.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
+        x = MaxPool3s2.apply(x)              # 3x3 stride-2 pad-1 max pool of the torchvision stem (c3d_maxpool3s2_*)
         out = {}
         for name, layer in zip(("p2", "p3", "p4", "p5"), (self.layer1, self.layer2, self.layer3, self.layer4)):
             for blk in layer:

@@ -152,8 +152,9 @@ class ROIHeads3D(nn.Module):
         fg = vals >= self.iou_thresh
         ioa = pairwise_ioa(gt["boxes"], boxes)
         ioa = torch.where(ign[:, :, None], ioa, torch.zeros_like(ioa)).max(dim=1).values
-        bg = ~fg
-        ign_hit = bg & (ioa >= self.ignore_thresh) & (bg.sum(1, keepdim=True) > 1) & ign.any(1, keepdim=True)
+        bg = ~fg & pvalid                     # roi_heads.py:892-897: the rule needs > 1 REAL background proposals ...
+        ign_hit = (bg & (ioa >= self.ignore_thresh) & (bg.sum(1, keepdim=True) > 1) & ign.any(1, keepdim=True)
+                   & valid.any(1, keepdim=True))       # ... and is dropped when the image has no valid GT (:846-855)
         cls = torch.gather(gt["classes"], 1, idx)
         cls = torch.where(fg, cls, torch.full_like(cls, K))
         cls = torch.where(ign_hit | ~pvalid, torch.full_like(cls, -1), cls)

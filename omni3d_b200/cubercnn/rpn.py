@@ -167,6 +167,10 @@ class RPNWithIgnore(nn.Module):
                                                 self.strides, cfg.MODEL.ANCHOR_GENERATOR.OFFSET)
         self.rpn_head = StandardRPNHead(in_channels, self.anchor_generator.num_anchors)
         self.iou_thresholds = list(R.IOU_THRESHOLDS)
+        if self.iou_thresholds[0] != self.iou_thresholds[-1]:
+            # a real ignore band [lo, hi) (detectron2 default [0.3, 0.7]) would need label -1 between the thresholds;
+            # the accelerated matcher implements the reference's single-threshold form (Base.yaml:57: [0.05, 0.05])
+            raise NotImplementedError("RPN.IOU_THRESHOLDS with lo != hi (ignore band) is not on the accelerated path")
         self.batch_size_per_image = R.BATCH_SIZE_PER_IMAGE
         self.positive_fraction = R.POSITIVE_FRACTION
         self.pre_nms_topk = {True: R.PRE_NMS_TOPK_TRAIN, False: R.PRE_NMS_TOPK_TEST}

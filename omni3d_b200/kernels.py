@@ -12,7 +12,7 @@ vp, i32, i64, f32, f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes
 
 class RoiLevels(ctypes.Structure):
     _fields_ = [("feat", vp * 5), ("grad", vp * 5), ("H", i32 * 5), ("W", i32 * 5), ("scale", f32 * 5),
-                ("num_levels", i32)]
+                ("num_levels", i32), ("num_images", i32)]
 
 
 def _bind():
@@ -39,6 +39,8 @@ def _bind():
     sig["c3d_cube_loss_fwd"] = [vp, vp, i32, vp, vp]
     sig["c3d_cube_loss_bwd"] = [vp, vp, vp, i32, vp, vp]
     sig["c3d_zero_stuff2"] = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    sig["c3d_maxpool3s2_fwd"] = [vp, vp, i32, i32, i32, i32, vp]
+    sig["c3d_maxpool3s2_bwd"] = [vp, vp, vp, i32, i32, i32, i32, i64, vp]
     L.c3d_bn_scratch_bytes.restype = ctypes.c_size_t
     L.c3d_bn_scratch_bytes.argtypes = [i32]
     L.c3d_nms_workspace_bytes.restype = ctypes.c_size_t
@@ -142,6 +144,25 @@ def maxpool2_bwd(x, dy):
     return dx
 
 
+def maxpool3s2_fwd(x):
+    L = _bind()
+    N, H, W, C = x.shape
+    y = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), device=x.device, dtype=x.dtype)
+    _lib.check(L.c3d_maxpool3s2_fwd(_p(x), _p(y), N, H, W, C, _st()))
+    return y
+
+
+def maxpool3s2_bwd(x, dy):
+    L = _bind()
+    N, H, W, C = x.shape
+    ds = pixel_stride(dy)
+    if ds is None:
+        dy, ds = dy.contiguous(), 0
+    dx = torch.empty_like(x)
+    _lib.check(L.c3d_maxpool3s2_bwd(_p(x), _p(dy), _p(dx), N, H, W, C, ds, _st()))
+    return dx
+
+
 def preprocess_images(images, mean, std, size_divisibility=64, cpad=16):
     """list of (3,H,W) fp32 or uint8 CUDA tensors -> (N,Hp,Wp,cpad) bf16 NHWC batch (normalised, zero padded)."""
     L = _bind()
@@ -162,6 +183,7 @@ def preprocess_images(images, mean, std, size_divisibility=64, cpad=16):
 def _levels(feats, strides, grads=None):
     lv = RoiLevels()
     lv.num_levels = len(feats)
+    lv.num_images = feats[0].shape[0]
     for i, f in enumerate(feats):
         lv.feat[i] = f.data_ptr()
         lv.grad[i] = grads[i].data_ptr() if grads is not None else None
@@ -299,7 +321,8 @@ def bias_act_bwd(dout, out, relu, dbias):
     partial = torch.empty((blocks, C), device=dout.device, dtype=torch.float32)
     scratch = torch.empty(128 * 2 * C, device=dout.device, dtype=torch.float64)
     dz = torch.empty(dout.shape, device=dout.device, dtype=torch.bfloat16)
-    _lib.check(L.c3d_bias_act_bwd(_p(dout), _p(out), int(relu), int(dout.dtype == torch.float32), _p(dz), _p(partial),
+    flags = int(dout.dtype == torch.float32) | (2 if (out is not None and out.dtype == torch.float32) else 0)
+    _lib.check(L.c3d_bias_act_bwd(_p(dout), _p(out), int(relu), flags, _p(dz), _p(partial),
                                   _p(dbias), P, C, _p(scratch), _st()), launches=3 if dbias is not None else 1)
     return dz
 

@@ -6,6 +6,8 @@ kernels' bf16 OHWI layouts once per parameter version.  Forward AND backward run
   conv fwd  -> c3d_conv2d_fwd          dgrad -> c3d_conv2d_fwd with flipped/transposed weights
   wgrad     -> c3d_conv2d_wgrad        BN    -> c3d_bn_finalize / c3d_bn_apply / c3d_bn_bwd
 """
+import weakref
+
 import torch
 
 from . import conv as K
@@ -24,17 +26,26 @@ def invalidate_packed():
     _phase_cache.clear()
 
 
+def _cache_key(w):
+    """Only nn.Parameter objects are cached, keyed on the OBJECT (weak reference) + storage + version + optimizer epoch.
+    Derived temporaries (the zero-padded stem weight, the fused RPN predictor weight) are leaf tensors under no_grad
+    whose storage the caching allocator hands back on the next forward: a data_ptr key would alias them across
+    load_state_dict / a second model, so they are packed on every call instead."""
+    if not isinstance(w, torch.nn.Parameter):
+        return None, None
+    return id(w), (w.data_ptr(), w._version, _epoch, tuple(w.shape), tuple(w.stride()))
+
+
 def _packed(w, kind):
     """bf16 kernel-layout copies of an fp32 OIHW master — (Cout,KH,KW,Cin) for the forward pass and
     (Cin,KH,KW,Cout) with the taps rotated by 180 degrees for the data gradient — produced by ONE
-    c3d_pack_conv_weight launch and cached per (storage, version, optimizer epoch)."""
-    key = w.data_ptr()
-    ver = (w._version, _epoch, tuple(w.shape))
-    hit = _pack_cache.get(key)
-    if hit is None or hit[0] != ver:
+    c3d_pack_conv_weight launch and cached per (parameter object, storage, version, optimizer epoch)."""
+    key, ver = _cache_key(w)
+    hit = _pack_cache.get(key) if key is not None else None
+    if hit is None or hit[0] != ver or hit[3]() is not w:
         f, g = K.pack_conv_weight(w)
-        hit = (ver, f, g)
-        if isinstance(w, torch.nn.Parameter) or w.is_leaf:
+        hit = (ver, f, g, weakref.ref(w) if key is not None else None)
+        if key is not None:
             _pack_cache[key] = hit
     return hit[1] if kind == "fwd" else hit[2]
 
@@ -47,10 +58,9 @@ def _phase_packs(w):
     """sub-kernels of a 3x3 / stride-2 / pad-1 conv's data gradient, one per output parity (a,b):
     dx[2i+a, 2j+b] = sum_{k'} dy[i+k'h, j+k'w] * W[.., kh(a,k'h), kw(b,k'w)] with kh(0,.) = [1], kh(1,.) = [2,0].
     -> {(a,b): bf16 (Cin, KH', KW', Cout)}, cached per parameter version / optimizer epoch."""
-    key = w.data_ptr()
-    ver = (w._version, _epoch, tuple(w.shape))
-    hit = _phase_cache.get(key)
-    if hit is not None and hit[0] == ver:
+    key, ver = _cache_key(w)
+    hit = _phase_cache.get(key) if key is not None else None
+    if hit is not None and hit[0] == ver and hit[2]() is w:
         return hit[1]
     taps = _tap_index.get(w.device)
     if taps is None:          # device-resident index tensors, built once (a python-list index is a host->device copy)
@@ -61,8 +71,8 @@ def _phase_packs(w):
             for b in (0, 1):
                 sub = w.index_select(2, taps[a]).index_select(3, taps[b])   # (Cout,Cin,KH',KW')
                 packs[(a, b)] = sub.permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)
-    if w.is_leaf:
-        _phase_cache[key] = (ver, packs)
+    if key is not None:
+        _phase_cache[key] = (ver, packs, weakref.ref(w))
     return packs
 
 
@@ -182,6 +192,21 @@ class MaxPool2(torch.autograd.Function):
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
         return Kx.maxpool2_bwd(x, dy)
+
+
+class MaxPool3s2(torch.autograd.Function):
+    """3x3 / stride 2 / pad 1 max pool of the torchvision ResNet stem (resnet.py:45-50) on NHWC bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        return Kx.maxpool3s2_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return Kx.maxpool3s2_bwd(x, dy)
 
 
 class ROIAlign(torch.autograd.Function):

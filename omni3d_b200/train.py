@@ -58,6 +58,11 @@ class FlatSGDTrainer:
     def __init__(self, cfg, model, channels_last_weights=True, use_graph=None):
         if cfg.SOLVER.TYPE != "sgd":
             raise ValueError("{} is not supported as an optimizer on the accelerated path.".format(cfg.SOLVER.TYPE))
+        if getattr(cfg.SOLVER, "NESTEROV", False):
+            raise NotImplementedError("SOLVER.NESTEROV is not on the flat-arena path (reference default: False)")
+        clip = getattr(cfg.SOLVER, "CLIP_GRADIENTS", None)
+        if clip is not None and getattr(clip, "ENABLED", False):
+            raise NotImplementedError("SOLVER.CLIP_GRADIENTS.ENABLED is not on the flat-arena path (solver/build.py:58-62)")
         self.cfg, self.model = cfg, model
         self.world = _world()
         dev = next(model.parameters()).device
@@ -127,6 +132,7 @@ class FlatSGDTrainer:
         self.status_dev = torch.zeros(len(LOSS_KEYS) + 4, device=dev)
         self.status_event = None
         self.iteration = 0
+        self.steps_run = 0                      # steps executed by THIS object (graph warm-up; `iteration` may be restored)
         self.stabilize = cfg.MODEL.STABILIZE > 0
         # CUDA-graph replay of the step body (see step() / _body()); C3D_TRAIN_GRAPH=0 disables it
         if use_graph is None:
@@ -227,7 +233,7 @@ class FlatSGDTrainer:
         lr = lr_at(self.cfg, self.iteration)
         staged = self.model.stage_inputs(batched_inputs) if hasattr(self.model, "stage_inputs") else batched_inputs
         loss_dict = None
-        if self.use_graph and self.iteration >= self.graph_warmup:
+        if self.use_graph and self.steps_run >= self.graph_warmup:
             sig = self._signature(staged)
             if self.graph is not None and (sig[0] != self.graph_sig[0] or sig[1] > self.graph_sig[1]):
                 self.graph, self.static = None, None     # other shapes: record again
@@ -245,6 +251,9 @@ class FlatSGDTrainer:
                 self._copy_into_static(staged)
                 self.lr_dev.fill_(lr)
                 self._replay()
+                # the replayed SGD kernel rewrote flat_p through raw pointers: bf16 packs cached by an eval / eager
+                # forward that ran between two replays are stale now (the graph itself re-packs inside its own pool)
+                nnfunc.invalidate_packed()
                 _lib.LAUNCHES["n"] += self.graph_launches
                 loss_dict = self.graph_losses
         if loss_dict is None:
@@ -257,6 +266,7 @@ class FlatSGDTrainer:
         else:
             self.status_event = True
         self.iteration += 1
+        self.steps_run += 1
         return loss_dict
 
     def _replay(self):
@@ -299,6 +309,7 @@ class FlatSGDTrainer:
             self.graph_launches = _lib.LAUNCHES["n"] - n0
             self.graph, self.graph_sig, self.graph_losses = graphs, sig, losses
             self._replay()          # recording does not execute: run the step that was just recorded
+            nnfunc.invalidate_packed()
             return losses
         except Exception as e:      # noqa: BLE001 — never silently: say so, then keep training eagerly
             import sys
@@ -310,6 +321,21 @@ class FlatSGDTrainer:
             self.use_graph, self.graph, self.static = False, None, None
             torch.cuda.synchronize()
             return None
+
+    # -- checkpoint / resume (the reference restores optimizer, scheduler and start_iter through its checkpointer,
+    #    tools/train_net.py:128-143,443; its retry path depends on that) --------------------------------------
+    def state_dict(self):
+        return {"momentum": self.flat_m.detach().clone(), "controller": self.state.detach().clone(),
+                "iteration": int(self.iteration), "bounds": dict(self.bounds)}
+
+    def load_state_dict(self, sd, start_iter=None):
+        if tuple(sd["momentum"].shape) != tuple(self.flat_m.shape) or dict(sd["bounds"]) != dict(self.bounds):
+            raise ValueError("trainer state does not match this model's parameter arena")
+        with torch.no_grad():
+            self.flat_m.copy_(sd["momentum"].to(self.flat_m.device))
+            self.state.copy_(sd["controller"].to(self.state.device))
+        self.iteration = int(sd["iteration"] if start_iter is None else start_iter)
+        nnfunc.invalidate_packed()
 
     def status(self, wait=True):
         """{'losses': {...}, 'total_loss', 'recent_loss', 'iterations_success', 'iterations_explode', 'retry'}."""

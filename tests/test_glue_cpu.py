@@ -132,3 +132,126 @@ def test_stage_inputs_is_the_only_host_interface():
     assert gt["classes"][1, 2].item() == -2 and torch.equal(gt["poses"][1, 2], torch.eye(3))
     f = synth.make_batch(1, 64, 64, num_gt=2, seed=4)
     assert model.stage_inputs(f)["images"][0].dtype == torch.float32
+
+
+# ---- the product's OWN proposal labelling against the oracle's pre-sampling outputs ------------------
+def synthetic_proposals(items, P, seed):
+    """(B,P,4) proposals that exercise every label: jittered copies of the valid GT (foreground at varying IoU), boxes
+    inside the ignore regions, random background; per-image count < P (padding slots)."""
+    g = torch.Generator().manual_seed(seed)
+    B = len(items)
+    boxes = torch.zeros(B, P, 4)
+    counts = torch.zeros(B, dtype=torch.int32)
+    for i, it in enumerate(items):
+        H, W = it["image"].shape[1:]
+        gb = it["gt"]["boxes"]
+        n = P - 7 * i
+        rows = []
+        for j in range(n):
+            r = j % 3
+            if r == 0:                                   # jittered GT (valid or ignore alike)
+                b = gb[torch.randint(0, len(gb), (1,), generator=g)[0]].clone()
+                wh = (b[2:] - b[:2])
+                b += (torch.rand(4, generator=g) - 0.5) * 0.5 * torch.cat([wh, wh])
+            elif r == 1:                                 # small box inside some GT (IoA with an ignore region = 1)
+                k = gb[torch.randint(0, len(gb), (1,), generator=g)[0]]
+                c = k[:2] + torch.rand(2, generator=g) * (k[2:] - k[:2]) * 0.5
+                b = torch.cat([c, c + (k[2:] - k[:2]) * 0.3])
+            else:
+                c = torch.rand(2, generator=g) * torch.tensor([W * 0.8, H * 0.8])
+                b = torch.cat([c, c + torch.rand(2, generator=g) * torch.tensor([W * 0.2, H * 0.2]) + 2])
+            b[0::2] = b[0::2].clamp(0, W)
+            b[1::2] = b[1::2].clamp(0, H)
+            if b[2] - b[0] < 1 or b[3] - b[1] < 1:
+                b = torch.tensor([0.0, 0.0, 8.0, 8.0])
+            rows.append(b)
+        boxes[i, :n] = torch.stack(rows)
+        counts[i] = n
+    return boxes, counts
+
+
+def oracle_prelabels(orc, items, boxes, counts):
+    """the oracle's (= reference's roi_heads.py:862-929) matched GT boxes / IoUs / class labels of every proposal
+    (appended GT included), captured right before its multinomial sampling."""
+    from detectron2.structures import Boxes, Instances
+    from detectron2.utils.events import EventStorage
+    import oracle.cubercnn_oracle.model as om
+    rh = orc.roi_heads
+    cap = {"labels": [], "ious": [], "midx": []}
+    o_sub, o_match = om.iou_weighted_subsample, rh.proposal_matcher
+
+    def sub(labels, num, frac, bg, ious, eps=1e-4):
+        cap["labels"].append(labels.clone()); cap["ious"].append(ious.clone())
+        return o_sub(labels, num, frac, bg, ious, eps)
+
+    class M:
+        def __call__(self, q):
+            mi, ml = o_match(q)
+            cap["midx"].append(mi.clone())
+            return mi, ml
+    d2 = model_io.to_d2_inputs(items)
+    props = []
+    for i, it in enumerate(d2):
+        p = Instances(it["instances"].image_size)
+        n = int(counts[i])
+        p.proposal_boxes = Boxes(boxes[i, :n].clone())
+        p.objectness_logits = torch.zeros(n)
+        props.append(p)
+    om.iou_weighted_subsample, rh.proposal_matcher = sub, M()
+    try:
+        torch.manual_seed(0)
+        with EventStorage(0):
+            sampled = rh.label_and_sample_proposals(props, [it["instances"] for it in d2])
+    finally:
+        om.iou_weighted_subsample, rh.proposal_matcher = o_sub, o_match
+    return cap, sampled, d2
+
+
+def check_prelabels(midx, miou, cls, gt, cap, d2, counts, P):
+    """product (B,P+G) outputs == oracle per-image outputs, bit for bit (same fp32 IoU formula)."""
+    for i, it in enumerate(d2):
+        inst = it["instances"]
+        vmask = inst.gt_classes >= 0
+        valid_pos = vmask.nonzero().squeeze(1)                 # padded-GT index of the oracle's k-th valid target
+        n, nv = int(counts[i]), int(vmask.sum())
+        sel = torch.cat([torch.arange(n), P + valid_pos])       # proposals, then the appended valid GT
+        assert len(sel) == len(cap["labels"][i])
+        assert torch.equal(cls[i][sel].cpu(), cap["labels"][i]), i
+        assert torch.equal(miou[i][sel].cpu(), cap["ious"][i]), i
+        vb = inst.gt_boxes.tensor[vmask]
+        assert torch.equal(gt["boxes"][i].cpu()[midx[i][sel].cpu()], vb[cap["midx"][i]]), i
+        # padding slots and appended non-valid GT are never candidates
+        rest = torch.ones(cls.shape[1], dtype=torch.bool); rest[sel] = False
+        assert (cls[i].cpu()[rest] == -1).all()
+
+
+def _label_case(seed, num_gt=6, extra_ignore=True):
+    items = synth.make_batch(3, 160, 192, num_gt=num_gt, seed=seed)
+    if extra_ignore:                                            # a second ignore region in image 0, none in image 2
+        items[0]["gt"]["classes"][0] = -1
+        items[2]["gt"]["classes"][-1] = 3
+    return items
+
+
+def test_match_proposals_equals_oracle_prelabels():
+    pcfg, ocfg = _cfgs()
+    torch.manual_seed(0)
+    orc = co.build_model(ocfg)
+    from omni3d_b200.cubercnn.roi_heads import ROIHeads3D
+    rh = ROIHeads3D.__new__(ROIHeads3D)
+    RH = pcfg.MODEL.ROI_HEADS
+    rh.num_classes, rh.iou_thresh, rh.ignore_thresh = RH.NUM_CLASSES, RH.IOU_THRESHOLDS[0], pcfg.MODEL.RPN.IGNORE_THRESHOLD
+    P = 96
+    for seed in (3, 4):
+        items = _label_case(seed)
+        boxes, counts = synthetic_proposals(items, P, seed)
+        cap, _, d2 = oracle_prelabels(orc, items, boxes, counts)
+        gt = collate_gt(items, torch.device("cpu"))
+        pvalid = torch.arange(P)[None] < counts[:, None]
+        allb = torch.cat([boxes, gt["boxes"]], 1)
+        allv = torch.cat([pvalid, gt["present"] & (gt["classes"] >= 0)], 1)
+        midx, miou, cls = ROIHeads3D.match_proposals(rh, allb, allv, gt)
+        check_prelabels(midx, miou, cls, gt, cap, d2, counts, P)
+        # all three label kinds occur, so the comparison is not vacuous
+        flat = torch.cat(cap["labels"])
+        assert (flat == -1).any() and (flat == RH.NUM_CLASSES).any() and ((flat >= 0) & (flat < RH.NUM_CLASSES)).any()

@@ -236,26 +236,3 @@ def test_cuda_graph_step_matches_eager_step():
         assert abs(a - b) <= 0.12 * abs(a), (tot[False], tot[True])
     # steps 3..5 replay the graph on three different batches
     assert len({round(v, 4) for v in tot[True][3:]}) == 3, tot[True]
-
-
-@pytest.mark.skipif(not __import__("os").environ.get("C3D_PENDING_TESTS"),
-                    reason="round-2 parity test, not yet validated on a B200 (the ResNet34 product path itself runs: "
-                           "tools/resnet34_smoke.py); enable with C3D_PENDING_TESTS=1")
-def test_resnet34_fpn_features_frozen_bn_pending():
-    """ResNet34-FPN features of the product path vs the fp32 oracle with BatchNorm on running statistics."""
-    from omni3d_b200 import cubercnn as pc
-    from oracle import cubercnn_oracle as co
-    from oracle import model_io
-    torch.manual_seed(0)
-    orc = co.build_model(co.load_cfg("cubercnn_ResNet34_FPN.yaml"))
-    torch.manual_seed(0)
-    prod = pc.build_model(pc.load_cfg("cubercnn_ResNet34_FPN.yaml", ["MODEL.WEIGHTS_PRETRAIN", "none"]))
-    prod.load_state_dict(orc.state_dict())
-    items = synth.make_batch(2, H, W, with_gt=False, seed=7)
-    _freeze_bn(prod); _freeze_bn(orc)
-    with torch.no_grad():
-        x, _ = prod.preprocess_image(items)
-        feats = prod.backbone(x)
-        ref = orc.backbone(orc.preprocess_image(model_io.to_d2_inputs(items)).tensor)
-    for k in ref:
-        assert _rel(feats[k].float().cpu().permute(0, 3, 1, 2), ref[k]) < 3e-2, k
