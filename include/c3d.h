@@ -61,6 +61,18 @@ int32_t c3d_box3d_overlap(const float* boxes_dt, int64_t n_dt, const float* boxe
                           float eps_coplanar, float eps_nonzero, float* iou, int32_t* n_bad,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Segmented (CSR) box3d_overlap: `num_groups` independent (detections x ground truths) blocks in ONE launch — replaces the
+ * per-(image, category) calls of Omni3Deval.computeIoU (cubercnn/evaluation/omni3d_evaluation.py:1339-1343, 1359-1431,
+ * call site :1401-1412).  boxes_dt [n_dt][8][3] / boxes_gt [n_gt][8][3] hold all groups back to back; group g owns dt rows
+ * [dt_off[g], dt_off[g+1]) and gt rows [gt_off[g], gt_off[g+1]) (int32 device arrays of num_groups+1 entries); its IoU
+ * matrix is written row-major at iou + pair_off[g] (int64 device array, pair_off[g+1]-pair_off[g] = rows x cols,
+ * pair_off[num_groups] = total_pairs).  Row checks / n_bad as in c3d_box3d_overlap (over all dt boxes). */
+size_t c3d_box3d_overlap_segmented_workspace_bytes(int64_t n_dt, int64_t n_gt, int64_t total_pairs);
+int32_t c3d_box3d_overlap_segmented(const float* boxes_dt, int64_t n_dt, const float* boxes_gt, int64_t n_gt,
+                                    const int32_t* dt_off, const int32_t* gt_off, const int64_t* pair_off,
+                                    int32_t num_groups, int64_t total_pairs, float eps_coplanar, float eps_nonzero,
+                                    float* iou, int32_t* n_bad, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * NHWC bf16 implicit-GEMM convolution on tcgen05 tensor cores (TMA-staged, fp32 accumulate in TMEM).
  * Replaces the cuDNN calls behind nn.Conv2d in cubercnn/modeling/backbone/dla.py:43-51,159-161,
@@ -104,6 +116,26 @@ int32_t c3d_conv2d_wgrad_ex(const c3d_conv_desc* d, const void* x, const void* d
  * forward pack and/or bf16 (Cin,KH,KW,Cout) 180-degree-rotated data-gradient pack (either output may be NULL) */
 int32_t c3d_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin, int32_t KH, int32_t KW, int32_t src_is_ohwi,
                              void* fwd_ohwi, void* dgrad_ihwo, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fully-connected layers on the same tcgen05 kernels (bf16 operands, fp32 accumulate in TMEM, bias + ReLU fused).
+ * Replace the cuBLAS GEMMs behind nn.Linear in detectron2 FastRCNNConvFCHead / FastRCNNOutputLayers
+ * (configs/Base.yaml:67-70, cubercnn/modeling/roi_heads/fast_rcnn.py:119-143) and in CubeHead
+ * (cubercnn/modeling/roi_heads/cube_head.py:63-73,108-144,146-197).
+ *   x  (rows, K) bf16 row-major; w (N, K) bf16 = nn.Linear.weight; wt (K, N) bf16 = its transpose;
+ *   K % 16 == 0, N % 16 == 0 (callers zero-pad the predictors).
+ * c3d_pack_linear_weight: fp32 master (N, K) -> bf16 w (N, K') and (optional) wt (K', N).  C * PP == K with PP > 1
+ *   re-orders the input features from (c, p) [NCHW-flattened RoI, the reference's layout] to (p, c) [NHWC-flattened RoI].
+ * c3d_linear_wgrad: dw (fp32, += with atomics) = dy^T x.  master_chw != 0: dw is addressed in the master's (c, p)
+ *   feature order (accumulate straight into the optimizer's gradient arena), else in the packed (p, c) order.
+ * ------------------------------------------------------------------------------------------ */
+int32_t c3d_pack_linear_weight(const float* w, int32_t N, int32_t K, int32_t C, int32_t PP, void* w_bf16, void* wt_bf16,
+                               void* stream);
+int32_t c3d_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t rows, int32_t K, int32_t N,
+                       int32_t relu, int32_t out_fp32, void* stream);
+int32_t c3d_linear_dgrad(const void* dy, const void* wt, void* dx, int64_t rows, int32_t N, int32_t K, void* stream);
+int32_t c3d_linear_wgrad(const void* x, const void* dy, float* dw, int64_t rows, int32_t K, int32_t N, int32_t C,
+                         int32_t PP, int32_t master_chw, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * HBM-bound NHWC bf16 kernels around the convolutions.
@@ -242,12 +274,12 @@ int32_t c3d_rpn_loss_bwd(const float* logits, const float* deltas, const int8_t*
                          float* ddeltas, void* stream);
 
 /* RPN proposal decoding of one FPN level's top-k candidates for all images (apply_deltas, clip, finite / min-size
- * filter; detectron2 find_top_rpn_proposals via rpn.py:221-284).  topk_idx / topk_score [B][K] index the level's
- * anchors [A][4] and deltas [B][A][4]; image_hw [B][2] = (h, w).  Results go to columns col0..col0+K-1 of the
+ * filter; detectron2 find_top_rpn_proposals via rpn.py:221-284).  topk_idx / topk_score [B][K] (rows in_stride elements
+ * apart; 0 => K) index the level's anchors [A][4] and deltas [B][A][4]; image_hw [B][2] = (h, w).  Results go to columns col0..col0+K-1 of the
  * concatenated [B][Ktot] arrays: boxes (xyxy), key (score, or -inf when filtered), lvl (= level as float); nvalid[b] and
  * maxc[b] (max kept coordinate, fp32 bits; both zero-initialised by the caller) are accumulated with atomics. */
-int32_t c3d_rpn_decode_level(const int64_t* topk_idx, const float* topk_score, const float* deltas, const float* anchors,
-                             const float* image_hw, int32_t B, int32_t K, int64_t A, const float* weights4_host,
+int32_t c3d_rpn_decode_level(const int64_t* topk_idx, const float* topk_score, int64_t in_stride, const float* deltas,
+                             const float* anchors, const float* image_hw, int32_t B, int32_t K, int64_t A, const float* weights4_host,
                              float scale_clamp, float min_size, int32_t level, int32_t col0, int32_t Ktot, float* boxes,
                              float* key, float* lvl, int32_t* nvalid, float* maxc, void* stream);
 
@@ -263,6 +295,64 @@ int32_t c3d_rpn_decode_level(const int64_t* topk_idx, const float* topk_score, c
  * ------------------------------------------------------------------------------------------ */
 int32_t c3d_cube_loss_fwd(const float* raw, const float* aux, int32_t n, float* out, void* stream);
 int32_t c3d_cube_loss_bwd(const float* raw, const float* aux, const float* dout, int32_t n, float* draw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Selection / sampling kernels of the RPN and ROI-head glue (omni3d_b200/csrc/select_ops.cu).
+ * ------------------------------------------------------------------------------------------ */
+/* Sorted (descending) top-k of `nseg` row segments per image in ONE launch (grid B x nseg): the per-level pre-NMS top-k
+ * of detectron2 find_top_rpn_proposals (via cubercnn/modeling/proposal_generator/rpn.py:221-284, configs/Base.yaml:51-54),
+ * the score sort of the concatenated candidates (k == n), the top-M of the inference candidates (fast_rcnn.py:57-116).
+ * Segment s of image b reads vals + b*row_stride [0, n) and writes its k results (value, index inside the segment) to
+ * columns [out_col, out_col + k) of row b of out_vals / out_idx / out_idx64 (row length out_stride); k <= 8192.
+ * Ties: equal values come out in ascending index order; WHICH of more-than-needed equal values are taken is unspecified
+ * (as for torch.topk).  out_count [B][nseg] (may be NULL) = number of selected values > -inf. */
+typedef struct {
+  const float* vals;
+  int64_t row_stride;
+  int32_t n, k, out_col;
+} c3d_topk_seg;
+int32_t c3d_topk_segments(const c3d_topk_seg* segs, int32_t nseg, int32_t B, int32_t out_stride, float* out_vals,
+                          int32_t* out_idx, int64_t* out_idx64, int32_t* out_count, void* stream);
+
+/* ROIHeads3D.label_and_sample_proposals (cubercnn/modeling/roi_heads/roi_heads.py:826-929), one image per block:
+ * matcher ([IOU_THRESHOLD] / labels [0,1]) over [proposals | appended valid GT], ignore-region rule (background proposals
+ * with IoA >= ignore_thresh become -1 when the image has > 1 background proposals), IoU-weighted sampling WITHOUT
+ * replacement of <= Fcap foreground and the remaining background proposals (Gumbel top-k on a Philox stream: the same
+ * distribution as torch.multinomial(iou + 1e-4), rpn.py:275-328), foreground-first compaction into S slots and the gather
+ * of the matched GT fields.  P + G <= 2048, G <= 256.  rng = {seed, step counter} on the device (bump_rng != 0: the
+ * counter is incremented afterwards, so a replayed CUDA graph draws fresh noise every step).
+ * Pre-sampling outputs (all three or none) are [B][P+G]: matched GT index, matched IoU (>= 0), class label
+ * (K = background, -1 = ignore / padding).  Sampled outputs are [B][S]. */
+typedef struct {
+  const float* prop_boxes;      /* [B][P][4] */
+  const int32_t* prop_count;    /* [B] */
+  const float* gt_boxes;        /* [B][G][4] */
+  const int64_t* gt_classes;    /* [B][G], < 0 = ignore region */
+  const uint8_t* gt_present;    /* [B][G] */
+  const float* gt_boxes3D;      /* [B][G][9] */
+  const float* gt_poses;        /* [B][G][9] */
+  int32_t B, P, G, K, S, Fcap, append_gt;
+  float iou_thresh, ignore_thresh;
+  const uint64_t* rng;
+  int32_t bump_rng;
+  int64_t* matched_idx; float* matched_iou; int64_t* labels;
+  float* s_boxes; uint8_t* s_valid; int64_t* s_classes; float* s_gt_boxes; float* s_gt_boxes3D; float* s_gt_poses;
+  int64_t* s_index;             /* index into [proposals | GT] of every slot (may be NULL) */
+  float* stats;                 /* [2] += (#foreground, #background samples) over the batch (may be NULL) */
+} c3d_label_sample_args;
+int32_t c3d_label_sample_proposals(const c3d_label_sample_args* args, void* stream);
+
+/* RPNWithIgnore.label_and_sample_anchors, sampling part (rpn.py:62-105, 275-328), around c3d_topk_segments:
+ *   keys   [B][2][A]: Gumbel keys of the positive (labels01 == 1) / negative (== 0) anchors, -inf elsewhere;
+ *          counts [B][2] = number of positive / negative candidates
+ *   finish: out_labels [B][A] int8 = -1, sampled negatives 0 (-1 when inside an ignore region and > 1 negatives were
+ *          sampled), sampled positives 1, the best anchor of every valid GT 1.  topk_idx [B][2][k] from the top-k of keys. */
+int32_t c3d_anchor_sample_keys(const int8_t* labels01, const float* matched_iou, int32_t B, int64_t A, const uint64_t* rng,
+                               float* keys, int32_t* counts, void* stream);
+int32_t c3d_anchor_sample_finish(const int8_t* labels01, const float* max_ioa, const int32_t* topk_idx, const int32_t* counts,
+                                 const int32_t* best_idx, const uint8_t* gt_valid, const uint8_t* gt_ign, int32_t B, int32_t G,
+                                 int64_t A, int32_t k, int32_t cap_pos, int32_t n_total, float ignore_thresh,
+                                 int8_t* out_labels, uint64_t* rng_bump, void* stream);
 
 #ifdef __cplusplus
 }

@@ -60,4 +60,7 @@ EXPORTS = [
     "c3d_nms_workspace_bytes", "c3d_nms_batched", "c3d_bias_act_bwd", "c3d_sumpool2", "c3d_zero_stuff2", "c3d_cube_loss_fwd", "c3d_cube_loss_bwd",
     "c3d_anchor_match", "c3d_preprocess_image_u8", "c3d_sgd_momentum_dev", "c3d_rpn_loss_fwd", "c3d_rpn_loss_bwd", "c3d_nms_batched_grouped", "c3d_rpn_decode_level",
     "c3d_maxpool3s2_fwd", "c3d_maxpool3s2_bwd",
+    "c3d_pack_linear_weight", "c3d_linear_fwd", "c3d_linear_dgrad", "c3d_linear_wgrad",
+    "c3d_box3d_overlap_segmented_workspace_bytes", "c3d_box3d_overlap_segmented",
+    "c3d_topk_segments", "c3d_label_sample_proposals", "c3d_anchor_sample_keys", "c3d_anchor_sample_finish",
 ]

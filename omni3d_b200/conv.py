@@ -40,6 +40,15 @@ def _bind():
         L.c3d_conv2d_wgrad_ex.argtypes = [P, vp, vp, vp, i32, vp]
         L.c3d_pack_conv_weight.restype = i32
         L.c3d_pack_conv_weight.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp]
+        i64 = ctypes.c_int64
+        L.c3d_pack_linear_weight.restype = i32
+        L.c3d_pack_linear_weight.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
+        L.c3d_linear_fwd.restype = i32
+        L.c3d_linear_fwd.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
+        L.c3d_linear_dgrad.restype = i32
+        L.c3d_linear_dgrad.argtypes = [vp, vp, vp, i64, i32, i32, vp]
+        L.c3d_linear_wgrad.restype = i32
+        L.c3d_linear_wgrad.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]
         _bound = True
     return L
 
@@ -123,4 +132,55 @@ def conv2d_wgrad(x, dy, KH, KW, stride=1, pad=0, dw=None, oihw=False):
         dw = torch.zeros((Cout, Cin, KH, KW) if oihw else (Cout, KH, KW, Cin), device=x.device, dtype=torch.float32)
     d = ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
     _lib.check(L.c3d_conv2d_wgrad_ex(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), int(oihw), _stream()))
+    return dw
+
+
+# ---- fully-connected layers on the same kernels (c3d_linear_*) -------------------------------------------------------
+def pack_linear_weight(w, chw=None, want_t=True):
+    """fp32 master (N, K) -> bf16 (N, K') [+ bf16 (K', N)].  chw = (C, PP): the master's input features are ordered
+    (c, p) (nn.Linear over an NCHW-flattened RoI) and are re-ordered to (p, c) (NHWC-flattened RoI)."""
+    L = _bind()
+    N, Kdim = w.shape
+    w = w.detach().contiguous()
+    C, PP = chw if chw is not None else (Kdim, 1)
+    f = torch.empty((N, Kdim), device=w.device, dtype=torch.bfloat16)
+    t = torch.empty((Kdim, N), device=w.device, dtype=torch.bfloat16) if want_t else None
+    _lib.check(L.c3d_pack_linear_weight(_ptr(w), N, Kdim, C, PP, _ptr(f), _ptr(t), _stream()), launches=2 if want_t else 1)
+    return f, t
+
+
+def linear_fwd(x, w, bias=None, relu=False, out_fp32=False):
+    """x (rows, K) bf16, w (N, K) bf16, bias (N,) fp32 -> [relu](x w^T + bias) (rows, N) bf16 | fp32."""
+    L = _bind()
+    rows, Kdim = x.shape
+    N = w.shape[0]
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.is_contiguous() and w.is_contiguous()
+    assert w.shape[1] == Kdim and (bias is None or (bias.dtype == torch.float32 and bias.is_contiguous()))
+    y = torch.empty((rows, N), device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    _lib.check(L.c3d_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), rows, Kdim, N, int(relu), int(out_fp32), _stream()))
+    return y
+
+
+def linear_dgrad(dy, wt):
+    """dy (rows, N) bf16, wt (K, N) bf16 (the transposed weight) -> dx (rows, K) bf16."""
+    L = _bind()
+    rows, N = dy.shape
+    Kdim = wt.shape[0]
+    assert dy.dtype == torch.bfloat16 and wt.dtype == torch.bfloat16 and dy.is_contiguous() and wt.is_contiguous()
+    dx = torch.empty((rows, Kdim), device=dy.device, dtype=torch.bfloat16)
+    _lib.check(L.c3d_linear_dgrad(_ptr(dy), _ptr(wt), _ptr(dx), rows, N, Kdim, _stream()))
+    return dx
+
+
+def linear_wgrad(x, dy, dw=None, chw=None, master_chw=True):
+    """dw (N, K) fp32 (+)= dy^T x.  chw = (C, PP) + master_chw: address dw in the master's (c, p) feature order."""
+    L = _bind()
+    rows, Kdim = x.shape
+    N = dy.shape[1]
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
+    if dw is None:
+        dw = torch.zeros((N, Kdim), device=x.device, dtype=torch.float32)
+    C, PP = chw if chw is not None else (Kdim, 1)
+    _lib.check(L.c3d_linear_wgrad(_ptr(x), _ptr(dy), _ptr(dw), rows, Kdim, N, C, PP, int(bool(master_chw and chw is not None)),
+                                  _stream()))
     return dw

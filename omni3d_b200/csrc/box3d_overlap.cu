@@ -259,9 +259,21 @@ struct PairArgs {
   Ctrl* ctrl;
   unsigned long long* overflow;   // queue of pair indices
   unsigned overflow_cap;
+  // segmented (CSR) mode: `ngroups` independent (dt group x gt group) blocks in one launch — Omni3Deval.computeIoU's
+  // one call per (image, category) (omni3d_evaluation.py:1339-1343,1401-1412).  pair k belongs to group g with
+  // pair_off[g] <= k < pair_off[g+1]; inside it row-major over (dt_off[g+1]-dt_off[g]) x (gt_off[g+1]-gt_off[g]).
+  const long long* pair_off; const int* dt_off; const int* gt_off; int ngroups;
 };
 
 __device__ __forceinline__ void pair_to_ij(const PairArgs& A, long long k, int* i, int* j) {
+  if (A.ngroups > 0) {
+    int lo = 0, hi = A.ngroups;                              // last g with pair_off[g] <= k
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(A.pair_off + mid) <= k) lo = mid; else hi = mid; }
+    const int d0 = __ldg(A.dt_off + lo), g0 = __ldg(A.gt_off + lo), ng = __ldg(A.gt_off + lo + 1) - g0;
+    const long long r = k - __ldg(A.pair_off + lo);
+    *i = d0 + (int)(r / ng); *j = A.n1 + g0 + (int)(r % ng);
+    return;
+  }
   if (A.n2 == 0) { *i = (int)k; *j = (int)k + A.n1; }      // paired: box2 records follow box1's
   else { *i = (int)(k / A.n2); *j = A.n1 + (int)(k % A.n2); }
 }
@@ -348,10 +360,13 @@ struct WsLayout {
   size_t ctrl, rec, sph, flags, overflow, slabs, total;
 };
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static WsLayout ws_layout_pairs(int64_t n1, int64_t n2, int64_t npairs);
 static WsLayout ws_layout(int64_t n1, int64_t n2) {
+  return ws_layout_pairs(n1, n2 == 0 ? n1 : n2, n2 == 0 ? n1 : n1 * n2);
+}
+static WsLayout ws_layout_pairs(int64_t n1, int64_t m2, int64_t npairs) {
   WsLayout L;
-  int64_t nb = n1 + (n2 == 0 ? n1 : n2);
-  int64_t npairs = n2 == 0 ? n1 : n1 * n2;
+  int64_t nb = n1 + m2;
   size_t o = 0;
   L.ctrl = o; o = align_up(o + sizeof(Ctrl), 256);
   L.rec = o; o = align_up(o + (size_t)nb * kRecFloats * 4, 256);
@@ -363,12 +378,14 @@ static WsLayout ws_layout(int64_t n1, int64_t n2) {
   return L;
 }
 
+struct SegInfo { const int64_t* pair_off; const int32_t* dt_off; const int32_t* gt_off; int32_t ngroups; int64_t total_pairs; };
+
 static int32_t run_iou(const float* b1, int64_t n1, const float* b2, int64_t n2, bool paired,
                        bool do_check, float eps_c, float eps_nz, float* vol, float* iou, int32_t* nfaces,
-                       int32_t* n_bad, void* ws, size_t ws_bytes, cudaStream_t st) {
+                       int32_t* n_bad, void* ws, size_t ws_bytes, cudaStream_t st, const SegInfo* seg = nullptr) {
   if (n1 < 0 || n2 < 0) return set_error(C3D_EINVAL, "negative box count");
   int64_t m2 = paired ? n1 : n2;
-  int64_t npairs = paired ? n1 : n1 * n2;
+  int64_t npairs = seg ? seg->total_pairs : (paired ? n1 : n1 * n2);
   if (n1 + m2 > (int64_t)INT32_MAX / 2 || npairs > ((int64_t)1 << 36))
     return set_error(C3D_EINVAL, "problem too large (%lld x %lld)", (long long)n1, (long long)m2);
   if (npairs == 0 && !(do_check && n1 > 0)) {
@@ -377,7 +394,7 @@ static int32_t run_iou(const float* b1, int64_t n1, const float* b2, int64_t n2,
   }
   if (!b1 || (!b2 && !paired && n2 > 0) || (!iou && npairs > 0) || !ws)
     return set_error(C3D_EINVAL, "null pointer");
-  WsLayout L = ws_layout(n1, paired ? 0 : n2);
+  WsLayout L = seg ? ws_layout_pairs(n1, n2, npairs) : ws_layout(n1, paired ? 0 : n2);
   if (ws_bytes < L.total)
     return set_error(C3D_EWORKSPACE, "workspace %zu < required %zu", ws_bytes, L.total);
   if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return set_error(C3D_EINVAL, "workspace must be 256-byte aligned");
@@ -397,6 +414,11 @@ static int32_t run_iou(const float* b1, int64_t n1, const float* b2, int64_t n2,
     A.vol = vol; A.iou = iou; A.nfaces = nfaces; A.ctrl = ctrl;
     A.overflow = reinterpret_cast<unsigned long long*>(w + L.overflow);
     A.overflow_cap = (unsigned)(npairs < kMaxOverflowQueue ? npairs : kMaxOverflowQueue);
+    A.pair_off = nullptr; A.dt_off = nullptr; A.gt_off = nullptr; A.ngroups = 0;
+    if (seg) {
+      A.pair_off = reinterpret_cast<const long long*>(seg->pair_off); A.dt_off = seg->dt_off; A.gt_off = seg->gt_off;
+      A.ngroups = seg->ngroups;
+    }
     size_t smem = (size_t)kWarpsPerBlock * (128 + 4 * 9 * kCap) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -444,4 +466,25 @@ extern "C" int32_t c3d_box3d_overlap(const float* boxes_dt, int64_t n_dt, const 
   }
   return c3d::run_iou(boxes_dt, n_dt, boxes_gt, n_gt, false, true, eps_coplanar, eps_nonzero, nullptr, iou,
                       nullptr, n_bad, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t c3d_box3d_overlap_segmented_workspace_bytes(int64_t n_dt, int64_t n_gt, int64_t total_pairs) {
+  if (n_dt < 0 || n_gt < 0 || total_pairs < 0) return 0;
+  return c3d::ws_layout_pairs(n_dt, n_gt, total_pairs).total;
+}
+extern "C" int32_t c3d_box3d_overlap_segmented(const float* boxes_dt, int64_t n_dt, const float* boxes_gt, int64_t n_gt,
+                                               const int32_t* dt_off, const int32_t* gt_off, const int64_t* pair_off,
+                                               int32_t num_groups, int64_t total_pairs, float eps_coplanar,
+                                               float eps_nonzero, float* iou, int32_t* n_bad, void* workspace,
+                                               size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (num_groups < 0 || total_pairs < 0) return c3d::set_error(C3D_EINVAL, "segmented overlap: negative sizes");
+  if (n_dt == 0 || num_groups == 0) {
+    if (n_bad) cudaMemsetAsync(n_bad, 0, 2 * sizeof(int32_t), st);
+    return C3D_OK;
+  }
+  if (!dt_off || !gt_off || !pair_off) return c3d::set_error(C3D_EINVAL, "segmented overlap: null offsets");
+  c3d::SegInfo seg{pair_off, dt_off, gt_off, num_groups, total_pairs};
+  return c3d::run_iou(boxes_dt, n_dt, boxes_gt, n_gt, false, true, eps_coplanar, eps_nonzero, nullptr, iou, nullptr, n_bad,
+                      workspace, workspace_bytes, st, &seg);
 }

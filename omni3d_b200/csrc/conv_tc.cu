@@ -510,22 +510,28 @@ struct WgradKParams {
   int ca, a_chunks_max;                      // A boxes: width ca channels
   float* dw;                                 // fp32, accumulated with atomics
   int oihw;                                  // 0: dw is [Cout][KH][KW][Cin]; 1: [Cout][Cin][KH][KW] (master layout)
+  int lin;                                   // 1: fully-connected layer (c3d_linear_wgrad): x is (rows, KH*KW*Cin) with the
+                                             // features in (tap, ci) order — box b reads channels [b*cw, (b+1)*cw) with no
+                                             // spatial shift; KH/KW/Cin only drive the epilogue's master-layout index
 };
 
-template <int STAGES>
+// PIX = pixels (GEMM K) per pipeline stage: 128 px x 2 stages or 64 px x 4 stages (same 192 KB).  The deeper pipeline
+// hides the TMA latency (a 128-px stage is only ~0.5 us of MMA work, less than one L2/HBM round trip), the larger
+// box fits feature maps whose rows do not tile into 64-pixel boxes (20x20 -> 4x20).
+template <int STAGES, int PIX>
 struct WgradSmem {
-  static constexpr int kABytes = 2 * 128 * 128;            // up to two [128 px][64 ch] chunks (or narrower)
-  static constexpr int kBBytes = 128 * 256 * 2;            // 256 columns x 128 pixels
-  static constexpr int kStageBytes = kABytes + kBBytes;    // 96 KB
+  static constexpr int kABytes = PIX * 128 * 2;            // up to two [PIX px][64 ch] chunks (or narrower)
+  static constexpr int kBBytes = PIX * 256 * 2;            // 256 columns x PIX pixels
+  static constexpr int kStageBytes = kABytes + kBBytes;    // 96 KB (PIX 128) / 48 KB (PIX 64)
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;
 };
 
-template <int STAGES>
+template <int STAGES, int PIX>
 __global__ void __launch_bounds__(192)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                      const WgradKParams P) {
-  using S = WgradSmem<STAGES>;
+  using S = WgradSmem<STAGES, PIX>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
@@ -544,7 +550,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
   const int R = P.RH * P.RW;
   int a_chunks = (P.Cout - co0 + P.ca - 1) / P.ca;
   if (a_chunks > P.a_chunks_max) a_chunks = P.a_chunks_max;
-  const uint32_t a_box_bytes = (uint32_t)(128 * P.ca * 2), b_box_bytes = (uint32_t)(128 * P.cw * 2);
+  const uint32_t a_box_bytes = (uint32_t)(PIX * P.ca * 2), b_box_bytes = (uint32_t)(PIX * P.cw * 2);
 
   if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&tmap_dy); ptx::prefetch_tensormap(&tmap_x); }
   if (warp == 1 && lane == 0) {
@@ -576,8 +582,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
             const int box = box0 + b;
             const int tap = box / P.nci, chunk = box - tap * P.nci;
             const int kh = tap / P.KW, kw = tap - kh * P.KW;
-            ptx::tma_load_4d(sb + b * b_box_bytes, &tmap_x, &full_bar[stage], chunk * P.cw,
-                             wo0 * P.stride + kw - P.pad, ho0 * P.stride + kh - P.pad, img);
+            if (P.lin)
+              ptx::tma_load_4d(sb + b * b_box_bytes, &tmap_x, &full_bar[stage], box * P.cw, wo0, ho0, img);
+            else
+              ptx::tma_load_4d(sb + b * b_box_bytes, &tmap_x, &full_bar[stage], chunk * P.cw,
+                               wo0 * P.stride + kw - P.pad, ho0 * P.stride + kh - P.pad, img);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -645,13 +654,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
   }
 }
 
-// pixel box for wgrad: RH*RW must be a multiple of 16 (UMMA K) and <= 128
-static void pick_tile_k(int Ho, int Wo, int stride, int* RH, int* RW) {
+// pixel box for wgrad: RH*RW must be a multiple of 16 (UMMA K) and <= max_pix; returns the covered fraction
+static double pick_tile_k(int Ho, int Wo, int stride, int* RH, int* RW, int max_pix = 128) {
   double best = -1; int bth = 1, btw = 16;
-  for (int tw = 1; tw <= 128; ++tw) {
+  for (int tw = 1; tw <= max_pix; ++tw) {
     if (tw * stride > 256) break;
     if (tw > Wo && tw != 16) continue;
-    for (int th = 1; th * tw <= 128; ++th) {
+    for (int th = 1; th * tw <= max_pix; ++th) {
       if ((th * tw) % 16 != 0 || th * stride > 256) continue;
       long long tiles = (long long)((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
       double eff = (double)Ho * Wo / (double)(tiles * th * tw) * (th * tw >= 64 ? 1.0 : 0.9);
@@ -659,6 +668,7 @@ static void pick_tile_k(int Ho, int Wo, int stride, int* RH, int* RW) {
     }
   }
   *RH = bth; *RW = btw;
+  return best;
 }
 
 template <int BN, int BK, int ST>
@@ -810,11 +820,20 @@ extern "C" int32_t c3d_conv2d_wgrad_ex(const c3d_conv_desc* d, const void* x, co
 extern "C" int32_t c3d_conv2d_wgrad(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
   return c3d_conv2d_wgrad_ex(d, x, dy, dw, 0, stream);
 }
+// lin_c > 0: fully-connected layer — d describes the layer as a 1x1 conv over (1,1,rows) "pixels" with d->Cin input
+// features that are laid out as (lin_pp taps) x (lin_c channels); the epilogue then addresses dw as [Cout][lin_c][lin_pp]
+// when oihw (the nn.Linear master weight over a (C,P,P)-flattened input) or [Cout][lin_pp][lin_c] otherwise.
+static int32_t wgrad_impl(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, int32_t oihw, void* stream,
+                          int lin_c, int lin_pp);
 extern "C" int32_t c3d_conv2d_wgrad_ex(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, int32_t oihw,
                                        void* stream) {
+  return wgrad_impl(d, x, dy, dw, oihw, stream, 0, 0);
+}
+static int32_t wgrad_impl(const c3d_conv_desc* d, const void* x, const void* dy, float* dw, int32_t oihw, void* stream,
+                          int lin_c, int lin_pp) {
   if (!d || !x || !dy || !dw) return set_error(C3D_EINVAL, "wgrad: null pointer");
   const int Cin = d->Cin, Cout = d->Cout;
-  if (halo_wgrad_eligible(d)) return launch_halo_wgrad(d, x, dy, dw, oihw, static_cast<cudaStream_t>(stream));
+  if (!lin_c && halo_wgrad_eligible(d)) return launch_halo_wgrad(d, x, dy, dw, oihw, static_cast<cudaStream_t>(stream));
   if (Cin % 16 != 0 || Cout % 16 != 0) return set_error(C3D_EINVAL, "wgrad: channels must be multiples of 16");
   if (d->stride < 1 || d->stride > 2) return set_error(C3D_EINVAL, "wgrad: stride %d unsupported", d->stride);
   const int Ho = (d->H + 2 * d->pad - d->KH) / d->stride + 1;
@@ -824,12 +843,25 @@ extern "C" int32_t c3d_conv2d_wgrad_ex(const c3d_conv_desc* d, const void* x, co
   WgradKParams P;
   P.N = d->N; P.Ho = Ho; P.Wo = Wo; P.Cout = Cout; P.Cin = Cin;
   P.KH = d->KH; P.KW = d->KW; P.stride = d->stride; P.pad = d->pad;
-  pick_tile_k(Ho, Wo, d->stride, &P.RH, &P.RW);
+  P.lin = lin_c > 0;
+  if (P.lin) {
+    if (d->KH != 1 || d->KW != 1 || d->stride != 1 || d->pad != 0 || lin_c % 16 != 0 || (long long)lin_c * lin_pp != Cin)
+      return set_error(C3D_EINVAL, "linear wgrad: bad feature factorisation %d x %d != %d", lin_c, lin_pp, Cin);
+    P.Cin = lin_c; P.KH = lin_pp; P.KW = 1;      // epilogue index space: (tap = p, ci = c); the loader ignores kh / kw
+  }
+  // 64-pixel stages (4-deep pipeline) unless the map tiles clearly better into 128-pixel boxes
+  int rh64, rw64;
+  const double eff128 = pick_tile_k(Ho, Wo, d->stride, &P.RH, &P.RW, 128);
+  const double eff64 = pick_tile_k(Ho, Wo, d->stride, &rh64, &rw64, 64);
+  static const bool force128 = getenv("C3D_WGRAD_PIX128") != nullptr;
+  const bool pix64 = !force128 && eff64 >= 0.93 * eff128;
+  if (pix64) { P.RH = rh64; P.RW = rw64; }
   P.tiles_h = (Ho + P.RH - 1) / P.RH; P.tiles_w = (Wo + P.RW - 1) / P.RW;
   P.num_tiles = d->N * P.tiles_h * P.tiles_w;
-  const int taps = d->KH * d->KW;
-  P.cw = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
-  P.nci = Cin / P.cw;
+  const int taps = P.KH * P.KW;
+  const int Cin_e = P.Cin;                       // channels per tap in the epilogue's index space
+  P.cw = (Cin_e % 64 == 0) ? 64 : (Cin_e % 32 == 0 ? 32 : 16);
+  P.nci = Cin_e / P.cw;
   P.boxes_per_cta = 256 / P.cw;
   P.total_boxes = taps * P.nci;
   P.ca = (Cout % 64 == 0) ? 64 : (Cout % 32 == 0 ? 32 : 16);
@@ -839,7 +871,7 @@ extern "C" int32_t c3d_conv2d_wgrad_ex(const c3d_conv_desc* d, const void* x, co
   // split-K over pixels (1 CTA/SM): every split costs 128 x N fp32 atomics, so big weight tensors get exactly one
   // wave of CTAs (<= 148) while small ones (<= 64K elements: the pixel-heavy early layers) get ~4 waves for balance
   long long base = (long long)groups * co_tiles;
-  const long long welems = (long long)Cout * taps * Cin;
+  const long long welems = (long long)Cout * taps * Cin_e;
   int splits = welems <= 65536 ? (int)((4LL * kNumSMs + base - 1) / base) : (int)(kNumSMs / base);
   if (splits > P.num_tiles) splits = P.num_tiles;
   if (splits < 1) splits = 1;
@@ -872,14 +904,104 @@ extern "C" int32_t c3d_conv2d_wgrad_ex(const c3d_conv_desc* d, const void* x, co
   }
   dim3 grid((unsigned)splits, (unsigned)groups, (unsigned)co_tiles);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  using S = WgradSmem<2>;
-  auto kern = conv_wgrad_tc_kernel<2>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         WgradSmem<2, 128>::kTotal);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               WgradSmem<4, 64>::kTotal);
     if (e != cudaSuccess) return set_error(C3D_ECUDA, "wgrad smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  kern<<<grid, 192, S::kTotal, st>>>(mdy, mx, P);
+  if (pix64) conv_wgrad_tc_kernel<4, 64><<<grid, 192, WgradSmem<4, 64>::kTotal, st>>>(mdy, mx, P);
+  else conv_wgrad_tc_kernel<2, 128><<<grid, 192, WgradSmem<2, 128>::kTotal, st>>>(mdy, mx, P);
   return check_launch("conv_wgrad_tc_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fully-connected layers of the box head / cube head (detectron2 FastRCNNConvFCHead, configs/Base.yaml:67-70;
+// cubercnn/modeling/roi_heads/cube_head.py:63-73,108-144) on the SAME tcgen05 kernels: a linear layer over `rows`
+// feature vectors is the 1x1 convolution of a (1, 1, rows, K) "image" — 128-row M tiles, persistent CTAs, BLOCK_N 256,
+// bias + ReLU fused in the epilogue; the weight gradient is the split-K MN-major GEMM of conv_wgrad_tc_kernel.
+namespace c3d {
+// fp32 master (N, K = C*PP) whose input features are ordered (c, p) [nn.Linear over a (C,P,P)-flattened NCHW RoI] ->
+// bf16 (N, K') with K' ordered (p, c) [the NHWC-flattened RoI the ROIAlign kernel produces].  PP == 1: plain cast.
+__global__ void pack_linear_rows_kernel(const float* __restrict__ w, int N, int C, int PP, bf16* __restrict__ out) {
+  extern __shared__ float tile[];                       // [64 channels][PP]
+  const int n = blockIdx.y, c0 = blockIdx.x * 64;
+  const int nc = min(64, C - c0);
+  const float* src = w + ((size_t)n * C + c0) * PP;
+  for (int i = threadIdx.x; i < nc * PP; i += blockDim.x) tile[i] = src[i];
+  __syncthreads();
+  bf16* dst = out + (size_t)n * C * PP + c0;
+  for (int i = threadIdx.x; i < nc * PP; i += blockDim.x) {
+    const int p = i / nc, c = i - p * nc;
+    dst[(size_t)p * C + c] = __float2bfloat16(tile[c * PP + p]);
+  }
+}
+// bf16 (R, Cc) -> bf16 (Cc, R)
+__global__ void transpose_bf16_kernel(const bf16* __restrict__ in, int R, int Cc, bf16* __restrict__ out) {
+  __shared__ bf16 t[64][66];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    const int r = r0 + i;
+    for (int j = threadIdx.x; j < 64; j += blockDim.x)
+      if (r < R && c0 + j < Cc) t[i][j] = in[(size_t)r * Cc + c0 + j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    const int c = c0 + i;
+    for (int j = threadIdx.x; j < 64; j += blockDim.x)
+      if (c < Cc && r0 + j < R) out[(size_t)c * R + r0 + j] = t[j][i];
+  }
+}
+static void linear_desc(c3d_conv_desc* d, int64_t rows, int K, int N, int relu, int out_fp32) {
+  memset(d, 0, sizeof(*d));
+  d->N = 1; d->H = 1; d->W = (int32_t)rows; d->Cin = K; d->Cout = N; d->KH = 1; d->KW = 1; d->stride = 1; d->pad = 0;
+  d->relu = relu; d->out_fp32 = out_fp32;
+}
+}  // namespace c3d
+
+extern "C" int32_t c3d_pack_linear_weight(const float* w, int32_t N, int32_t K, int32_t C, int32_t PP, void* w_bf16,
+                                          void* wt_bf16, void* stream) {
+  if (!w || !w_bf16 || N <= 0 || K <= 0) return set_error(C3D_EINVAL, "pack_linear_weight: bad args");
+  if (C <= 0 || PP <= 0) { C = K; PP = 1; }
+  if ((long long)C * PP != K || PP > 256) return set_error(C3D_EINVAL, "pack_linear_weight: C*PP != K");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 g((C + 63) / 64, N);
+  pack_linear_rows_kernel<<<g, 256, 64 * PP * sizeof(float), st>>>(w, N, C, PP, (bf16*)w_bf16);
+  if (wt_bf16) {
+    dim3 gt((K + 63) / 64, (N + 63) / 64);
+    transpose_bf16_kernel<<<gt, dim3(32, 8), 0, st>>>((const bf16*)w_bf16, N, K, (bf16*)wt_bf16);
+  }
+  return check_launch("pack_linear_weight");
+}
+
+extern "C" int32_t c3d_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t rows, int32_t K,
+                                  int32_t N, int32_t relu, int32_t out_fp32, void* stream) {
+  if (rows <= 0) return C3D_OK;
+  if (rows > 0x7fffffffLL) return set_error(C3D_EINVAL, "linear: too many rows");
+  c3d_conv_desc d;
+  linear_desc(&d, rows, K, N, relu, out_fp32);
+  return c3d_conv2d_fwd(&d, x, w, bias, nullptr, y, nullptr, stream);
+}
+
+extern "C" int32_t c3d_linear_dgrad(const void* dy, const void* wt, void* dx, int64_t rows, int32_t N, int32_t K,
+                                    void* stream) {
+  if (rows <= 0) return C3D_OK;
+  if (rows > 0x7fffffffLL) return set_error(C3D_EINVAL, "linear: too many rows");
+  c3d_conv_desc d;
+  linear_desc(&d, rows, N, K, 0, 0);           // dx (rows, K) = dy (rows, N) . W  ==  1x1 conv with weight W^T (K, N)
+  return c3d_conv2d_fwd(&d, dy, wt, nullptr, nullptr, dx, nullptr, stream);
+}
+
+extern "C" int32_t c3d_linear_wgrad(const void* x, const void* dy, float* dw, int64_t rows, int32_t K, int32_t N,
+                                    int32_t C, int32_t PP, int32_t master_chw, void* stream) {
+  if (rows <= 0) return C3D_OK;
+  if (rows > 0x7fffffffLL) return set_error(C3D_EINVAL, "linear: too many rows");
+  if (C <= 0 || PP <= 0) { C = K; PP = 1; }
+  c3d_conv_desc d;
+  linear_desc(&d, rows, K, N, 0, 0);
+  return wgrad_impl(&d, x, dy, dw, master_chw ? 1 : 0, stream, C, PP);
 }

@@ -256,14 +256,14 @@ namespace c3d {
 
 __global__ void rpn_decode_kernel(const long long* __restrict__ topk_idx, const float* __restrict__ topk_score,
                                   const float4* __restrict__ deltas, const float4* __restrict__ anchors,
-                                  const float* __restrict__ hw, int B, int K, long long A, float wx, float wy, float ww,
+                                  const float* __restrict__ hw, int B, int K, long long in_stride, long long A, float wx, float wy, float ww,
                                   float wh, float scale_clamp, float min_size, float level, int col0, int Ktot,
                                   float4* __restrict__ boxes, float* __restrict__ key, float* __restrict__ lvl,
                                   int* __restrict__ nvalid, int* __restrict__ maxc_bits) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * K) return;
   const int b = i / K, k = i - b * K;
-  const long long a = topk_idx[i];
+  const long long a = topk_idx[(long long)b * in_stride + k];
   const float4 d = deltas[(size_t)b * A + a];
   const float4 an = anchors[a];
   const float w = __fsub_rn(an.z, an.x), h = __fsub_rn(an.w, an.y);
@@ -276,7 +276,7 @@ __global__ void rpn_decode_kernel(const long long* __restrict__ topk_idx, const 
   const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
   float x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw)), y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
   float x2 = __fadd_rn(pcx, __fmul_rn(0.5f, pw)), y2 = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
-  const float s = topk_score[i];
+  const float s = topk_score[(long long)b * in_stride + k];
   const bool finite = isfinite(x1) && isfinite(y1) && isfinite(x2) && isfinite(y2) && isfinite(s);
   const float H = hw[2 * b], W = hw[2 * b + 1];
   // torch.minimum(boxes.clamp(min=0), lim): NaN propagates through both (irrelevant: filtered by `finite`)
@@ -295,7 +295,7 @@ __global__ void rpn_decode_kernel(const long long* __restrict__ topk_idx, const 
 
 }  // namespace c3d
 
-extern "C" int32_t c3d_rpn_decode_level(const int64_t* topk_idx, const float* topk_score, const float* deltas,
+extern "C" int32_t c3d_rpn_decode_level(const int64_t* topk_idx, const float* topk_score, int64_t in_stride, const float* deltas,
                                         const float* anchors, const float* image_hw, int32_t B, int32_t K, int64_t A,
                                         const float* weights4_host, float scale_clamp, float min_size, int32_t level,
                                         int32_t col0, int32_t Ktot, float* boxes, float* key, float* lvl, int32_t* nvalid,
@@ -306,7 +306,7 @@ extern "C" int32_t c3d_rpn_decode_level(const int64_t* topk_idx, const float* to
   const int total = B * K;
   rpn_decode_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(topk_idx), topk_score, reinterpret_cast<const float4*>(deltas),
-      reinterpret_cast<const float4*>(anchors), image_hw, B, K, A, weights4_host[0], weights4_host[1], weights4_host[2],
+      reinterpret_cast<const float4*>(anchors), image_hw, B, K, in_stride > 0 ? in_stride : K, A, weights4_host[0], weights4_host[1], weights4_host[2],
       weights4_host[3], scale_clamp, min_size, (float)level, col0, Ktot, reinterpret_cast<float4*>(boxes), key, lvl, nvalid,
       reinterpret_cast<int*>(maxc));
   return check_launch("rpn_decode");

@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from ..nnfunc import ROIAlign
+from ..nnfunc import LinearAct, ROIAlign
 from . import geometry as G
 from .registry import ROI_CUBE_HEAD_REGISTRY, ROI_HEADS_REGISTRY
 from .rpn import apply_deltas, get_deltas, gumbel_topk_sample, pairwise_ioa, pairwise_iou
@@ -27,15 +27,32 @@ def assign_levels(boxes, min_level=2, max_level=6):
     return lvl.clamp(min=min_level, max=max_level) - min_level
 
 
-def linear_bf16(x, lin, relu=False, weight=None):
-    w = lin.weight if weight is None else weight
-    y = F.linear(x, w.to(torch.bfloat16), lin.bias.to(torch.bfloat16))
-    return F.relu(y) if relu else y
+def fc(x, lin, relu=False, chw=None, out_fp32=False):
+    """[relu](x W^T + b) on the tcgen05 GEMM (c3d_linear_*).  chw = (C, P*P): W is the reference's weight over a
+    (C,P,P)-flattened RoI while x is the (P,P,C)-flattened NHWC RoI the ROIAlign kernel emits (features re-ordered
+    when the weight is packed to bf16; the weight gradient is written back in the master's order)."""
+    return LinearAct.apply(x, lin.weight, lin.bias, relu, out_fp32, chw)
 
 
-def chw_to_hwc_weight(w, C, P):
-    """fc weight over a (C,P,P)-flattened input -> the same weight over an (P,P,C)-flattened (NHWC) input."""
-    return w.view(w.shape[0], C, P, P).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+_zero_pad = {}
+
+
+def fused_predictors(h, lins, n_pad):
+    """several small nn.Linear predictors over the same features as ONE zero-padded GEMM -> list of fp32 outputs."""
+    widths = [l.weight.shape[0] for l in lins]
+    pad = n_pad - sum(widths)
+    key = (pad, h.shape[1], h.device)
+    z = _zero_pad.get(key)
+    if z is None:
+        z = _zero_pad[key] = (torch.zeros((pad, h.shape[1]), device=h.device), torch.zeros(pad, device=h.device))
+    w = torch.cat([l.weight for l in lins] + [z[0]], 0)
+    b = torch.cat([l.bias for l in lins] + [z[1]], 0)
+    y = LinearAct.apply(h, w, b, False, True, None)
+    out, o = [], 0
+    for n in widths:
+        out.append(y[:, o:o + n])
+        o += n
+    return out
 
 
 class FastRCNNConvFCHead(nn.Sequential):
@@ -137,6 +154,7 @@ class ROIHeads3D(nn.Module):
         self.generator = None
         self.stats = {}
         self.fused_cube = True        # c3d_cube_loss_fwd/bwd; False = the batched torch fp32 formulation below
+        self.fused_sampling = True    # c3d_label_sample_proposals; False = the batched torch formulation below
 
     # -- proposal labelling / sampling (roi_heads.py:826-929) -----------------------------------------
     @torch.no_grad()
@@ -167,6 +185,19 @@ class ROIHeads3D(nn.Module):
             return gt["sampled"]
         B, P, _ = prop_boxes.shape
         dev = prop_boxes.device
+        S, K = self.batch_size_per_image, self.num_classes
+        G = gt["boxes"].shape[1]
+        if (dev.type == "cuda" and self.fused_sampling and self.generator is None and G <= 256
+                and P + (G if self.append_gt else 0) <= 2048):
+            # one launch: matcher + ignore rule + IoU-weighted sampling + fg-first compaction + GT gather
+            from .. import kernels as Kx
+            out = Kx.label_sample_proposals(prop_boxes, prop_count, gt, K, S, int(S * self.positive_fraction), self.iou_thresh,
+                                            self.ignore_thresh, append_gt=self.append_gt)
+            st = out.pop("stats")
+            self.stats["roi_head/num_fg_samples"] = st[0] / B
+            self.stats["roi_head/num_bg_samples"] = st[1] / B
+            out["fcap"] = int(S * self.positive_fraction)
+            return out
         pvalid = torch.arange(P, device=dev)[None] < prop_count[:, None]
         boxes = prop_boxes
         if self.append_gt:
@@ -217,13 +248,13 @@ class ROIHeads3D(nn.Module):
 
     def box_branch(self, x):
         C, P = self.in_channels, self.pooled
-        h = linear_bf16(x, self.box_head.fc1, relu=True, weight=chw_to_hwc_weight(self.box_head.fc1.weight, C, P))
+        h = fc(x, self.box_head.fc1, relu=True, chw=(C, P * P))
         k = 2
         while hasattr(self.box_head, "fc%d" % k):
-            h = linear_bf16(h, getattr(self.box_head, "fc%d" % k), relu=True)
+            h = fc(h, getattr(self.box_head, "fc%d" % k), relu=True)
             k += 1
-        scores = linear_bf16(h, self.box_predictor.cls_score).float()
-        deltas = linear_bf16(h, self.box_predictor.bbox_pred).float()
+        n = self.box_predictor.cls_score.weight.shape[0] + self.box_predictor.bbox_pred.weight.shape[0]
+        scores, deltas = fused_predictors(h, [self.box_predictor.cls_score, self.box_predictor.bbox_pred], -(-n // 256) * 256)
         return scores, deltas
 
     def box_losses(self, scores, deltas, smp):
@@ -251,18 +282,20 @@ class ROIHeads3D(nn.Module):
         """x (n, 7*7*C) bf16, classes (n,) -> per-class gathered raw head outputs (fp32)."""
         ch, C, P, K = self.cube_head, self.in_channels, self.pooled, self.num_classes
         fg = ch.feature_generator
-        h = linear_bf16(x, fg.fc1, relu=True, weight=chw_to_hwc_weight(fg.fc1.weight, C, P))
+        h = fc(x, fg.fc1, relu=True, chw=(C, P * P))
         k = 2
         while hasattr(fg, "fc%d" % k):
-            h = linear_bf16(h, getattr(fg, "fc%d" % k), relu=True)
+            h = fc(h, getattr(fg, "fc%d" % k), relu=True)
             k += 1
         n = x.shape[0]
         c = classes.clamp(0, K - 1)
-        pick = lambda lin, m: torch.gather(linear_bf16(h, lin).float().view(n, K, m), 1,
-                                           c[:, None, None].expand(-1, 1, m)).squeeze(1)
-        ur = pick(ch.bbox_3D_uncertainty, 1).squeeze(1)
-        return dict(deltas=pick(ch.bbox_3D_center_deltas, 2), dims=pick(ch.bbox_3D_dims, 3), pose6=pick(ch.bbox_3D_pose, 6),
-                    z=pick(ch.bbox_3D_center_depth, 1).squeeze(1), uncert=ur.clip(0.01), uncert_raw=ur)
+        heads = [ch.bbox_3D_center_deltas, ch.bbox_3D_dims, ch.bbox_3D_pose, ch.bbox_3D_center_depth, ch.bbox_3D_uncertainty]
+        tot = sum(l.weight.shape[0] for l in heads)
+        outs = fused_predictors(h, heads, -(-tot // 256) * 256)          # one GEMM for the five K-way predictors
+        pick = lambda o, m: torch.gather(o.reshape(n, K, m), 1, c[:, None, None].expand(-1, 1, m)).squeeze(1)
+        ur = pick(outs[4], 1).squeeze(1)
+        return dict(deltas=pick(outs[0], 2), dims=pick(outs[1], 3), pose6=pick(outs[2], 6),
+                    z=pick(outs[3], 1).squeeze(1), uncert=ur.clip(0.01), uncert_raw=ur)
 
     def decode(self, raw, boxes, classes, Kb, v2r):
         """roi_heads.py:409-525: 2D centre, dims (exp * prior), egocentric pose, metric depth."""

@@ -185,6 +185,8 @@ class RPNWithIgnore(nn.Module):
         self.nms_trick_max_numel = 20000
         self.fused_loss = True                 # c3d_rpn_loss_fwd/bwd instead of the (B,A)-shaped torch formulation
         self.fused_decode = True               # c3d_rpn_decode_level instead of ~35 torch ops per level
+        self.fused_topk = True                 # c3d_topk_segments instead of ATen topk per level + radix sort
+        self.fused_sampling = True             # c3d_anchor_sample_* instead of the torch Gumbel top-k formulation
         self.stats = {}
 
     # -- labels -----------------------------------------------------------------------------------
@@ -224,6 +226,11 @@ class RPNWithIgnore(nn.Module):
         """gt_classes (B,G) (-1 = ignore region), gt_present (B,G) bool (non-padding)."""
         valid = gt_present & (gt_classes >= 0)
         ign = gt_present & (gt_classes < 0)
+        if anchors.is_cuda and self.fused_sampling and self.generator is None:
+            idx, miou, lab, ioa, best_idx = Kx.anchor_match(anchors, gt_boxes, valid, ign, self.iou_thresholds[-1])
+            out = Kx.anchor_sample(lab, miou, ioa, best_idx, valid, ign, self.batch_size_per_image,
+                                   int(self.batch_size_per_image * self.positive_fraction), self.ignore_thresh)
+            return out, idx
         idx, miou, lab, best, ioa = self.match_anchors(anchors, gt_boxes, valid, ign)
         B, A = lab.shape
         n_total = self.batch_size_per_image
@@ -312,12 +319,21 @@ class RPNWithIgnore(nn.Module):
             maxc = torch.zeros((B,), device=dev)
             hw = hw.contiguous().float()
             col = 0
+            if self.fused_topk:       # all levels' pre-NMS top-k in ONE launch (c3d_topk_segments), then the score sort
+                tv, ti = Kx.topk_segments([(lg if lg.stride(1) == 1 else lg.contiguous(), k)
+                                           for lg, k in zip(logits_per_level, ks)], want_idx64=True)
             for li, (anc, lg, dl, k) in enumerate(zip(anchors_per_level, logits_per_level, deltas_per_level, ks)):
-                s, i = lg.topk(k, dim=1)
+                if self.fused_topk:
+                    s, i = tv[:, col:col + k], ti[:, col:col + k]
+                else:
+                    s, i = lg.topk(k, dim=1)
                 Kx.rpn_decode_level(i, s, dl.contiguous(), anc, hw, self.weights, SCALE_CLAMP, self.min_box_size, li, col,
                                     boxes, key, lvl, nvalid, maxc)
                 col += k
-            key, order = key.sort(dim=1, descending=True)
+            if self.fused_topk and Ktot <= 8192:
+                key, order = Kx.topk_segments([(key, Ktot)], want_idx64=True)
+            else:
+                key, order = key.sort(dim=1, descending=True)
             boxes = torch.gather(boxes, 1, order[:, :, None].expand(-1, -1, 4))
             lvl = torch.gather(lvl, 1, order)
         else:

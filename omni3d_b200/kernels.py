@@ -15,6 +15,19 @@ class RoiLevels(ctypes.Structure):
                 ("num_levels", i32), ("num_images", i32)]
 
 
+class TopkSeg(ctypes.Structure):
+    _fields_ = [("vals", vp), ("row_stride", i64), ("n", i32), ("k", i32), ("out_col", i32)]
+
+
+class LabelSampleArgs(ctypes.Structure):
+    _fields_ = [("prop_boxes", vp), ("prop_count", vp), ("gt_boxes", vp), ("gt_classes", vp), ("gt_present", vp),
+                ("gt_boxes3D", vp), ("gt_poses", vp), ("B", i32), ("P", i32), ("G", i32), ("K", i32), ("S", i32),
+                ("Fcap", i32), ("append_gt", i32), ("iou_thresh", f32), ("ignore_thresh", f32), ("rng", vp),
+                ("bump_rng", i32), ("matched_idx", vp), ("matched_iou", vp), ("labels", vp), ("s_boxes", vp),
+                ("s_valid", vp), ("s_classes", vp), ("s_gt_boxes", vp), ("s_gt_boxes3D", vp), ("s_gt_poses", vp),
+                ("s_index", vp), ("stats", vp)]
+
+
 def _bind():
     global _bound
     L = _lib.lib()
@@ -49,10 +62,14 @@ def _bind():
     sig["c3d_nms_batched_grouped"] = [vp, vp, vp, vp, i32, i32, i32, f32, i32, i32, i32, vp, vp, vp, ctypes.c_size_t, vp]
     sig["c3d_rpn_loss_fwd"] = [vp, vp, vp, vp, vp, vp, i32, i64, i32, ctypes.POINTER(f32), vp, vp]
     sig["c3d_rpn_loss_bwd"] = [vp, vp, vp, vp, vp, vp, i32, i64, i32, ctypes.POINTER(f32), vp, vp, vp, vp, vp]
-    sig["c3d_rpn_decode_level"] = [vp, vp, vp, vp, vp, i32, i32, i64, ctypes.POINTER(f32), f32, f32, i32, i32, i32, vp, vp, vp,
+    sig["c3d_rpn_decode_level"] = [vp, vp, i64, vp, vp, vp, i32, i32, i64, ctypes.POINTER(f32), f32, f32, i32, i32, i32, vp, vp, vp,
                                    vp, vp, vp]
     sig["c3d_anchor_match"] = [vp, i64, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp]
     sig["c3d_preprocess_image_u8"] = [vp, i32, i32, vp, i32, i32, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), vp]
+    sig["c3d_topk_segments"] = [ctypes.POINTER(TopkSeg), i32, i32, i32, vp, vp, vp, vp, vp]
+    sig["c3d_label_sample_proposals"] = [ctypes.POINTER(LabelSampleArgs), vp]
+    sig["c3d_anchor_sample_keys"] = [vp, vp, i32, i64, vp, vp, vp, vp]
+    sig["c3d_anchor_sample_finish"] = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, i32, i32, f32, vp, vp, vp]
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.restype = i32
@@ -284,7 +301,8 @@ def rpn_decode_level(topk_idx, topk_score, deltas, anchors, image_hw, weights, s
     L = _bind()
     B, K = topk_idx.shape
     w = (f32 * 4)(*[float(v) for v in weights])
-    _lib.check(L.c3d_rpn_decode_level(_p(topk_idx), _p(topk_score), _p(deltas), _p(anchors), _p(image_hw), B, K,
+    assert topk_idx.dtype == torch.int64 and topk_idx.stride(1) == 1 and topk_score.stride() == topk_idx.stride()
+    _lib.check(L.c3d_rpn_decode_level(_p(topk_idx), _p(topk_score), topk_idx.stride(0), _p(deltas), _p(anchors), _p(image_hw), B, K,
                                       deltas.shape[1], w, float(scale_clamp), float(min_size), int(level), int(col0),
                                       boxes.shape[1], _p(boxes), _p(key), _p(lvl), _p(nvalid), _p(maxc), _st()))
 
@@ -357,3 +375,117 @@ def cube_loss_bwd(raw, aux, dout):
     draw = torch.empty((n, 13), device=raw.device, dtype=torch.float32)
     _lib.check(L.c3d_cube_loss_bwd(_p(raw), _p(aux), _p(dout), n, _p(draw), _st()))
     return draw
+
+
+# ---- selection / sampling (select_ops.cu) ----------------------------------------------------------------------------
+_rng_state = {}
+
+
+def rng_state(device, seed=None):
+    """{seed, step counter} (2 x int64) on the device: the Philox stream of the sampling kernels.  The counter is advanced
+    BY the kernels, so a CUDA-graph replay draws fresh noise every step without any host write."""
+    key = (device.type, device.index)
+    st = _rng_state.get(key)
+    if st is None or seed is not None:
+        if seed is None:
+            seed = torch.initial_seed()
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    seed += 7919 * dist.get_rank()
+            except Exception:      # noqa: BLE001
+                pass
+        st = _rng_state[key] = torch.tensor([seed & 0x7fffffffffffffff, 0], dtype=torch.int64, device=device)
+    return st
+
+
+def topk_segments(segs, want_idx64=False, want_counts=False):
+    """segs: list of (vals (B,n) fp32 [row-strided ok], k).  -> vals (B, sum k) sorted descending inside every segment,
+    idx (B, sum k) int32 or int64 (index inside the segment's row) [, counts (B, nseg) of values > -inf]."""
+    L = _bind()
+    B = segs[0][0].shape[0]
+    dev = segs[0][0].device
+    arr = (TopkSeg * len(segs))()
+    col = 0
+    keep = []
+    for i, (v, k) in enumerate(segs):
+        assert v.dtype == torch.float32 and v.dim() == 2 and v.stride(1) == 1 and v.shape[0] == B
+        keep.append(v)
+        arr[i].vals, arr[i].row_stride, arr[i].n, arr[i].k, arr[i].out_col = v.data_ptr(), v.stride(0), v.shape[1], int(k), col
+        col += int(k)
+    out_v = torch.empty((B, col), dtype=torch.float32, device=dev)
+    out_i = torch.empty((B, col), dtype=torch.int64 if want_idx64 else torch.int32, device=dev)
+    cnt = torch.empty((B, len(segs)), dtype=torch.int32, device=dev) if want_counts else None
+    _lib.check(L.c3d_topk_segments(arr, len(segs), B, col, _p(out_v), None if want_idx64 else _p(out_i),
+                                   _p(out_i) if want_idx64 else None, _p(cnt), _st()))
+    return (out_v, out_i, cnt) if want_counts else (out_v, out_i)
+
+
+def label_sample_proposals(prop_boxes, prop_count, gt, K, S, Fcap, iou_thresh, ignore_thresh, append_gt=True, rng=None,
+                           bump_rng=True, want_prelabels=False, want_index=False):
+    """-> dict(boxes (B,S,4), valid (B,S) bool, classes (B,S) int64, gt_boxes, gt_boxes3D (B,S,9), gt_poses (B,S,3,3),
+    stats (2,) [, index (B,S)] [, pre = (matched_idx, matched_iou, labels) each (B,P+G)])."""
+    L = _bind()
+    B, P, _ = prop_boxes.shape
+    G = gt["boxes"].shape[1]
+    dev = prop_boxes.device
+    f = lambda t: t.contiguous().float()
+    pb, gb, g3, gp = f(prop_boxes), f(gt["boxes"]), f(gt["boxes3D"][..., :9]), f(gt["poses"].reshape(B, G, 9))
+    pc = prop_count.to(torch.int32).contiguous()
+    gc = gt["classes"].to(torch.int64).contiguous()
+    pres = gt["present"].to(torch.uint8).contiguous()
+    n = P + (G if append_gt else 0)
+    out = dict(boxes=torch.empty((B, S, 4), device=dev), valid=torch.empty((B, S), dtype=torch.uint8, device=dev),
+               classes=torch.empty((B, S), dtype=torch.int64, device=dev), gt_boxes=torch.empty((B, S, 4), device=dev),
+               gt_boxes3D=torch.empty((B, S, 9), device=dev), gt_poses=torch.empty((B, S, 3, 3), device=dev),
+               stats=torch.zeros(2, device=dev))
+    pre = None
+    if want_prelabels:
+        pre = (torch.empty((B, n), dtype=torch.int64, device=dev), torch.empty((B, n), device=dev),
+               torch.empty((B, n), dtype=torch.int64, device=dev))
+    idx = torch.empty((B, S), dtype=torch.int64, device=dev) if want_index else None
+    if rng is None:
+        rng = rng_state(dev)
+    a = LabelSampleArgs()
+    a.prop_boxes, a.prop_count, a.gt_boxes, a.gt_classes, a.gt_present = pb.data_ptr(), pc.data_ptr(), gb.data_ptr(), gc.data_ptr(), pres.data_ptr()
+    a.gt_boxes3D, a.gt_poses = g3.data_ptr(), gp.data_ptr()
+    a.B, a.P, a.G, a.K, a.S, a.Fcap, a.append_gt = B, P, G, int(K), int(S), int(Fcap), int(bool(append_gt))
+    a.iou_thresh, a.ignore_thresh = float(iou_thresh), float(ignore_thresh)
+    a.rng, a.bump_rng = rng.data_ptr(), int(bool(bump_rng))
+    if pre is not None:
+        a.matched_idx, a.matched_iou, a.labels = pre[0].data_ptr(), pre[1].data_ptr(), pre[2].data_ptr()
+    a.s_boxes, a.s_valid, a.s_classes = out["boxes"].data_ptr(), out["valid"].data_ptr(), out["classes"].data_ptr()
+    a.s_gt_boxes, a.s_gt_boxes3D, a.s_gt_poses = out["gt_boxes"].data_ptr(), out["gt_boxes3D"].data_ptr(), out["gt_poses"].data_ptr()
+    a.s_index = idx.data_ptr() if idx is not None else None
+    a.stats = out["stats"].data_ptr()
+    _lib.check(L.c3d_label_sample_proposals(ctypes.byref(a), _st()), launches=2 if bump_rng else 1)
+    out["valid"] = out["valid"].view(torch.bool)
+    if idx is not None:
+        out["index"] = idx
+    if pre is not None:
+        out["pre"] = pre
+    return out
+
+
+def anchor_sample(labels01, matched_iou, max_ioa, best_idx, gt_valid, gt_ign, n_total, cap_pos, ignore_thresh, rng=None,
+                  bump_rng=True):
+    """labels01 (B,A) int8 matcher labels {0,1} -> sampled labels (B,A) int8 in {-1,0,1} (rpn.py:62-105)."""
+    L = _bind()
+    B, A = labels01.shape
+    dev = labels01.device
+    G = gt_valid.shape[1]
+    if rng is None:
+        rng = rng_state(dev)
+    keys = torch.empty((B, 2, A), dtype=torch.float32, device=dev)
+    counts = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    lab = labels01.contiguous()
+    _lib.check(L.c3d_anchor_sample_keys(_p(lab), _p(matched_iou.contiguous()), B, A, _p(rng), _p(keys), _p(counts), _st()))
+    k = int(max(cap_pos, n_total))
+    kv = keys.view(B, 2 * A)
+    _, idx = topk_segments([(kv[:, :A], k), (kv[:, A:], k)])
+    out = torch.empty((B, A), dtype=torch.int8, device=dev)
+    v8, i8 = gt_valid.to(torch.uint8).contiguous(), gt_ign.to(torch.uint8).contiguous()
+    _lib.check(L.c3d_anchor_sample_finish(_p(lab), _p(max_ioa.contiguous()), _p(idx), _p(counts), _p(best_idx.contiguous()),
+                                          _p(v8), _p(i8), B, G, A, k, int(cap_pos), int(n_total), float(ignore_thresh),
+                                          _p(out), _p(rng) if bump_rng else None, _st()))
+    return out

@@ -24,6 +24,7 @@ def invalidate_packed():
     _epoch += 1
     _pack_cache.clear()
     _phase_cache.clear()
+    _lin_cache.clear()
 
 
 def _cache_key(w):
@@ -179,6 +180,54 @@ class ConvBias(torch.autograd.Function):
         dx = _dgrad(dzb, w, stride, pad, x.shape[1:3]) if ctx.needs_input_grad[0] else None
         dw = _wgrad_to_master(x, dzb, w, stride, pad) if ctx.needs_input_grad[1] else None
         return dx, dw, dbias if ret_b else None, dadd, None, None, None, None
+
+
+_lin_cache = {}
+
+
+def _packed_linear(w, chw):
+    """bf16 (N,K') forward operand and its (K',N) transpose for the data gradient, cached like the conv packs."""
+    key, ver = _cache_key(w)
+    hit = _lin_cache.get(key) if key is not None else None
+    if hit is None or hit[0] != (ver, chw) or hit[3]() is not w:
+        f, t = K.pack_linear_weight(w, chw)
+        hit = ((ver, chw), f, t, weakref.ref(w) if key is not None else None)
+        if key is not None:
+            _lin_cache[key] = hit
+    return hit[1], hit[2]
+
+
+class LinearAct(torch.autograd.Function):
+    """y = [relu](x W^T + b) on the tcgen05 GEMM (c3d_linear_fwd / _dgrad / _wgrad) — the FC layers of
+    FastRCNNConvFCHead / FastRCNNOutputLayers / CubeHead (Base.yaml:67-70, cube_head.py:63-73,108-144).
+    x (rows, K) bf16; W fp32 master (N, K) in the reference's layout; chw = (C, PP) when the master's input features are
+    ordered (c, p) while x is the NHWC-flattened RoI (p, c)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, relu, out_fp32, chw):
+        x = x.contiguous()
+        wp, wt = _packed_linear(w, chw)
+        b = bias.detach().float().contiguous() if bias is not None else None
+        y = K.linear_fwd(x, wp, b, relu, out_fp32)
+        ctx.save_for_backward(x, w, bias, y if relu else None, wt)
+        ctx.cfg = (relu, chw)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, bias, y, wt = ctx.saved_tensors
+        relu, chw = ctx.cfg
+        dbias, ret_b = _grad_slot(bias) if bias is not None and ctx.needs_input_grad[2] else (None, False)
+        dz = Kx.bias_act_bwd(dy, y, relu, dbias)                       # bf16 (rows, N); dbias += column sums
+        dx = K.linear_dgrad(dz, wt) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            g = w.grad if w.is_leaf else None
+            if g is not None and g.dtype == torch.float32 and g.shape == w.shape and g.is_contiguous():
+                K.linear_wgrad(x, dz, dw=g, chw=chw)        # straight into the trainer's gradient arena (master layout)
+            else:
+                dw = K.linear_wgrad(x, dz, chw=chw)
+        return dx, dw, dbias if ret_b else None, None, None, None
 
 
 class MaxPool2(torch.autograd.Function):

@@ -37,5 +37,5 @@ def R_from_allocentric(K, R_view, u, v):
     valid = angle > 0
     M = axis_angle_to_matrix(angle.unsqueeze(1) * axis / norms.unsqueeze(1))
     R = R_view.clone()
-    R[valid] = torch.bmm(M[valid], R_view[valid])
+    R[valid] = torch.bmm(M[valid], R_view[valid]).to(R.dtype)      # (.to: no-op in fp32; keeps autocast runs legal)
     return R

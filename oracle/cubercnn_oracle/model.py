@@ -73,11 +73,11 @@ class RPNWithIgnore(RPN):
             gt_i, ign_i = x.gt_boxes[x.gt_classes >= 0], x.gt_boxes[x.gt_classes < 0]
             mqm = pairwise_iou(gt_i, anchors)
             matched_idxs, lab = self.anchor_matcher(mqm)
-            matched_ious = mqm[matched_idxs, torch.arange(mqm.shape[1])]
+            matched_ious = mqm[matched_idxs, torch.arange(mqm.shape[1], device=mqm.device)]
             # the best anchor of every GT is forced positive if the matcher labelled it positive (:71-84)
             best = mqm.max(dim=1)[1] if mqm.shape[0] else torch.zeros(0, dtype=torch.long)
             best = torch.tensor(sorted(set(best.tolist()) & set((lab == 1).nonzero().squeeze(1).tolist())),
-                                dtype=torch.long)
+                                dtype=torch.long, device=lab.device)
             pos, neg = iou_weighted_subsample(lab, self.batch_size_per_image, self.positive_fraction, 0, matched_ious)
             lab.fill_(-1)
             lab.scatter_(0, pos, 1)
@@ -249,7 +249,7 @@ class ROIHeads3D(StandardROIHeads):
                 if bg.numel() > 1:
                     ioa = pairwise_ioa(tign.gt_boxes, prop.proposal_boxes[bg])
                     mlab[bg[ioa.max(0)[0] >= self.ignore_thresh]] = -1
-            mious = mqm[midx, torch.arange(mqm.shape[1])]
+            mious = mqm[midx, torch.arange(mqm.shape[1], device=mqm.device)]
             if has_gt:
                 cls = tgt.gt_classes[midx]
                 cls[mlab == 0] = self.num_classes
@@ -315,7 +315,7 @@ class ROIHeads3D(StandardROIHeads):
             return instances if not self.training else (instances, {})
         counts = [len(p) for p in proposals]
         rep = lambda vals: torch.cat([torch.as_tensor(v, dtype=torch.float32).reshape(1, -1).repeat(c, 1)
-                                      for v, c in zip(vals, counts)])
+                                      for v, c in zip(vals, counts)]).to(x.device)      # (the reference .cuda()s these)
         Kb = rep([(Ks[i] / im_scales_ratio[i]).reshape(-1) for i in range(len(Ks))]).view(n, 3, 3)
         Kb[:, -1, -1] = 1
         focal = rep([Ks[i][1, 1] for i in range(len(Ks))]).squeeze(1)
@@ -326,7 +326,7 @@ class ROIHeads3D(StandardROIHeads):
         sw, sh = src[:, 2] - src[:, 0], src[:, 3] - src[:, 1]
         scx, scy = src[:, 0] + 0.5 * sw, src[:, 1] + 0.5 * sh
         d2, z, dims, pose, uncert = self.cube_head(x)
-        ar = torch.arange(n)
+        ar = torch.arange(n, device=x.device)
         z, dims, pose, uncert, d2 = z[ar, classes, :], dims[ar, classes, :], pose[ar, classes], uncert[ar, classes], \
             d2[ar, classes, :]
         cx, cy = scx + sw * d2[:, 0], scy + sh * d2[:, 1]

@@ -125,3 +125,81 @@ def test_determinism():
     r2 = box3d.iou_box3d(a, b, with_counts=True)
     for x, y in zip(r1, r2):
         assert torch.equal(x, y)
+
+
+# ---- all (image, category) groups of Omni3Deval.computeIoU in one segmented launch ---------------------
+def _groups(seed, G=40):
+    rng = np.random.default_rng(seed)
+    dts, gts = [], []
+    for g in range(G):
+        n, m = int(rng.integers(0, 40)), int(rng.integers(0, 12))
+        if g == 3:
+            n, m = 0, 5
+        if g == 4:
+            n, m = 6, 0
+        if g == 5:
+            n, m = 0, 0
+        if g == 6:
+            n, m = 100, 30
+        L = float(rng.choice([1.0, 3.0, 10.0]))
+        a = boxgen.random_boxes(n, L, seed * 1000 + g) if n else np.zeros((0, 8, 3), np.float32)
+        if n >= 8:
+            a, _ = boxgen.inject_degenerate(a, 0.1, g)
+        dts.append(a)
+        gts.append(boxgen.random_boxes(m, L, seed * 1000 + g + 500) if m else np.zeros((0, 8, 3), np.float32))
+    return dts, gts
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_segmented_overlap_equals_per_group_oracle(seed, capsys):
+    from omni3d_b200 import evaluation as ev
+    dts, gts = _groups(seed)
+    res, bad = ev.box3d_overlap_segmented(dts, gts, return_bad_counts=True)
+    nb = np.zeros(2, np.int64)
+    for a, b, r in zip(dts, gts, res):
+        assert r.shape == (len(a), len(b)) and r.dtype == np.float32
+        if len(a) and len(b):
+            ref, k = oracle.box3d_overlap(a, b)
+            assert np.array_equal(r, ref)
+        if len(a):
+            c, z = oracle.check_boxes(a)
+            nb += [int((~c).sum()), int((~z).sum())]
+    assert list(bad) == list(nb) and nb.min() > 0
+    out = capsys.readouterr().out
+    assert "non-coplanar boxes at eval" in out and "zero volume boxes at eval" in out
+
+
+def test_compute_ious_3d_matches_reference_call_pattern():
+    """== {(imgId, catId): computeIoU(imgId, catId)} of omni3d_evaluation.py:1339-1343 with box3d_overlap = the oracle:
+    score-sorted (stable), truncated to maxDets, [] for empty groups."""
+    from omni3d_b200 import evaluation as ev
+    rng = np.random.default_rng(7)
+    dts, gts = {}, {}
+    imgs, cats = [11, 12, 13], [0, 1, 2]
+    for i in imgs:
+        for c in cats:
+            n, m = int(rng.integers(0, 9)), int(rng.integers(0, 4))
+            if (i, c) == (12, 1):
+                n, m = 0, 0
+            a = boxgen.random_boxes(n, 2.0, i * 10 + c) if n else []
+            b = boxgen.random_boxes(m, 2.0, i * 10 + c + 7) if m else []
+            sc = np.round(rng.uniform(0, 1, n), 1)                      # ties: the merge sort keeps input order
+            dts[i, c] = [{"score": float(s), "bbox3D": a[k].tolist(), "bbox": [0, 0, 1, 1]} for k, s in enumerate(sc)]
+            gts[i, c] = [{"bbox3D": b[k].tolist(), "bbox": [0, 0, 1, 1]} for k in range(m)]
+    got = ev.compute_ious_3d(dts, gts, imgs, cats, max_dets=5)
+    for i in imgs:
+        for c in cats:
+            dt, gt = dts[i, c], gts[i, c]
+            if not dt and not gt:
+                assert got[i, c] == []
+                continue
+            inds = np.argsort([-d["score"] for d in dt], kind="mergesort")
+            dt = [dt[k] for k in inds][:5]
+            ious, prox = got[i, c]
+            assert prox is None
+            if dt and gt:
+                ref, _ = oracle.box3d_overlap(np.array([d["bbox3D"] for d in dt], np.float32),
+                                              np.array([g["bbox3D"] for g in gt], np.float32))
+                assert np.array_equal(ious, ref)
+            else:
+                assert ious == []

@@ -60,8 +60,14 @@ def test_conv_real_shapes_vs_torch_fp32(name, N, H, W, Cin, Cout, k, s, p):
             wv = wr.clone().requires_grad_(True)
             bv = b.detach().clone().requires_grad_(True)
             with torch.enable_grad():
-                yr = F.relu(F.conv2d(xr, wv, bv, s, p))
-                yr.backward(dy[i:i + step].float().permute(0, 3, 1, 2))
+                yl = F.conv2d(xr, wv, bv, s, p)
+                yr = F.relu(yl)
+                # the backward is compared under the PRODUCT's ReLU mask: among 10^7..10^8 outputs a few pre-activations lie
+                # within fp32 summation-order noise of 0, and one flipped mask bit moves a whole gradient row by O(|dy| |w|)
+                mask = (y.detach()[i:i + step] > 0).permute(0, 3, 1, 2)
+                yl.backward(dy[i:i + step].float().permute(0, 3, 1, 2) * mask)
+            flips = ((yr > 0) != mask).float().mean().item()
+            assert flips < 1e-4, (name, "relu mask disagreement", flips)
             e_y = max(e_y, (y.detach()[i:i + step].float() - yr.permute(0, 2, 3, 1)).abs().max().item())
             m_y = max(m_y, yr.abs().max().item())
             e_x = max(e_x, (x.grad[i:i + step].float() - xr.grad.permute(0, 2, 3, 1)).abs().max().item())
@@ -255,3 +261,46 @@ def test_trainer_state_dict_roundtrip():
     assert tr2.iteration == 2 and torch.equal(tr2.flat_m, tr.flat_m) and torch.equal(tr2.flat_p, tr.flat_p)
     with pytest.raises(NotImplementedError):
         FlatSGDTrainer(pc.load_cfg("cubercnn_DLA34_FPN.yaml", ["MODEL.WEIGHTS_PRETRAIN", "none", "SOLVER.NESTEROV", True]), model2)
+
+
+# ---- FC layers on the tcgen05 GEMM ------------------------------------------
+@pytest.mark.parametrize("rows,C,PP,N,relu,out_fp32", [(384, 64, 4, 256, True, False), (1000, 1024, 1, 256, False, True),
+                                                       (4096, 1024, 1, 768, False, True), (16384, 256, 49, 1024, True, False),
+                                                       (200, 128, 1, 64, True, False)])
+def test_linear_act_vs_torch(rows, C, PP, N, relu, out_fp32):
+    """c3d_linear_fwd/_dgrad/_wgrad (+ bias/ReLU epilogue, (c,p)->(p,c) feature re-ordering of the fc1 weights, weight
+    gradient written in the master's order) vs fp32 torch on the same bf16-rounded operands."""
+    from omni3d_b200.nnfunc import LinearAct
+    torch.backends.cuda.matmul.allow_tf32 = False
+    K = C * PP
+    x = _r(rows, K).bfloat16().requires_grad_(True)                      # (p, c)-ordered features (NHWC-flattened RoI)
+    w = torch.nn.Parameter(_r(N, K, seed=1) / K ** 0.5)                   # master: (c, p)-ordered input features
+    b = torch.nn.Parameter(_r(N, seed=2))
+    chw = (C, PP) if PP > 1 else None
+    y = LinearAct.apply(x, w, b, relu, out_fp32, chw)
+    assert y.dtype == (torch.float32 if out_fp32 else torch.bfloat16)
+    dy = _r(rows, N, seed=3)
+    dy = dy if out_fp32 else dy.bfloat16()
+    y.backward(dy)
+    xr = x.detach().float().view(rows, PP, C).permute(0, 2, 1).reshape(rows, K).requires_grad_(True)
+    wr = w.detach().bfloat16().float().requires_grad_(True)
+    br = b.detach().clone().requires_grad_(True)
+    yl = F.linear(xr, wr, br)
+    yr = F.relu(yl) if relu else yl
+    # backward under the product's ReLU mask (see test_conv_real_shapes_vs_torch_fp32)
+    mask = (y.detach() > 0) if relu else torch.ones_like(yl, dtype=torch.bool)
+    if relu:
+        assert ((yr > 0) != mask).float().mean().item() < 1e-4
+    yl.backward(dy.float() * mask)
+    tol = lambda ref: 1.2e-2 * ref.abs().max().item() + 1e-3
+    assert (y.float() - yr).abs().max().item() <= tol(yr)
+    gx = xr.grad.view(rows, C, PP).permute(0, 2, 1).reshape(rows, K)
+    assert (x.grad.float() - gx).abs().max().item() <= tol(gx)
+    # dz is rounded to bf16 before the weight-gradient GEMM when dy arrives in fp32
+    assert _rel(w.grad, wr.grad) <= (1e-2 if out_fp32 else 2e-3), _rel(w.grad, wr.grad)
+    assert _rel(b.grad, br.grad) <= (1e-2 if out_fp32 else 2e-3)
+    # second pass: w.grad / b.grad exist now (like the trainer's flat gradient arena) -> accumulated in place by the kernels
+    y2 = LinearAct.apply(x.detach(), w, b, relu, out_fp32, chw)
+    y2.backward(dy)
+    assert _rel(w.grad, 2 * wr.grad) <= (1e-2 if out_fp32 else 2e-3)
+    assert _rel(b.grad, 2 * br.grad) <= (1e-2 if out_fp32 else 2e-3)
