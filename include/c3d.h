@@ -354,6 +354,16 @@ int32_t c3d_anchor_sample_finish(const int8_t* labels01, const float* max_ioa, c
                                  int64_t A, int32_t k, int32_t cap_pos, int32_t n_total, float ignore_thresh,
                                  int8_t* out_labels, uint64_t* rng_bump, void* stream);
 
+/* Inference post-processing before the NMS (cubercnn/modeling/roi_heads/fast_rcnn.py:76-100) for all images of a batch:
+ * probs [B][P][K+1] (softmax scores, last = background), boxes [B][P][K][4] (per-class decoded boxes, unclipped),
+ * prop_count [B], image_hw [B][2].  Proposals with any non-finite score / coordinate are dropped, boxes are clipped to
+ * the image, (proposal p, class k) pairs with score > score_thresh become candidates at index p*K + k:
+ * cand_score [B][P*K] (-inf = not a candidate), cand_boxes [B][P*K][4], maxc [B] = max candidate coordinate,
+ * total [B] = number of candidates.  Followed by c3d_topk_segments + c3d_nms_batched (per-class) + top-100. */
+int32_t c3d_det_candidates(const float* probs, const float* boxes, const int32_t* prop_count, const float* image_hw,
+                           int32_t B, int32_t P, int32_t K, float score_thresh, float* cand_score, float* cand_boxes,
+                           float* maxc, int32_t* total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -366,6 +366,41 @@ anchor_sample_finish_kernel(const signed char* __restrict__ lab, const float* __
 
 __global__ void rng_bump_kernel(unsigned long long* rng) { rng[1] += 1; }
 
+// ------------------------------------------------------------------------------------------------------------------
+// fast_rcnn_inference_single_image, steps before the NMS (cubercnn/modeling/roi_heads/fast_rcnn.py:76-100) for all images:
+// drop proposals with a non-finite score or box, clip the per-class boxes to the image, keep (proposal, class) pairs with
+// score > thresh.  One warp per proposal.  Candidate (p, k) lives at index p*K + k (= filter_mask.nonzero() order).
+__global__ void det_candidates_kernel(const float* __restrict__ probs /*[B][P][K+1]*/, const float4* __restrict__ boxes /*[B][P][K]*/,
+                                      const int* __restrict__ prop_count, const float* __restrict__ hw /*[B][2]*/, int B, int P,
+                                      int K, float thresh, float* __restrict__ cand_score /*[B][P*K]*/,
+                                      float4* __restrict__ cand_boxes, int* __restrict__ maxc_bits /*[B]*/, int* __restrict__ total /*[B]*/) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * P) return;
+  const int b = warp / P, p = warp - b * P;
+  const float* pr = probs + (size_t)warp * (K + 1);
+  const float4* bx = boxes + (size_t)warp * K;
+  bool ok = p < prop_count[b];
+  for (int k = lane; k <= K; k += 32) ok = ok && isfinite(pr[k]);
+  for (int k = lane; k < K; k += 32) { const float4 v = bx[k]; ok = ok && isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w); }
+  ok = __all_sync(0xffffffffu, ok);
+  const float H = hw[2 * b], W = hw[2 * b + 1];
+  float mx = 0.f; int cnt = 0;
+  for (int k = lane; k < K; k += 32) {
+    float4 v = bx[k];
+    v.x = fminf(fmaxf(v.x, 0.f), W); v.y = fminf(fmaxf(v.y, 0.f), H);
+    v.z = fminf(fmaxf(v.z, 0.f), W); v.w = fminf(fmaxf(v.w, 0.f), H);
+    const float s = pr[k];
+    const bool keep = ok && s > thresh;
+    const size_t o = ((size_t)b * P + p) * K + k;
+    cand_score[o] = keep ? s : -INFINITY;
+    cand_boxes[o] = v;
+    if (keep) { mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w))); ++cnt; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+  if (lane == 0 && cnt) { atomicMax(maxc_bits + b, __float_as_int(mx)); atomicAdd(total + b, cnt); }
+}
+
 }  // namespace c3d
 
 using namespace c3d;
@@ -451,4 +486,21 @@ extern "C" int32_t c3d_anchor_sample_finish(const int8_t* labels01, const float*
       reinterpret_cast<const signed char*>(labels01), max_ioa, topk_idx, counts, best_idx, gt_valid, gt_ign, G, A, k, cap_pos,
       n_total, ignore_thresh, reinterpret_cast<signed char*>(out_labels), reinterpret_cast<unsigned long long*>(rng_bump));
   return check_launch("anchor_sample_finish");
+}
+
+extern "C" int32_t c3d_det_candidates(const float* probs, const float* boxes, const int32_t* prop_count, const float* image_hw,
+                                      int32_t B, int32_t P, int32_t K, float score_thresh, float* cand_score, float* cand_boxes,
+                                      float* maxc, int32_t* total, void* stream) {
+  if (!probs || !boxes || !prop_count || !image_hw || !cand_score || !cand_boxes || !maxc || !total || B < 1 || P < 1 || K < 1)
+    return set_error(C3D_EINVAL, "det_candidates: bad args");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(maxc, 0, sizeof(float) * B, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(total, 0, sizeof(int) * B, st);
+  if (e != cudaSuccess) return set_error(C3D_ECUDA, "det_candidates: %s", cudaGetErrorString(e));
+  const long long threads = (long long)B * P * 32;
+  det_candidates_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(probs, reinterpret_cast<const float4*>(boxes), prop_count,
+                                                                        image_hw, B, P, K, score_thresh, cand_score,
+                                                                        reinterpret_cast<float4*>(cand_boxes),
+                                                                        reinterpret_cast<int*>(maxc), total);
+  return check_launch("det_candidates");
 }

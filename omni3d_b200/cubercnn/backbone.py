@@ -17,8 +17,44 @@ from ..nnfunc import ConvBias, ConvBNAct, MaxPool2, MaxPool3s2
 from .registry import BACKBONE_REGISTRY
 
 
+_fold_cache = {}
+
+
+def set_bn_folding(model, enable=True):
+    """mark every BatchNorm2d of `model`: in eval mode (and under no_grad) its conv+BN pair runs as ONE convolution with the
+    BatchNorm folded into weight and bias (omni3d_b200.checkpoint.fold_batchnorm)."""
+    for m in model.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m._c3d_fold = bool(enable)
+    _fold_cache.clear()
+
+
+def _folded(conv, bn, cin):
+    """bf16 OHWI pack of w * gamma * rstd and the fp32 bias beta - mean * gamma * rstd, cached per parameter / statistics
+    version (load_state_dict and optimizer steps bump them; the trainer's raw-pointer updates bump nnfunc's epoch)."""
+    from .. import conv as K
+    from .. import nnfunc
+    from ..checkpoint import folded_conv_params
+    ts = (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    ver = tuple((t.data_ptr(), t._version) for t in ts) + (nnfunc._epoch, cin)
+    hit = _fold_cache.get(id(bn))
+    if hit is None or hit[0] != ver or hit[3] is not bn:
+        w, b = folded_conv_params(conv.weight.detach(), bn)
+        if w.shape[1] != cin:
+            w = F.pad(w, (0, 0, 0, 0, 0, cin - w.shape[1]))
+        wp, _ = K.pack_conv_weight(w, want_dgrad=False)
+        hit = (ver, wp, b.contiguous(), bn)
+        _fold_cache[id(bn)] = hit
+    return hit[1], hit[2]
+
+
 def conv_bn(x, conv, bn, residual=None, relu=True):
     """x NHWC bf16 -> [relu](BN(conv(x)) [+ residual]) through the fused kernels."""
+    if not bn.training and getattr(bn, "_c3d_fold", False) and not torch.is_grad_enabled():
+        from .. import conv as K
+        wp, b = _folded(conv, bn, x.shape[-1])
+        res = residual.contiguous() if residual is not None else None
+        return K.conv2d_fwd(x.contiguous(), wp, b, conv.stride[0], conv.padding[0], relu=relu, addend=res)
     w = conv.weight
     if w.shape[1] != x.shape[-1]:                       # stem: Cin 3 zero-padded to the 16 the TMA box needs
         w = F.pad(w, (0, 0, 0, 0, 0, x.shape[-1] - w.shape[1]))

@@ -155,6 +155,8 @@ class ROIHeads3D(nn.Module):
         self.stats = {}
         self.fused_cube = True        # c3d_cube_loss_fwd/bwd; False = the batched torch fp32 formulation below
         self.fused_sampling = True    # c3d_label_sample_proposals; False = the batched torch formulation below
+        # torchvision.ops.batched_nms: coordinate trick up to this many box coordinates, per-class NMS above (CUDA value)
+        self.nms_trick_max_numel = 20000
 
     # -- proposal labelling / sampling (roi_heads.py:826-929) -----------------------------------------
     @torch.no_grad()
@@ -409,56 +411,104 @@ class ROIHeads3D(nn.Module):
             return None, losses
         return self.inference(feats, prop_boxes, prop_count, image_sizes, Ks, ratios), {}
 
+    # -- inference (fast_rcnn.py:57-143 + roi_heads.py:227-246,774-819), batched over all images ---------------
     @torch.no_grad()
-    def inference(self, feats, prop_boxes, prop_count, image_sizes, Ks, ratios):
-        """fast_rcnn.py:57-143 + roi_heads.py:227-246,774-819 (per-image loop: eval is not the bench path)."""
-        from torchvision.ops import batched_nms
-        from .structures import Boxes, Instances
+    def box_dense(self, feats, prop_boxes, prop_count):
+        """-> probs (B,P,K+1) softmax scores, boxes (B,P,K,4) per-class decoded boxes (FastRCNNOutputLayers.predict_*)."""
         B, P, _ = prop_boxes.shape
-        dev = prop_boxes.device
         K = self.num_classes
-        pvalid = torch.arange(P, device=dev)[None] < prop_count[:, None]
+        pvalid = torch.arange(P, device=prop_boxes.device)[None] < prop_count[:, None]
         x = self.pool(feats, prop_boxes, pvalid)
         scores, deltas = self.box_branch(x)
         probs = F.softmax(scores, -1).view(B, P, K + 1)
-        pboxes = apply_deltas(deltas, prop_boxes.reshape(-1, 4), self.box_weights).view(B, P, K, 4)
-        det_boxes, det_cls, det_scores, det_full, counts = [], [], [], [], []
+        pboxes = apply_deltas(deltas.contiguous(), prop_boxes.reshape(-1, 4), self.box_weights).view(B, P, K, 4)
+        return probs, pboxes
+
+    @torch.no_grad()
+    def select_detections(self, probs, pboxes, prop_count, hw, max_candidates=8192):
+        """fast_rcnn_inference for ALL images without a per-image loop: finite / score filter + clip
+        (c3d_det_candidates) -> top-M candidates in score order (c3d_topk_segments) -> per-class greedy NMS
+        (c3d_nms_batched, categories = classes) -> first DETECTIONS_PER_IMAGE survivors.
+        -> boxes (B,D,4), scores (B,D), classes (B,D), scores_full (B,D,K), proposal index (B,D), count (B,) — identical to
+        the per-image reference whenever the D-th survivor lies inside the top-M candidates (checked; else exact rounds)."""
+        from .. import kernels as Kx
+        B, P, K1 = probs.shape
+        K, D = K1 - 1, self.test_topk
+        cs, cb, maxc, total = Kx.det_candidates(probs, pboxes, prop_count, hw, self.test_score_thresh)
+        M = min(P * K, max_candidates)
+        sv, si, cnt = Kx.topk_segments([(cs, M)], want_idx64=True, want_counts=True)
+        sb = torch.gather(cb, 1, si[:, :, None].expand(-1, -1, 4))
+        cats = (si % K).float()
+        keep, kcnt = Kx.nms_batched(sb, cnt.reshape(-1).contiguous(), self.test_nms_thresh, D, cats=cats, maxc=maxc,
+                                    trick_max_numel=self.nms_trick_max_numel)
+        safe = keep.clamp(min=0).long()
+        flat = torch.gather(si, 1, safe)
+        out = dict(boxes=torch.gather(sb, 1, safe[:, :, None].expand(-1, -1, 4)), scores=torch.gather(sv, 1, safe),
+                   classes=flat % K, prop=flat // K, count=kcnt)
+        host = torch.stack([kcnt, total]).tolist()            # the ONE device->host read of the post-processing
         for i in range(B):
-            n = int(prop_count[i])
-            h, w = image_sizes[i]
-            b, s = pboxes[i, :n], probs[i, :n]
-            ok = torch.isfinite(b).all(-1).all(-1) & torch.isfinite(s).all(-1)
-            b, s = b[ok], s[ok][:, :-1]
-            lim = torch.tensor([w, h, w, h], dtype=torch.float32, device=dev)
-            b = torch.minimum(b.clamp(min=0), lim)
-            m = s > self.test_score_thresh
-            inds = m.nonzero()
-            bb, ss, sf = b[m], s[m], s[inds[:, 0]]
-            keep = batched_nms(bb, ss, inds[:, 1], self.test_nms_thresh)[: self.test_topk]
-            det_boxes.append(bb[keep]); det_scores.append(ss[keep]); det_full.append(sf[keep]); det_cls.append(inds[keep][:, 1])
-            counts.append(len(keep))
-        results = []
-        D = max(max(counts), 1)
-        padb = torch.zeros((B, D, 4), device=dev)
-        padc = torch.zeros((B, D), dtype=torch.long, device=dev)
-        padv = torch.zeros((B, D), dtype=torch.bool, device=dev)
-        for i in range(B):
-            padb[i, :counts[i]] = det_boxes[i]; padc[i, :counts[i]] = det_cls[i]; padv[i, :counts[i]] = True
-        xc = self.pool(feats, padb, padv)
+            if host[0][i] < D and host[1][i] > M:             # the D-th survivor may lie beyond the top-M: exact rounds
+                self._select_rounds(i, cs, cb, maxc, out, M, D, K)
+                host[0][i] = int(out["count"][i])
+        out["scores_full"] = torch.gather(probs[:, :, :K], 1, out["prop"][:, :, None].expand(-1, -1, K))
+        out["counts_host"] = host[0]
+        return out
+
+    @torch.no_grad()
+    def _select_rounds(self, i, cs, cb, maxc, out, M, D, K):
+        """rare path of select_detections for one image: walk the fully sorted candidate list in chunks, every chunk
+        preceded by the survivors so far (they are higher-scored and mutually compatible, so the greedy scan keeps them)."""
+        from .. import kernels as Kx
+        score, order = cs[i].sort(descending=True)
+        n = int(torch.isfinite(score).sum())
+        kept = torch.zeros(0, dtype=torch.long, device=cs.device)        # indices into the candidate array
+        pos = 0
+        while pos < n and kept.numel() < D:
+            chunk = order[pos:min(n, pos + M - kept.numel())]
+            idx = torch.cat([kept, chunk])
+            pos += chunk.numel()
+            nv = torch.tensor([idx.numel()], dtype=torch.int32, device=cs.device)
+            keep, kc = Kx.nms_batched(cb[i][idx][None].contiguous(), nv, self.test_nms_thresh, D, cats=(idx % K).float()[None],
+                                      maxc=maxc[i:i + 1], trick_max_numel=0)
+            kept = idx[keep[0, :int(kc[0])].long()]
+        c = kept.numel()
+        out["boxes"][i, :c], out["scores"][i, :c] = cb[i][kept], cs[i][kept]
+        out["classes"][i, :c], out["prop"][i, :c], out["count"][i] = kept % K, kept // K, c
+
+    @torch.no_grad()
+    def cube_decode(self, feats, boxes, classes, valid, image_sizes, Ks, ratios):
+        """roi_heads.py:326-524,774-819 at inference for (B,D) detections -> dict of (B*D, ...) 3D outputs."""
+        B, D, _ = boxes.shape
+        dev = boxes.device
+        xc = self.pool(feats, boxes, valid)
         Kb, v2r, rr = self.per_box_camera(Ks, ratios, [s[0] for s in image_sizes], D, B, dev)
-        raw = self.cube_outputs(xc, padc.reshape(-1))
-        cx, cy, dims, pose, z = self.decode(raw, padb.reshape(-1, 4), padc.reshape(-1), Kb, v2r)
+        raw = self.cube_outputs(xc, classes.reshape(-1))
+        cx, cy, dims, pose, z = self.decode(raw, boxes.reshape(-1, 4), classes.reshape(-1), Kb, v2r)
         fx, fy, px, py = Kb[:, 0, 0], Kb[:, 1, 1], Kb[:, 0, 2], Kb[:, 1, 2]
         cam = torch.stack((z * (cx - px) / fx, z * (cy - py) / fy, z), 1)
-        conf = torch.exp(-raw["uncert"])
-        c2d = torch.stack((cx, cy), 1) * rr[:, None]
-        corners = G.cuboid_corners(cam, dims, pose)
-        for i in range(B):
-            sl = slice(i * D, i * D + counts[i])
+        return dict(cam=cam, dims=dims, pose=pose, conf=torch.exp(-raw["uncert"]), c2d=torch.stack((cx, cy), 1) * rr[:, None],
+                    corners=G.cuboid_corners(cam, dims, pose))
+
+    @torch.no_grad()
+    def inference(self, feats, prop_boxes, prop_count, image_sizes, Ks, ratios, hw=None):
+        from .structures import Boxes, Instances
+        B = prop_boxes.shape[0]
+        dev = prop_boxes.device
+        if hw is None:
+            hw = torch.as_tensor(image_sizes, dtype=torch.float32, device=dev)
+        probs, pboxes = self.box_dense(feats, prop_boxes, prop_count)
+        det = self.select_detections(probs, pboxes, prop_count, hw)
+        D = det["boxes"].shape[1]
+        valid = torch.arange(D, device=dev)[None] < det["count"][:, None]
+        c3 = self.cube_decode(feats, det["boxes"], det["classes"], valid, image_sizes, Ks, ratios)
+        scores = (det["scores"].reshape(-1) * c3["conf"]) ** 0.5
+        results = []
+        for i, n in enumerate(det["counts_host"]):               # views only: no device work, no host sync
+            sl = slice(i * D, i * D + n)
             inst = Instances(tuple(image_sizes[i]))
-            inst.pred_boxes = Boxes(det_boxes[i]); inst.scores = (det_scores[i] * conf[sl]) ** 0.5
-            inst.scores_full = det_full[i]; inst.pred_classes = det_cls[i]
-            inst.pred_bbox3D = corners[sl]; inst.pred_center_cam = cam[sl]; inst.pred_center_2D = c2d[sl]
-            inst.pred_dimensions = dims[sl]; inst.pred_pose = pose[sl]
+            inst.pred_boxes = Boxes(det["boxes"][i, :n]); inst.scores = scores[sl]
+            inst.scores_full = det["scores_full"][i, :n]; inst.pred_classes = det["classes"][i, :n]
+            inst.pred_bbox3D = c3["corners"][sl]; inst.pred_center_cam = c3["cam"][sl]; inst.pred_center_2D = c3["c2d"][sl]
+            inst.pred_dimensions = c3["dims"][sl]; inst.pred_pose = c3["pose"][sl]
             results.append(inst)
         return results

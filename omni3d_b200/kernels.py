@@ -69,6 +69,7 @@ def _bind():
     sig["c3d_topk_segments"] = [ctypes.POINTER(TopkSeg), i32, i32, i32, vp, vp, vp, vp, vp]
     sig["c3d_label_sample_proposals"] = [ctypes.POINTER(LabelSampleArgs), vp]
     sig["c3d_anchor_sample_keys"] = [vp, vp, i32, i64, vp, vp, vp, vp]
+    sig["c3d_det_candidates"] = [vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]
     sig["c3d_anchor_sample_finish"] = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, i32, i32, f32, vp, vp, vp]
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -489,3 +490,21 @@ def anchor_sample(labels01, matched_iou, max_ioa, best_idx, gt_valid, gt_ign, n_
                                           _p(v8), _p(i8), B, G, A, k, int(cap_pos), int(n_total), float(ignore_thresh),
                                           _p(out), _p(rng) if bump_rng else None, _st()))
     return out
+
+
+def det_candidates(probs, boxes, prop_count, image_hw, score_thresh):
+    """probs (B,P,K+1), boxes (B,P,K,4) fp32 -> cand_score (B,P*K) (-inf = filtered), cand_boxes (B,P*K,4) clipped,
+    maxc (B,), total (B,) int32 (fast_rcnn.py:76-100 for the whole batch)."""
+    L = _bind()
+    B, P, K1 = probs.shape
+    K = K1 - 1
+    dev = probs.device
+    probs, boxes = probs.contiguous().float(), boxes.contiguous().float()
+    cs = torch.empty((B, P * K), dtype=torch.float32, device=dev)
+    cb = torch.empty((B, P * K, 4), dtype=torch.float32, device=dev)
+    maxc = torch.empty((B,), dtype=torch.float32, device=dev)
+    total = torch.empty((B,), dtype=torch.int32, device=dev)
+    _lib.check(L.c3d_det_candidates(_p(probs), _p(boxes), _p(prop_count.to(torch.int32).contiguous()),
+                                    _p(image_hw.contiguous().float()), B, P, K, float(score_thresh), _p(cs), _p(cb), _p(maxc),
+                                    _p(total), _st()))
+    return cs, cb, maxc, total

@@ -236,3 +236,95 @@ def test_cuda_graph_step_matches_eager_step():
         assert abs(a - b) <= 0.12 * abs(a), (tot[False], tot[True])
     # steps 3..5 replay the graph on three different batches
     assert len({round(v, 4) for v in tot[True][3:]}) == 3, tot[True]
+
+
+def test_inference_stages_vs_oracle(pair):
+    """Inference parity stage by stage (the discrete post-processing is compared bit-exactly on identical inputs in
+    test_select_gpu.py): with the ORACLE's proposals, (1) the dense box-head outputs — softmax scores and per-class decoded
+    boxes of every proposal — and, with the ORACLE's detections, (2) the cube head's 3D outputs (centre, dimensions, pose,
+    corners, confidence) agree with the fp32 oracle within the bf16 tolerance.  Eval-mode BatchNorm (running statistics)."""
+    prod, orc = pair
+    from oracle import model_io
+    _sync_state(prod, orc)
+    items = synth.make_batch(2, H, W, with_gt=False, seed=3)
+    prod.eval(); orc.eval()
+    d2 = model_io.to_d2_inputs(items)
+    with torch.no_grad():
+        images = orc.preprocess_image(d2)
+        f = orc.backbone(images.tensor)
+        props, _ = orc.proposal_generator(images, f, None)
+        rh = orc.roi_heads
+        feats_o = [f[k] for k in rh.box_in_features]
+        pred = rh.box_predictor(rh.box_head(rh.box_pooler(feats_o, [p.proposal_boxes for p in props])))
+        o_probs = rh.box_predictor.predict_probs(pred, props)
+        o_boxes = rh.box_predictor.predict_boxes(pred, props)
+        ref = orc(d2)
+        # product, teacher-forced with the oracle's proposals
+        x, sizes = prod.preprocess_image(items)
+        feats = prod.backbone(x)
+        pr = prod.roi_heads
+        fl = [feats[k] for k in pr.in_features]
+        P = max(len(p) for p in props)
+        pb = torch.zeros(len(props), P, 4); pc = torch.zeros(len(props), dtype=torch.int32)
+        for i, p in enumerate(props):
+            pb[i, :len(p)], pc[i] = p.proposal_boxes.tensor, len(p)
+        probs, pboxes = pr.box_dense(fl, pb.cuda(), pc.cuda())
+    K = pr.num_classes
+    for i, p in enumerate(props):
+        n = len(p)
+        assert (probs[i, :n].cpu() - o_probs[i]).abs().max().item() < 2e-3            # probabilities ~ 1/51 at random init
+        assert _rel(probs[i, :n].cpu() - 1.0 / (K + 1), o_probs[i] - 1.0 / (K + 1)) < 0.15
+        ob = o_boxes[i].view(n, K, 4)
+        assert (pboxes[i, :n].cpu() - ob).abs().max().item() < 0.25                   # pixels
+    # (2) cube head on the oracle's own detections
+    D = max(len(r["instances"]) for r in ref)
+    if D == 0:
+        pytest.skip("oracle produced no detections")
+    db = torch.zeros(len(ref), D, 4); dc = torch.zeros(len(ref), D, dtype=torch.long); dv = torch.zeros(len(ref), D, dtype=torch.bool)
+    Ks = torch.tensor([it["K"] for it in items]).cuda()
+    ratios = torch.tensor([it["height"] / s[0] for it, s in zip(items, sizes)]).cuda()
+    for i, r in enumerate(ref):
+        inst = r["instances"]
+        n = len(inst)
+        # the oracle's boxes are post-processed to the original resolution (= the input resolution here: ratio 1)
+        db[i, :n], dc[i, :n], dv[i, :n] = inst.pred_boxes.tensor, inst.pred_classes, True
+    with torch.no_grad():
+        c3 = pr.cube_decode(fl, db.cuda(), dc.cuda(), dv.cuda(), sizes, Ks, ratios)
+    for i, r in enumerate(ref):
+        inst = r["instances"]
+        n = len(inst)
+        sl = slice(i * D, i * D + n)
+        assert _rel(c3["dims"][sl].cpu(), inst.pred_dimensions) < 3e-2
+        assert _rel(c3["cam"][sl].cpu(), inst.pred_center_cam) < 3e-2
+        assert _rel(c3["pose"][sl].cpu(), inst.pred_pose) < 3e-2
+        assert _rel(c3["corners"][sl].cpu(), inst.pred_bbox3D) < 3e-2
+        assert _rel(c3["c2d"][sl].cpu(), inst.pred_center_2D) < 1e-2
+
+
+def test_bn_folding_matches_unfolded_eval_and_oracle(pair):
+    """eval-mode BatchNorm folded into the convolution (one kernel, bias + residual + ReLU epilogue) gives the
+    unfolded path's features up to bf16 rounding, and the oracle's within the frozen-BN tolerance."""
+    prod, orc = pair
+    from omni3d_b200 import checkpoint as ck
+    from oracle import model_io
+    _sync_state(prod, orc)
+    saved = {k: v.clone() for k, v in orc.state_dict().items()}
+    with torch.no_grad():                       # non-trivial running statistics / affine parameters
+        for m in orc.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5); m.weight.uniform_(0.8, 1.2); m.bias.normal_(0, 0.1)
+    prod.load_state_dict(orc.state_dict())
+    items = synth.make_batch(2, H, W, with_gt=False, seed=13)
+    prod.eval(); orc.eval()
+    with torch.no_grad():
+        x, _ = prod.preprocess_image(items)
+        plain = prod.backbone(x)
+        ck.fold_batchnorm(prod, True)
+        folded = prod.backbone(x)
+        ck.fold_batchnorm(prod, False)
+        ref = orc.backbone(orc.preprocess_image(model_io.to_d2_inputs(items)).tensor)
+    for k in ref:
+        assert _rel(folded[k].float(), plain[k].float()) < 2e-2, k
+        assert _rel(folded[k].float().cpu().permute(0, 3, 1, 2), ref[k]) < 3e-2, k
+    orc.load_state_dict(saved)
+    _sync_state(prod, orc)

@@ -180,3 +180,54 @@ def test_anchor_sample_kernel_semantics_and_distribution():
         npos = min(int((lab[b] == 1).sum()), cap)
         assert npos <= int((ref[b] == 1).sum()) <= npos + int(valid[b].sum())
         assert abs(int((ref[b] >= 0).sum()) - int((out[b] >= 0).sum())) <= int(valid[b].sum()) + int(((lab[b] == 0) & (ioa[b] >= 0.5)).sum())
+
+
+# ---- batched inference post-processing == the oracle's per-image fast_rcnn_inference_single_image ---------
+def _rand_dets(B, P, K, seed, spread, peaked, clustered=False):
+    g = torch.Generator().manual_seed(seed)
+    ctr = torch.rand(B, P, 1, 2, generator=g) * torch.tensor([300.0, 200.0])
+    wh = torch.rand(B, P, K, 2, generator=g) * spread + 8
+    c = ctr + (torch.rand(B, P, K, 2, generator=g) - 0.5) * 20
+    if clustered:            # every box of a class nearly coincides: the greedy NMS keeps one or two per class
+        wh = torch.rand(B, P, K, 2, generator=g) * 6 + 40
+        c = torch.tensor([150.0, 100.0]) + (torch.rand(B, P, K, 2, generator=g) - 0.5) * 4
+    boxes = torch.cat([c - wh / 2, c + wh / 2], -1)                     # some stick out of the image: clipped
+    logits = torch.randn(B, P, K + 1, generator=g) * (3.0 if peaked else 0.3)
+    return torch.softmax(logits, -1), boxes
+
+
+@pytest.mark.parametrize("P,K,peaked,max_cand", [(200, 50, False, 8192), (60, 50, True, 8192), (300, 20, False, 512),
+                                                 (1000, 50, False, 8192)])
+def test_select_detections_equals_oracle_inference(P, K, peaked, max_cand):
+    """identical kept (box, score, class) lists, in order, for every image — including the exact-rounds path (max_cand 512:
+    heavy suppression pushes the 100th survivor beyond the top-M candidates) and a proposal with a non-finite box."""
+    from omni3d_b200.cubercnn.roi_heads import ROIHeads3D
+    from oracle.cubercnn_oracle.model import FastRCNNOutputs
+    B = 3
+    probs, boxes = _rand_dets(B, P, K, 5, 120.0, peaked, clustered=max_cand < 8192)
+    boxes[1, 7, 3, 2] = float("nan")
+    counts = torch.tensor([P, P - 5, P], dtype=torch.int32)
+    sizes = [(200, 300)] * B
+    rh = ROIHeads3D.__new__(ROIHeads3D)
+    rh.num_classes, rh.test_topk, rh.test_score_thresh, rh.test_nms_thresh = K, 100, 0.01, 0.5
+    rh.nms_trick_max_numel = 4000                                       # the CPU oracle runs torchvision's CPU threshold
+    hw = torch.tensor(sizes, dtype=torch.float32)
+    det = ROIHeads3D.select_detections(rh, probs.cuda(), boxes.cuda(), counts.cuda(), hw.cuda(), max_candidates=max_cand)
+    orc = FastRCNNOutputs.__new__(FastRCNNOutputs)
+    orc.test_score_thresh, orc.test_nms_thresh, orc.test_topk_per_image = 0.01, 0.5, 100
+    used_rounds = False
+    for i in range(B):
+        n = int(counts[i])
+        res, _ = FastRCNNOutputs._inference_one(orc, boxes[i, :n].reshape(n, -1), probs[i, :n], sizes[i])
+        c = det["counts_host"][i]
+        assert c == len(res), (i, c, len(res))
+        assert torch.equal(det["scores"][i, :c].cpu(), res.scores)
+        assert torch.equal(det["classes"][i, :c].cpu(), res.pred_classes)
+        assert torch.equal(det["boxes"][i, :c].cpu(), res.pred_boxes.tensor)
+        assert torch.equal(det["scores_full"][i, :c].cpu(), res.scores_full)
+        # the kept pairs really are (proposal, class) entries of the input
+        pi, ci = det["prop"][i, :c].cpu(), det["classes"][i, :c].cpu()
+        assert torch.equal(probs[i][pi, ci], res.scores)
+        used_rounds |= bool((probs[i, :n, :K] > 0.01).sum() > max_cand and c < 100)
+    if max_cand == 512:
+        assert used_rounds           # fewer than 100 survivors although more candidates than M: the exact-rounds path ran
