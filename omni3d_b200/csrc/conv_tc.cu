@@ -50,8 +50,147 @@ struct ConvSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;       // both multiples of 1024 for BLOCK_N>=32|BK=64
   static constexpr int kTileBytes = ((kStageBytes + 1023) / 1024) * 1024;
   static constexpr int kBarOffset = STAGES * kTileBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 4 * 32 * 2 * 4 + 1024 /*align slack*/;
+  static constexpr int kRedOffset = kBarOffset + 256;                      // BatchNorm partial sums [4 warps][2][32] fp32
+  static constexpr int kStgOffset = kRedOffset + 4 * 32 * 2 * 4;           // epilogue staging: 4 warps x 32 rows x 128 B
+  static constexpr int kTotal = kStgOffset + 4 * 4096 + 1024 /*align slack*/;
 };
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue of one 128-pixel x BLOCK_N accumulator tile, run by the 4 epilogue warps (warp q owns TMEM lanes 32q..32q+31 =
+// tile rows = output pixels): tcgen05.ld 16 columns at a time -> BatchNorm partial sums -> bias / addend / ReLU ->
+// bf16|fp32 NHWC store.  bf16 outputs with BLOCK_N >= 64 are written through a per-warp shared-memory transpose: a thread
+// owns one pixel, i.e. one 2*Cout-byte ROW of the output, so direct stores put the 32 lanes of every store instruction in
+// 32 different 128-byte lines (16 useful bytes each); staged, the warp writes 4 complete 128-byte row segments per
+// instruction (8x fewer LSU wavefronts) — what bounds the small-K layers (1x1 laterals / roots / projections, 64-channel
+// 3x3s), whose tiles spend longer in the epilogue than in the MMA loop.
+template <int BLOCK_N>
+__device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& P, const uint32_t tacc /*TMEM address incl. lane*/,
+                                                   const int q, const int lane, const int img, const int ho0, const int wo0,
+                                                   const int n0, const int tile_m, float* red, uint8_t* stg_all) {
+  const int r = q * 32 + lane;                 // tile row = TMEM lane
+  const int ty = r / P.TW, tx = r - ty * P.TW;
+  const int ho = ho0 + ty, wo = wo0 + tx;
+  const bool valid = (r < P.TH * P.TW) && (ho < P.Ho) && (wo < P.Wo);
+  const long long lpix = ((long long)img * P.Ho + ho) * P.Wo + wo;   // dense pixel index (addend / stats)
+  const long long pix = (long long)img * P.out_img_stride + (long long)ho * P.out_h_stride + (long long)wo * P.out_w_stride + P.out_off;
+  long long apix = 0;
+  if (P.add_mode == 1) apix = lpix;
+  else if (P.add_mode == 2) apix = ((long long)img * (P.Ho >> 1) + (ho >> 1)) * (P.Wo >> 1) + (wo >> 1);
+  constexpr bool kStaged = BLOCK_N >= 64;
+  uint8_t* stg = stg_all + q * 4096;
+  constexpr int kChunks = (BLOCK_N + 15) / 16;
+#pragma unroll 1
+  for (int ch = 0; ch < kChunks; ++ch) {
+    uint32_t v[16];
+    ptx::tmem_ld_32x32b_x16(tacc + (uint32_t)(ch * 16), v);
+    ptx::tmem_ld_wait();
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+    const int c0 = n0 + ch * 16;
+    if (P.stats) {
+      // per-channel sum / sum-of-squares over the valid rows of this tile (raw fp32 accumulators): log-step exchange
+      // keeping 16 -> 8 -> 4 -> 2 -> 1 values per lane, then the two 16-lane halves, fixed order => deterministic
+      float s[16], s2[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { float x = valid ? f[i] : 0.f; s[i] = x; s2[i] = x * x; }
+#pragma unroll
+      for (int step = 0; step < 4; ++step) {
+        const int half = 8 >> step;
+        const int mask = 1 << step;
+        const bool upper = (lane & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < half) {
+            float send = upper ? s[i] : s[i + half];
+            float keep = upper ? s[i + half] : s[i];
+            float send2 = upper ? s2[i] : s2[i + half];
+            float keep2 = upper ? s2[i + half] : s2[i];
+            s[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, mask);
+          }
+        }
+      }
+      s[0] += __shfl_xor_sync(0xffffffffu, s[0], 16);
+      s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 16);
+      const int cidx = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
+      if (lane < 16) { red[(q * 2 + 0) * 16 + cidx] = s[0]; red[(q * 2 + 1) * 16 + cidx] = s2[0]; }
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      if (q == 0 && lane < 16 && (c0 + lane) < P.Cout) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { a += red[(w * 2 + 0) * 16 + lane]; b += red[(w * 2 + 1) * 16 + lane]; }
+        float* dst = P.stats + (size_t)tile_m * 2 * P.Cout;
+        dst[c0 + lane] = a;
+        dst[P.Cout + c0 + lane] = b;
+      }
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+    }
+    const bool live = valid && c0 < P.Cout;
+    if (live) {
+      if (P.bias) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] += __ldg(P.bias + c0 + i);
+      }
+      if (P.add_mode) {
+        const bf16* abase = P.add_mode == 3 ? reinterpret_cast<const bf16*>(P.out) + pix * P.out_pix_stride
+                                            : P.addend + apix * P.add_pix_stride;
+        const uint4* ap = reinterpret_cast<const uint4*>(abase + c0);
+        uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+        const bf16* h0 = reinterpret_cast<const bf16*>(&a0);
+        const bf16* h1 = reinterpret_cast<const bf16*>(&a1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { f[i] += __bfloat162float(h0[i]); f[8 + i] += __bfloat162float(h1[i]); }
+      }
+      if (P.relu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+      }
+    }
+    if (P.out_fp32) {
+      if (live) {
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix * P.out_pix_stride + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      }
+      continue;
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      pk[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    if constexpr (!kStaged) {
+      if (live) {
+        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + pix * P.out_pix_stride + c0);
+        op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    } else {
+      // stage my row's 32 bytes: 16-byte slots XOR-swizzled by the row so that neither phase has bank conflicts
+      const int j0 = (ch & 3) * 2;
+      *reinterpret_cast<uint4*>(stg + lane * 128 + (((j0) ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(stg + lane * 128 + (((j0 + 1) ^ (lane & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      if ((ch & 3) == 3) {                     // 64 columns staged: write 4 complete 128-byte row segments per instruction
+        __syncwarp();
+        const int gcol = n0 + (ch - 3) * 16;
+        const int j = lane & 7;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + (lane >> 3);
+          const long long prow = __shfl_sync(0xffffffffu, pix, row);
+          const int vrow = __shfl_sync(0xffffffffu, (int)valid, row);
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + row * 128 + ((j ^ (row & 7)) << 4));
+          if (vrow && gcol < P.Cout)
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + prow * P.out_pix_stride + gcol + j * 8) = val;
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
 
 template <int BLOCK_N, int BLOCK_K, int STAGES>
 __global__ void __launch_bounds__(192)
@@ -66,7 +205,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* red = reinterpret_cast<float*>(smem + S::kBarOffset + 256);   // [4 warps][2][32]... used as [4][2][16]
+  float* red = reinterpret_cast<float*>(smem + S::kRedOffset);           // [4 warps][2][16]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -138,104 +277,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   } else {
     // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
     const int q = warp & 3;
-    const int r = q * 32 + lane;                 // tile row = TMEM lane
-    const int ty = r / P.TW, tx = r - ty * P.TW;
-    const int ho = ho0 + ty, wo = wo0 + tx;
-    const bool valid = (r < P.TH * P.TW) && (ho < P.Ho) && (wo < P.Wo);
-    const long long lpix = ((long long)img * P.Ho + ho) * P.Wo + wo;   // dense pixel index (addend / stats)
-    const long long pix = (long long)img * P.out_img_stride + (long long)ho * P.out_h_stride + (long long)wo * P.out_w_stride + P.out_off;
-    long long apix = 0;
-    if (P.add_mode == 1) apix = lpix;
-    else if (P.add_mode == 2) apix = ((long long)img * (P.Ho >> 1) + (ho >> 1)) * (P.Wo >> 1) + (wo >> 1);
-
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tcgen05_fence_after();
-    constexpr int kChunks = (BLOCK_N + 15) / 16;
-#pragma unroll 1
-    for (int ch = 0; ch < kChunks; ++ch) {
-      uint32_t v[16];
-      ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), v);
-      ptx::tmem_ld_wait();
-      float f[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-      const int c0 = n0 + ch * 16;
-      if (P.stats) {
-        // per-channel sum / sum-of-squares over the valid rows of this tile (raw fp32 accumulators).
-        // butterfly transpose-reduce: after 4 halving steps + 1, lane l holds channel (l & 15)'s
-        // total over its 16-lane half... we keep it simple & exact-order: two halves then combine.
-        float s[16], s2[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { float x = valid ? f[i] : 0.f; s[i] = x; s2[i] = x * x; }
-        // reduce across the 32 lanes of the warp: log-step exchange keeping 16 -> 8 -> 4 -> 2 -> 1 values
-#pragma unroll
-        for (int step = 0; step < 4; ++step) {
-          const int half = 8 >> step;                 // values kept after this step
-          const int mask = 1 << step;                 // partner lane distance
-          const bool upper = (lane & mask) != 0;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (i < half) {
-              float send = upper ? s[i] : s[i + half];
-              float keep = upper ? s[i + half] : s[i];
-              float send2 = upper ? s2[i] : s2[i + half];
-              float keep2 = upper ? s2[i + half] : s2[i];
-              s[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-              s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, mask);
-            }
-          }
-        }
-        // now lane holds channel index cidx = bitrev-ish of (lane & 15): bit step of lane selects the
-        // upper/lower half at that step => channel = sum_{step} ((lane>>step)&1) * (8>>step)
-        s[0] += __shfl_xor_sync(0xffffffffu, s[0], 16);
-        s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 16);
-        const int cidx = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
-        if (lane < 16) { red[(q * 2 + 0) * 16 + cidx] = s[0]; red[(q * 2 + 1) * 16 + cidx] = s2[0]; }
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
-        if (q == 0 && lane < 16 && (c0 + lane) < P.Cout) {
-          float a = 0.f, b = 0.f;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) { a += red[(w * 2 + 0) * 16 + lane]; b += red[(w * 2 + 1) * 16 + lane]; }
-          float* dst = P.stats + (size_t)tile_m * 2 * P.Cout;
-          dst[c0 + lane] = a;
-          dst[P.Cout + c0 + lane] = b;
-        }
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      }
-      if (valid && c0 < P.Cout) {
-        if (P.bias) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] += __ldg(P.bias + c0 + i);
-        }
-        if (P.add_mode) {
-          const uint4* ap = reinterpret_cast<const uint4*>(P.addend + apix * P.add_pix_stride + c0);
-          uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
-          const bf16* h0 = reinterpret_cast<const bf16*>(&a0);
-          const bf16* h1 = reinterpret_cast<const bf16*>(&a1);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { f[i] += __bfloat162float(h0[i]); f[8 + i] += __bfloat162float(h1[i]); }
-        }
-        if (P.relu) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
-        if (P.out_fp32) {
-          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix * P.out_pix_stride + c0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-        } else {
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + pix * P.out_pix_stride + c0);
-          op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-      }
-    }
+    conv_epilogue_tile<BLOCK_N>(P, tmem_base + ((uint32_t)(q * 32) << 16), q, lane, img, ho0, wo0, n0, tile_m, red,
+                                smem + S::kStgOffset);
   }
   ptx::tcgen05_fence_before();
   __syncthreads();
@@ -264,7 +309,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
   uint64_t* tfull_bar = empty_bar + STAGES;          // [2]
   uint64_t* tempty_bar = tfull_bar + 2;              // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* red = reinterpret_cast<float*>(smem + S::kBarOffset + 256);
+  float* red = reinterpret_cast<float*>(smem + S::kRedOffset);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = P.KH * P.KW * P.kc_blocks;
@@ -336,98 +381,10 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
       const int tile_m = tile / n_tiles, n0 = (tile - tile_m * n_tiles) * BLOCK_N;
       const int tw_i = tile_m % P.tiles_w, th_i = (tile_m / P.tiles_w) % P.tiles_h;
       const int img = tile_m / (P.tiles_w * P.tiles_h);
-      const int r = q * 32 + lane;
-      const int ty = r / P.TW, tx = r - ty * P.TW;
-      const int ho = th_i * P.TH + ty, wo = tw_i * P.TW + tx;
-      const bool valid = (r < P.TH * P.TW) && (ho < P.Ho) && (wo < P.Wo);
-      const long long lpix = ((long long)img * P.Ho + ho) * P.Wo + wo;   // dense pixel index (addend / stats)
-    const long long pix = (long long)img * P.out_img_stride + (long long)ho * P.out_h_stride + (long long)wo * P.out_w_stride + P.out_off;
-      long long apix = 0;
-      if (P.add_mode == 1) apix = lpix;
-      else if (P.add_mode == 2) apix = ((long long)img * (P.Ho >> 1) + (ho >> 1)) * (P.Wo >> 1) + (wo >> 1);
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tcgen05_fence_after();
-      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccCols;
-      constexpr int kChunks = (BLOCK_N + 15) / 16;
-#pragma unroll 1
-      for (int ch = 0; ch < kChunks; ++ch) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x32b_x16(tacc + (uint32_t)(ch * 16), v);
-        ptx::tmem_ld_wait();
-        float f[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-        const int c0 = n0 + ch * 16;
-        if (P.stats) {
-          float s[16], s2[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { float x = valid ? f[i] : 0.f; s[i] = x; s2[i] = x * x; }
-#pragma unroll
-          for (int step = 0; step < 4; ++step) {
-            const int half = 8 >> step;
-            const int mask = 1 << step;
-            const bool upper = (lane & mask) != 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (i < half) {
-                float send = upper ? s[i] : s[i + half];
-                float keep = upper ? s[i + half] : s[i];
-                float send2 = upper ? s2[i] : s2[i + half];
-                float keep2 = upper ? s2[i + half] : s2[i];
-                s[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-                s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, mask);
-              }
-            }
-          }
-          s[0] += __shfl_xor_sync(0xffffffffu, s[0], 16);
-          s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 16);
-          const int cidx = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
-          if (lane < 16) { red[(q * 2 + 0) * 16 + cidx] = s[0]; red[(q * 2 + 1) * 16 + cidx] = s2[0]; }
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
-          if (q == 0 && lane < 16 && (c0 + lane) < P.Cout) {
-            float a = 0.f, b = 0.f;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) { a += red[(w * 2 + 0) * 16 + lane]; b += red[(w * 2 + 1) * 16 + lane]; }
-            float* dst = P.stats + (size_t)tile_m * 2 * P.Cout;
-            dst[c0 + lane] = a;
-            dst[P.Cout + c0 + lane] = b;
-          }
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
-        }
-        if (valid && c0 < P.Cout) {
-          if (P.bias) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] += __ldg(P.bias + c0 + i);
-          }
-          if (P.add_mode) {
-            const uint4* ap = reinterpret_cast<const uint4*>(P.addend + apix * P.add_pix_stride + c0);
-            uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
-            const bf16* h0 = reinterpret_cast<const bf16*>(&a0);
-            const bf16* h1 = reinterpret_cast<const bf16*>(&a1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { f[i] += __bfloat162float(h0[i]); f[8 + i] += __bfloat162float(h1[i]); }
-          }
-          if (P.relu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-          }
-          if (P.out_fp32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix * P.out_pix_stride + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-          } else {
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + pix * P.out_pix_stride + c0);
-            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          }
-        }
-      }
+      conv_epilogue_tile<BLOCK_N>(P, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccCols, q, lane, img,
+                                  th_i * P.TH, tw_i * P.TW, n0, tile_m, red, smem + S::kStgOffset);
       // this warp is done reading the accumulator: hand it back to the MMA issuer
       ptx::tcgen05_fence_before();
       __syncwarp();
@@ -733,7 +690,9 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   const int Ho = d->out_h > 0 ? d->out_h : (d->H + 2 * d->pad - d->KH) / d->stride + 1;
   const int Wo = d->out_w > 0 ? d->out_w : (d->W + 2 * d->pad - d->KW) / d->stride + 1;
   if (d->add_mode == 2 && ((Ho & 1) || (Wo & 1))) return set_error(C3D_EINVAL, "conv2d: up2 addend needs even output");
-  if (d->add_mode && !addend) return set_error(C3D_EINVAL, "conv2d: addend missing");
+  if ((d->add_mode == 1 || d->add_mode == 2) && !addend) return set_error(C3D_EINVAL, "conv2d: addend missing");
+  if (d->add_mode == 3 && d->out_fp32) return set_error(C3D_EINVAL, "conv2d: in-place accumulate needs a bf16 output");
+  if (d->add_mode < 0 || d->add_mode > 3) return set_error(C3D_EINVAL, "conv2d: add_mode %d", d->add_mode);
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error(C3D_ECUDA, "cuTensorMapEncodeTiled unavailable");
 
