@@ -86,7 +86,8 @@ typedef struct {
   int32_t stride, pad;       /* stride 1 or 2 (same in h and w), symmetric zero padding */
   int32_t relu;              /* epilogue: max(.,0) after bias/addend */
   int32_t out_fp32;          /* output fp32 instead of bf16 */
-  int32_t add_mode;          /* 0 none; 1 addend (N,Ho,Wo,Cout); 2 addend (N,Ho/2,Wo/2,Cout) nearest-up x2 (FPN) */
+  int32_t add_mode;          /* 0 none; 1 addend (N,Ho,Wo,Cout); 2 addend (N,Ho/2,Wo/2,Cout) nearest-up x2 (FPN);
+                                3 accumulate in place: y (bf16) += result at the output's own (possibly strided) position */
   int64_t x_pix_stride, y_pix_stride, add_pix_stride;   /* elements; 0 => dense */
   /* optional strided output placement (in pixels): y pixel index = n*y_img_stride + ho*y_h_stride + wo*y_w_stride +
    * y_offset; all 0 => dense (N,Ho,Wo).  Used by the phase-decomposed stride-2 data gradient. */
@@ -94,6 +95,9 @@ typedef struct {
   /* optional explicit output size (0 => (H + 2*pad - KH)/stride + 1): lets a conv pad only on the high side
    * (taps that run past H/W read TMA zero fill) */
   int32_t out_h, out_w;
+  /* optional distance between consecutive input images in PIXELS (0 => dense H*W): lets a batch of row blocks of a
+   * larger matrix be read in place (the cube head's RoIs are the first Fc of every image's S pooled RoIs) */
+  int64_t x_img_stride;
 } c3d_conv_desc;
 
 /* number of 128-pixel output tiles (= rows of the BatchNorm partial-statistics buffer) and tile shape */
@@ -136,6 +140,16 @@ int32_t c3d_linear_fwd(const void* x, const void* w, const float* bias, void* y,
 int32_t c3d_linear_dgrad(const void* dy, const void* wt, void* dx, int64_t rows, int32_t N, int32_t K, void* stream);
 int32_t c3d_linear_wgrad(const void* x, const void* dy, float* dw, int64_t rows, int32_t K, int32_t N, int32_t C,
                          int32_t PP, int32_t master_chw, void* stream);
+/* Row-block variants: the `rows` = nseg * seg_rows feature vectors are nseg blocks of seg_rows consecutive rows that start
+ * every seg_stride rows inside a larger (.., K) matrix (x for fwd / wgrad, dx for dgrad); the other operand is dense.
+ * The cube head reads the first Fc of every image's S pooled RoIs in place, and its data gradient is ACCUMULATED
+ * (accumulate != 0: dx += dy . W) into the box head's — no gather copy, no zero-padded scatter, no add pass. */
+int32_t c3d_linear_fwd_blocks(const void* x, const void* w, const float* bias, void* y, int32_t nseg, int32_t seg_rows,
+                              int64_t seg_stride, int32_t K, int32_t N, int32_t relu, int32_t out_fp32, void* stream);
+int32_t c3d_linear_dgrad_blocks(const void* dy, const void* wt, void* dx, int32_t nseg, int32_t seg_rows, int64_t seg_stride,
+                                int32_t N, int32_t K, int32_t accumulate, void* stream);
+int32_t c3d_linear_wgrad_blocks(const void* x, const void* dy, float* dw, int32_t nseg, int32_t seg_rows, int64_t seg_stride,
+                                int32_t K, int32_t N, int32_t C, int32_t PP, int32_t master_chw, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * HBM-bound NHWC bf16 kernels around the convolutions.
@@ -157,9 +171,11 @@ int32_t c3d_bn_apply(const void* y, const float* mean, const float* rstd, const 
 int32_t c3d_bn_bwd_blocks(int64_t P, int32_t C);
 /* BatchNorm(+ReLU,+residual) backward: dy (bf16) w.r.t. the conv output, dgamma/dbeta accumulated (+=),
  * optional dres = masked dout for the residual branch. partial: fp32 [blocks][2][C]; coef: fp32 [3][C].
- * frozen_stats != 0: mean/rstd are running statistics (eval mode / freeze_bn, cubercnn/solver/build.py:71-76). */
+ * frozen_stats != 0: mean/rstd are running statistics (eval mode / freeze_bn, cubercnn/solver/build.py:71-76).
+ * out may be NULL for a ReLU layer WITHOUT residual when beta is given: the mask is then recomputed from y exactly as
+ * c3d_bn_apply produced it (saves re-reading `out` in both passes). */
 int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, const float* mean, const float* rstd,
-                   const float* gamma, int32_t relu, int32_t frozen_stats, float* partial, float* coef, float* dgamma,
+                   const float* gamma, const float* beta, int32_t relu, int32_t frozen_stats, float* partial, float* coef, float* dgamma,
                    float* dbeta,
                    void* dy, void* dres, int64_t P, int32_t C, int64_t dout_stride, int64_t out_stride,
                    int64_t dres_stride, void* scratch, void* stream);
@@ -363,6 +379,35 @@ int32_t c3d_anchor_sample_finish(const int8_t* labels01, const float* max_ioa, c
 int32_t c3d_det_candidates(const float* probs, const float* boxes, const int32_t* prop_count, const float* image_hw,
                            int32_t B, int32_t P, int32_t K, float score_thresh, float* cand_score, float* cand_boxes,
                            float* maxc, int32_t* total, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Loss assembly of the ROI heads (omni3d_b200/csrc/head_loss_ops.cu).
+ * ------------------------------------------------------------------------------------------ */
+/* FastRCNNOutputs.losses (cubercnn/modeling/roi_heads/fast_rcnn.py:145-194, box_reg_loss :196-260) on the fused predictor
+ * rows pred [R][ld] fp32 = [K+1 class scores | 4K class-specific deltas | pad]: classes int64 [R] (K = background, -1 =
+ * ignored), valid uint8 [R], boxes / gt_boxes [R][4], Box2BoxTransform weights (host, 4 floats).
+ * acc [8] = sum CE(valid), sum L1(fg), #valid, #fg, #argmax==class (valid), #argmax==class (fg), #argmax==K (fg), 0.
+ * bwd: dpred [R][ld] from g2 = {dL/dloss_cls, dL/dloss_box_reg} (both losses are normalised by #valid). */
+int32_t c3d_box_loss_fwd(const float* pred, int32_t ld, const int64_t* classes, const uint8_t* valid, const float* boxes,
+                         const float* gt_boxes, int32_t R, int32_t K, const float* weights4_host, float* acc8, void* stream);
+int32_t c3d_box_loss_bwd(const float* pred, int32_t ld, const int64_t* classes, const uint8_t* valid, const float* boxes,
+                         const float* gt_boxes, int32_t R, int32_t K, const float* weights4_host, const float* acc8,
+                         const float* g2, float* dpred, void* stream);
+/* Glue around c3d_cube_loss_fwd/bwd (cubercnn/modeling/roi_heads/roi_heads.py:372-461, 690-743, 932-941):
+ *  gather : pred [n][ld] fp32 = [deltas 2K | dims 3K | pose 6K | z K | uncertainty K | pad] -> the predicted class's raw13
+ *           rows and the aux28 constants (box, K / ratio, virtual->real depth, dims prior, GT) ; meta12 [B][12] = h, w,
+ *           height/h, K (9); RoI i belongs to image i / per_image; priors [K][3]
+ *  reduce : rows10 [n][10] -> sums12 (11 used: 6 finite-masked loss sums, |dz|, dims err, xy err, #(|dz|<0.2), conf) and
+ *           cnts8 (6 finite counts + #valid); its backward gives d rows [n][6]
+ *  scatter: d raw13 -> the class's columns of d pred [n][ld] (zero elsewhere) */
+int32_t c3d_cube_gather(const float* pred, int32_t ld, const int64_t* classes, const float* boxes, const float* meta12,
+                        const float* priors, const float* gt3, const float* gtR, int32_t n, int32_t per_image, int32_t K,
+                        float virtual_focal, float* raw13, float* aux28, void* stream);
+int32_t c3d_cube_reduce_fwd(const float* rows10, const uint8_t* valid, int32_t n, float* sums12, float* cnts8, void* stream);
+int32_t c3d_cube_reduce_bwd(const float* rows10, const uint8_t* valid, int32_t n, const float* cnts8, const float* g6,
+                            float* drows6, void* stream);
+int32_t c3d_cube_scatter(const float* draw13, const int64_t* classes, int32_t n, int32_t K, int32_t ld, float* dpred,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ class ConvDesc(ctypes.Structure):
                 ("x_pix_stride", ctypes.c_int64), ("y_pix_stride", ctypes.c_int64),
                 ("add_pix_stride", ctypes.c_int64), ("y_img_stride", ctypes.c_int64), ("y_h_stride", ctypes.c_int64),
                 ("y_w_stride", ctypes.c_int64), ("y_offset", ctypes.c_int64), ("out_h", ctypes.c_int32),
-                ("out_w", ctypes.c_int32)]
+                ("out_w", ctypes.c_int32), ("x_img_stride", ctypes.c_int64)]
 
 
 _bound = False
@@ -49,6 +49,12 @@ def _bind():
         L.c3d_linear_dgrad.argtypes = [vp, vp, vp, i64, i32, i32, vp]
         L.c3d_linear_wgrad.restype = i32
         L.c3d_linear_wgrad.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]
+        L.c3d_linear_fwd_blocks.restype = i32
+        L.c3d_linear_fwd_blocks.argtypes = [vp, vp, vp, vp, i32, i32, i64, i32, i32, i32, i32, vp]
+        L.c3d_linear_dgrad_blocks.restype = i32
+        L.c3d_linear_dgrad_blocks.argtypes = [vp, vp, vp, i32, i32, i64, i32, i32, i32, vp]
+        L.c3d_linear_wgrad_blocks.restype = i32
+        L.c3d_linear_wgrad_blocks.argtypes = [vp, vp, vp, i32, i32, i64, i32, i32, i32, i32, i32, vp]
         _bound = True
     return L
 
@@ -69,7 +75,7 @@ def make_desc(x, w, stride=1, pad=0, relu=False, out_fp32=False, add_mode=0):
     N, H, W, Cin = x.shape
     Cout, KH, KW, Cin2 = w.shape
     assert Cin == Cin2, (x.shape, w.shape)
-    return ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, int(relu), int(out_fp32), add_mode, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+    return ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, int(relu), int(out_fp32), add_mode, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
 
 
 def num_tiles(desc):
@@ -130,7 +136,7 @@ def conv2d_wgrad(x, dy, KH, KW, stride=1, pad=0, dw=None, oihw=False):
     assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
     if dw is None:
         dw = torch.zeros((Cout, Cin, KH, KW) if oihw else (Cout, KH, KW, Cin), device=x.device, dtype=torch.float32)
-    d = ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+    d = ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
     _lib.check(L.c3d_conv2d_wgrad_ex(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), int(oihw), _stream()))
     return dw
 
@@ -183,4 +189,37 @@ def linear_wgrad(x, dy, dw=None, chw=None, master_chw=True):
     C, PP = chw if chw is not None else (Kdim, 1)
     _lib.check(L.c3d_linear_wgrad(_ptr(x), _ptr(dy), _ptr(dw), rows, Kdim, N, C, PP, int(bool(master_chw and chw is not None)),
                                   _stream()))
+    return dw
+
+
+def linear_fwd_blocks(x, nseg, seg_rows, seg_stride, w, bias=None, relu=False, out_fp32=False):
+    """rows [b*seg_stride, b*seg_stride + seg_rows) of x (.., K), b < nseg, read in place -> dense (nseg*seg_rows, N)."""
+    L = _bind()
+    Kdim, N = x.shape[1], w.shape[0]
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and w.is_contiguous() and (nseg - 1) * seg_stride + seg_rows <= x.shape[0]
+    y = torch.empty((nseg * seg_rows, N), device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    _lib.check(L.c3d_linear_fwd_blocks(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), nseg, seg_rows, seg_stride, Kdim, N, int(relu),
+                                       int(out_fp32), _stream()))
+    return y
+
+
+def linear_dgrad_blocks(dy, wt, dx, nseg, seg_rows, seg_stride, accumulate=True):
+    """dx rows [b*seg_stride, +seg_rows) (+)= dy (nseg*seg_rows, N) . W, in place inside the larger dx (.., K)."""
+    L = _bind()
+    N, Kdim = dy.shape[1], wt.shape[0]
+    assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and dx.dtype == torch.bfloat16 and dx.is_contiguous()
+    assert dx.shape[1] == Kdim and (nseg - 1) * seg_stride + seg_rows <= dx.shape[0] and dy.shape[0] == nseg * seg_rows
+    _lib.check(L.c3d_linear_dgrad_blocks(_ptr(dy), _ptr(wt), _ptr(dx), nseg, seg_rows, seg_stride, N, Kdim, int(accumulate), _stream()))
+    return dx
+
+
+def linear_wgrad_blocks(x, dy, nseg, seg_rows, seg_stride, dw=None, chw=None, master_chw=True):
+    L = _bind()
+    Kdim, N = x.shape[1], dy.shape[1]
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
+    if dw is None:
+        dw = torch.zeros((N, Kdim), device=x.device, dtype=torch.float32)
+    C, PP = chw if chw is not None else (Kdim, 1)
+    _lib.check(L.c3d_linear_wgrad_blocks(_ptr(x), _ptr(dy), _ptr(dw), nseg, seg_rows, seg_stride, Kdim, N, C, PP,
+                                         int(bool(master_chw and chw is not None)), _stream()))
     return dw

@@ -222,6 +222,19 @@ C3D_HD void build_box_record(const float* __restrict__ corners, float* __restric
   }
 }
 
+// centre (mean of corners) + padded bounding radius only: the SAME arithmetic as build_box_record's sphere
+C3D_HD void box_sphere(const float* __restrict__ corners, float* sphere4) {
+  V3 c[8];
+  for (int i = 0; i < 8; ++i) c[i] = mk(corners[3 * i], corners[3 * i + 1], corners[3 * i + 2]);
+  V3 s = mk(0.f, 0.f, 0.f);
+  for (int i = 0; i < 8; ++i) s = s + c[i];
+  V3 bc = s / 8.0f;
+  float r2 = 0.0f;
+  for (int i = 0; i < 8; ++i) { V3 d = c[i] - bc; r2 = fmaxf(r2, dot(d, d)); }
+  sphere4[0] = bc.x; sphere4[1] = bc.y; sphere4[2] = bc.z;
+  sphere4[3] = sqrtf(r2) * 1.0009765625f + 1e-6f;
+}
+
 // Row validity of a dt box (omni3d_evaluation.py:65-104): returns bit0 = coplanar_ok,
 // bit1 = nonzero_ok.  NB the reference sums the six face offsets before abs() (:83-86).
 C3D_HD int check_box(const float* __restrict__ corners, float eps_coplanar, float eps_nonzero) {

@@ -61,6 +61,44 @@ __global__ void iou3d_prep_kernel(const float* __restrict__ b1, int n1, const fl
   }
 }
 
+// Paired mode (pair k = boxes1[k] x boxes2[k]): every box belongs to exactly one pair, so building the 256-byte record of a
+// box whose pair is rejected by the bounding-sphere test is wasted work and wasted HBM traffic (272 B written per box vs
+// 96 B read) — in the sparse regime that is ~all of them.  One thread per PAIR: both spheres from the raw corners, the test,
+// and the two records only for surviving pairs; rejected pairs get a NaN radius so that the pair kernel's own sphere test
+// (d2 <= (r1+r2)^2) fails without reading anything else.  Traffic per rejected pair: 192 B in + 32 B + 32 B + 8..12 B out.
+__global__ void iou3d_prep_paired_kernel(const float* __restrict__ b1, const float* __restrict__ b2, int n,
+                                         float* __restrict__ rec, float4* __restrict__ sph, Ctrl* ctrl) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) { ctrl->next_chunk = 0; ctrl->n_overflow = 0; ctrl->next_overflow = 0; }
+  if (k >= n) return;
+  const float* s1 = b1 + 24 * (size_t)k;
+  const float* s2 = b2 + 24 * (size_t)k;
+  float c1[4], c2[4];
+  box_sphere(s1, c1);
+  box_sphere(s2, c2);
+  const float dx = c1[0] - c2[0], dy = c1[1] - c2[1], dz = c1[2] - c2[2];
+  const float rs = c1[3] + c2[3];
+  const bool live = (dx * dx + dy * dy + dz * dz) <= rs * rs;
+  if (!live) {
+    const float qnan = __int_as_float(0x7fc00000);
+    sph[k] = make_float4(0.f, 0.f, 0.f, qnan);
+    sph[n + k] = make_float4(0.f, 0.f, 0.f, qnan);
+    return;
+  }
+  float r[kRecFloats];
+  float s4[4];
+  build_box_record(s1, r, s4);
+  float4* dst = reinterpret_cast<float4*>(rec + (size_t)k * kRecFloats);
+#pragma unroll
+  for (int q = 0; q < kRecFloats / 4; ++q) dst[q] = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+  sph[k] = make_float4(s4[0], s4[1], s4[2], s4[3]);
+  build_box_record(s2, r, s4);
+  dst = reinterpret_cast<float4*>(rec + (size_t)(n + k) * kRecFloats);
+#pragma unroll
+  for (int q = 0; q < kRecFloats / 4; ++q) dst[q] = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+  sph[n + k] = make_float4(s4[0], s4[1], s4[2], s4[3]);
+}
+
 __global__ void iou3d_count_bad_kernel(const uint8_t* __restrict__ rowflags, int n1, Ctrl* ctrl,
                                        int* __restrict__ n_bad_out) {
   // single block; tiny
@@ -404,8 +442,12 @@ static int32_t run_iou(const float* b1, int64_t n1, const float* b2, int64_t n2,
   float4* sph = reinterpret_cast<float4*>(w + L.sph);
   uint8_t* flags = reinterpret_cast<uint8_t*>(w + L.flags);
   int nb = (int)(n1 + m2);
-  iou3d_prep_kernel<<<(nb + 127) / 128, 128, 0, st>>>(b1, (int)n1, b2, (int)m2, rec, sph, flags, eps_c,
-                                                      eps_nz, do_check ? 1 : 0, ctrl);
+  static const bool paired_lazy = getenv("C3D_IOU_PAIRED_EAGER_PREP") == nullptr;
+  if (paired && !do_check && !seg && paired_lazy)
+    iou3d_prep_paired_kernel<<<((int)n1 + 127) / 128, 128, 0, st>>>(b1, b2, (int)n1, rec, sph, ctrl);
+  else
+    iou3d_prep_kernel<<<(nb + 127) / 128, 128, 0, st>>>(b1, (int)n1, b2, (int)m2, rec, sph, flags, eps_c,
+                                                        eps_nz, do_check ? 1 : 0, ctrl);
   if (do_check) iou3d_count_bad_kernel<<<1, 256, 0, st>>>(flags, (int)n1, ctrl, n_bad);
   if (npairs > 0) {
     PairArgs A;

@@ -76,7 +76,10 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& P, const u
   long long apix = 0;
   if (P.add_mode == 1) apix = lpix;
   else if (P.add_mode == 2) apix = ((long long)img * (P.Ho >> 1) + (ho >> 1)) * (P.Wo >> 1) + (wo >> 1);
-  constexpr bool kStaged = BLOCK_N >= 64;
+  // measured (profiles/r02): the staged store is SLOWER than direct 2 x 16-byte row stores (1x1 64->256 @160: 0.38 -> 0.72 ms;
+  // the write path merges the two half-sector stores, the extra shuffles / shared-memory round trip only add latency to a
+  // latency-bound epilogue) — compiled out, kept for the record
+  constexpr bool kStaged = false && BLOCK_N >= 64;
   uint8_t* stg = stg_all + q * 4096;
   constexpr int kChunks = (BLOCK_N + 15) / 16;
 #pragma unroll 1
@@ -716,7 +719,8 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   CUtensorMap mx, mw;
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-    cuuint64_t strides[3] = {(cuuint64_t)xps * 2, (cuuint64_t)xps * 2 * d->W, (cuuint64_t)xps * 2 * d->W * d->H};
+    cuuint64_t strides[3] = {(cuuint64_t)xps * 2, (cuuint64_t)xps * 2 * d->W,
+                             (cuuint64_t)xps * 2 * (d->x_img_stride ? d->x_img_stride : (long long)d->W * d->H)};
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(P.TW * d->stride), (cuuint32_t)(P.TH * d->stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
     CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
@@ -812,8 +816,10 @@ static int32_t wgrad_impl(const c3d_conv_desc* d, const void* x, const void* dy,
   int rh64, rw64;
   const double eff128 = pick_tile_k(Ho, Wo, d->stride, &P.RH, &P.RW, 128);
   const double eff64 = pick_tile_k(Ho, Wo, d->stride, &rh64, &rw64, 64);
-  static const bool force128 = getenv("C3D_WGRAD_PIX128") != nullptr;
-  const bool pix64 = !force128 && eff64 >= 0.93 * eff128;
+  // measured (profiles/r02): the 4 x 64-pixel pipeline is SLOWER (fpn 3x3 @160: 0.92 -> 1.83 ms) — the loop is bound by the
+  // per-stage barrier round trip of the single MMA-issuing lane, not by TMA latency; kept as an opt-in experiment
+  static const bool want64 = getenv("C3D_WGRAD_PIX64") != nullptr;
+  const bool pix64 = want64 && eff64 >= 0.93 * eff128;
   if (pix64) { P.RH = rh64; P.RW = rw64; }
   P.tiles_h = (Ho + P.RH - 1) / P.RH; P.tiles_w = (Wo + P.RW - 1) / P.RW;
   P.num_tiles = d->N * P.tiles_h * P.tiles_w;
@@ -853,7 +859,8 @@ static int32_t wgrad_impl(const c3d_conv_desc* d, const void* x, const void* dy,
   }
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-    cuuint64_t strides[3] = {(cuuint64_t)xps * 2, (cuuint64_t)xps * 2 * d->W, (cuuint64_t)xps * 2 * d->W * d->H};
+    cuuint64_t strides[3] = {(cuuint64_t)xps * 2, (cuuint64_t)xps * 2 * d->W,
+                             (cuuint64_t)xps * 2 * (d->x_img_stride ? d->x_img_stride : (long long)d->W * d->H)};
     cuuint32_t box[4] = {(cuuint32_t)P.cw, (cuuint32_t)(P.RW * d->stride), (cuuint32_t)(P.RH * d->stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
     CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
@@ -953,6 +960,41 @@ extern "C" int32_t c3d_linear_dgrad(const void* dy, const void* wt, void* dx, in
   c3d_conv_desc d;
   linear_desc(&d, rows, N, K, 0, 0);           // dx (rows, K) = dy (rows, N) . W  ==  1x1 conv with weight W^T (K, N)
   return c3d_conv2d_fwd(&d, dy, wt, nullptr, nullptr, dx, nullptr, stream);
+}
+
+extern "C" int32_t c3d_linear_fwd_blocks(const void* x, const void* w, const float* bias, void* y, int32_t nseg,
+                                         int32_t seg_rows, int64_t seg_stride, int32_t K, int32_t N, int32_t relu,
+                                         int32_t out_fp32, void* stream) {
+  if (nseg <= 0 || seg_rows <= 0) return C3D_OK;
+  if (seg_stride < seg_rows) return set_error(C3D_EINVAL, "linear blocks: seg_stride < seg_rows");
+  c3d_conv_desc d;
+  linear_desc(&d, seg_rows, K, N, relu, out_fp32);
+  d.N = nseg; d.x_img_stride = seg_stride;
+  return c3d_conv2d_fwd(&d, x, w, bias, nullptr, y, nullptr, stream);
+}
+
+extern "C" int32_t c3d_linear_dgrad_blocks(const void* dy, const void* wt, void* dx, int32_t nseg, int32_t seg_rows,
+                                           int64_t seg_stride, int32_t N, int32_t K, int32_t accumulate, void* stream) {
+  if (nseg <= 0 || seg_rows <= 0) return C3D_OK;
+  if (seg_stride < seg_rows) return set_error(C3D_EINVAL, "linear blocks: seg_stride < seg_rows");
+  c3d_conv_desc d;
+  linear_desc(&d, seg_rows, N, K, 0, 0);
+  d.N = nseg;
+  d.y_img_stride = seg_stride; d.y_h_stride = seg_rows; d.y_w_stride = 1; d.y_offset = 0;   // rows of block b start at b*seg_stride
+  d.add_mode = accumulate ? 3 : 0;
+  return c3d_conv2d_fwd(&d, dy, wt, nullptr, nullptr, dx, nullptr, stream);
+}
+
+extern "C" int32_t c3d_linear_wgrad_blocks(const void* x, const void* dy, float* dw, int32_t nseg, int32_t seg_rows,
+                                           int64_t seg_stride, int32_t K, int32_t N, int32_t C, int32_t PP,
+                                           int32_t master_chw, void* stream) {
+  if (nseg <= 0 || seg_rows <= 0) return C3D_OK;
+  if (seg_stride < seg_rows) return set_error(C3D_EINVAL, "linear blocks: seg_stride < seg_rows");
+  if (C <= 0 || PP <= 0) { C = K; PP = 1; }
+  c3d_conv_desc d;
+  linear_desc(&d, seg_rows, K, N, 0, 0);
+  d.N = nseg; d.x_img_stride = seg_stride;
+  return wgrad_impl(&d, x, dy, dw, master_chw ? 1 : 0, stream, C, PP);
 }
 
 extern "C" int32_t c3d_linear_wgrad(const void* x, const void* dy, float* dw, int64_t rows, int32_t K, int32_t N,

@@ -133,10 +133,10 @@ bn_apply_kernel(const bf16* __restrict__ y, const float* __restrict__ mean, cons
     if (residual) {
       V8 r = ld8(residual + p * res_stride + c);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] = (a.v[k] - m[k]) * sc[k] + bt[k] + r.v[k];
+      for (int k = 0; k < 8; ++k) o.v[k] = __fmaf_rn(a.v[k] - m[k], sc[k], bt[k]) + r.v[k];
     } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] = (a.v[k] - m[k]) * sc[k] + bt[k];
+      for (int k = 0; k < 8; ++k) o.v[k] = __fmaf_rn(a.v[k] - m[k], sc[k], bt[k]);
     }
     if (relu) {
 #pragma unroll
@@ -152,7 +152,10 @@ template <int THREADS>
 __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out,
                                      const bf16* __restrict__ y, const float* __restrict__ mean,
                                      const float* __restrict__ rstd, int relu, float* __restrict__ partial,
-                                     long long P, int C, long long dout_stride, long long out_stride) {
+                                     long long P, int C, long long dout_stride, long long out_stride,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta) {
+  // `out == nullptr` with relu: the layer has no residual, so its ReLU mask is a function of y alone — recompute
+  // out = fma(y - mean, rstd*gamma, beta) exactly as bn_apply_kernel did instead of reading 2 more bytes per element
   // thread layout: tx = channel-vector index (C/8 of them), rows strided by (THREADS / cv)
   const int cv = C >> 3;
   const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
@@ -161,14 +164,21 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* 
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s[k] = 0.f; t[k] = 0.f; }
   const int c = tx << 3;
-  float m[8], rs[8];
+  float m[8], rs[8], sc[8], bt[8];
+  const bool remask = relu && out == nullptr;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { m[k] = mean[c + k]; rs[k] = rstd[c + k]; }
+  for (int k = 0; k < 8; ++k) {
+    m[k] = mean[c + k]; rs[k] = rstd[c + k];
+    sc[k] = remask ? rs[k] * gamma[c + k] : 0.f; bt[k] = remask ? beta[c + k] : 0.f;
+  }
   if (ty < rows_per_block) {
     for (long long p = (long long)blockIdx.x * rows_per_block + ty; p < P; p += (long long)gridDim.x * rows_per_block) {
       V8 d = ld8(dout + p * dout_stride + c);
       V8 yy = ld8(y + p * C + c);
-      if (relu) {
+      if (remask) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (!(__fmaf_rn(yy.v[k] - m[k], sc[k], bt[k]) > 0.f)) d.v[k] = 0.f;
+      } else if (relu) {
         V8 o = ld8(out + p * out_stride + c);
 #pragma unroll
         for (int k = 0; k < 8; ++k) if (!(o.v[k] > 0.f)) d.v[k] = 0.f;
@@ -213,23 +223,29 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out, const bf16* __restrict__ y,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ coef, int relu,
                     bf16* __restrict__ dy, bf16* __restrict__ dres, long long P, int C, long long dout_stride,
-                    long long out_stride, long long dres_stride) {
+                    long long out_stride, long long dres_stride, const float* __restrict__ gamma,
+                    const float* __restrict__ beta) {
   const int cv = C >> 3;
   const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
   const int rows_per_block = blockDim.x / cv;
   if (ty >= rows_per_block) return;
   const int c = tx << 3;
-  float m[8], rs[8], c0[8], c1[8], c2[8];
+  float m[8], rs[8], c0[8], c1[8], c2[8], sc[8], bt[8];
+  const bool remask = relu && out == nullptr;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     m[k] = mean[c + k]; rs[k] = rstd[c + k];
     c0[k] = coef[c + k]; c1[k] = coef[C + c + k]; c2[k] = coef[2 * C + c + k];
+    sc[k] = remask ? rs[k] * gamma[c + k] : 0.f; bt[k] = remask ? beta[c + k] : 0.f;
   }
   const long long step = (long long)gridDim.x * rows_per_block;
   for (long long p = (long long)blockIdx.x * rows_per_block + ty; p < P; p += step) {
     V8 d = ld8(dout + p * dout_stride + c);
     V8 yy = ld8(y + p * C + c);
-    if (relu) {
+    if (remask) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if (!(__fmaf_rn(yy.v[k] - m[k], sc[k], bt[k]) > 0.f)) d.v[k] = 0.f;
+    } else if (relu) {
       V8 o = ld8(out + p * out_stride + c);
 #pragma unroll
       for (int k = 0; k < 8; ++k) if (!(o.v[k] > 0.f)) d.v[k] = 0.f;
@@ -588,21 +604,21 @@ extern "C" int32_t c3d_bn_bwd_blocks(int64_t P, int32_t C) {
   return (int32_t)b;
 }
 extern "C" int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, const float* mean, const float* rstd,
-                              const float* gamma, int32_t relu, int32_t frozen_stats, float* partial /*[blocks][2][C]*/,
-                              float* coef /*[3][C]*/,
+                              const float* gamma, const float* beta, int32_t relu, int32_t frozen_stats,
+                              float* partial /*[blocks][2][C]*/, float* coef /*[3][C]*/,
                               float* dgamma, float* dbeta, void* dy, void* dres, int64_t P, int32_t C,
                               int64_t dout_stride, int64_t out_stride, int64_t dres_stride, void* scratch,
                               void* stream) {
   C3D_REQ(dout && y && mean && rstd && gamma && partial && coef && dy && scratch && C % 8 == 0 && C <= 2048,
           "bn_bwd: bad args");
-  C3D_REQ(!relu || out, "bn_bwd: relu needs the forward output");
+  C3D_REQ(!relu || out || beta, "bn_bwd: relu needs the forward output, or beta to recompute its sign from y");
   if (P == 0) return C3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = c3d_bn_bwd_blocks(P, C);
   const long long ds = dout_stride ? dout_stride : C, os = out_stride ? out_stride : C;
   if (C / 8 <= 256)
     bn_bwd_reduce_kernel<256><<<blocks, 256, 0, st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)y, mean, rstd,
-                                                       relu, partial, P, C, ds, os);
+                                                       relu, partial, P, C, ds, os, gamma, beta);
   else
     return set_error(C3D_EINVAL, "bn_bwd: C too large");
   int slabs;
@@ -611,7 +627,7 @@ extern "C" int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, 
                                                        dgamma, dbeta, frozen_stats);
   bn_bwd_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)y,
                                                                    mean, rstd, coef, relu, (bf16*)dy, (bf16*)dres, P, C,
-                                                                   ds, os, dres_stride ? dres_stride : C);
+                                                                   ds, os, dres_stride ? dres_stride : C, gamma, beta);
   return check_launch("bn_bwd");
 }
 extern "C" int32_t c3d_maxpool2_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,

@@ -66,29 +66,61 @@ __global__ void nms_mask_kernel(const float4* __restrict__ boxes, const int* __r
   }
 }
 
+// Greedy scan of one score-ordered list of m rows by ONE warp, 64 rows at a time: the chunk's own keeps are resolved from
+// its diagonal mask word alone (64 register-only steps: one shuffle each), then the kept rows' remaining words are OR-ed
+// into the live "removed" bitset (word w on lane w % 32, slot w / 32) with independent, pipelined loads — instead of one
+// dependent global load per kept row (a 1000-keep scan was ~0.7 ms of pure L2 latency).  Returns the keep mask of every
+// chunk through `emit(chunk, keepbits)`; stops after max_keep keeps.  rows: mask + row*words, only words >= row/64 valid.
+template <typename Emit>
+__device__ __forceinline__ int nms_scan_chunks(const unsigned long long* __restrict__ rows, int m, int words, int max_keep,
+                                               int lane, Emit emit) {
+  unsigned long long r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+  const int wc = (m + 63) >> 6;
+  int cnt = 0;
+  for (int c = 0; c < wc && cnt < max_keep; ++c) {
+    const int base = c << 6, nrows = min(64, m - base);
+    const unsigned long long d0 = lane < nrows ? rows[(size_t)(base + lane) * words + c] : 0ull;
+    const unsigned long long d1 = lane + 32 < nrows ? rows[(size_t)(base + lane + 32) * words + c] : 0ull;
+    const int slot = c >> 5, owner = c & 31;
+    unsigned long long cur = slot == 0 ? r0 : (slot == 1 ? r1 : (slot == 2 ? r2 : r3));
+    cur = __shfl_sync(0xffffffffu, cur, owner);
+    unsigned long long keep = 0ull;
+    int room = max_keep - cnt;
+    for (int i = 0; i < nrows && room > 0; ++i) {
+      const unsigned long long di = __shfl_sync(0xffffffffu, i < 32 ? d0 : d1, i & 31);
+      if (!((cur >> i) & 1ull)) { keep |= 1ull << i; cur |= di; --room; }
+    }
+    emit(c, keep);
+    cnt += __popcll(keep);
+    // OR the kept rows' later words into the live bitset
+    unsigned long long k = keep;
+    while (k) {
+      const int i = __ffsll((long long)k) - 1;
+      k &= k - 1;
+      const unsigned long long* row = rows + (size_t)(base + i) * words;
+      int ww = lane;
+      if (ww > c && ww < wc) r0 |= row[ww];
+      ww = lane + 32; if (ww > c && ww < wc) r1 |= row[ww];
+      ww = lane + 64; if (ww > c && ww < wc) r2 |= row[ww];
+      ww = lane + 96; if (ww > c && ww < wc) r3 |= row[ww];
+    }
+  }
+  return cnt;
+}
+
 __global__ void nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ nvalid, int n,
                                 int words, int max_keep, int* __restrict__ keep_idx, int* __restrict__ keep_cnt) {
   const int b = blockIdx.x, lane = threadIdx.x;
   const int nv = nvalid[b];
-  unsigned long long r0 = 0, r1 = 0, r2 = 0, r3 = 0;     // removed bits: word w lives on lane w%32, slot w/32
-  int cnt = 0;
   int* out = keep_idx + (size_t)b * max_keep;
-  for (int i = 0; i < nv && cnt < max_keep; ++i) {
-    const int w = i >> 6, slot = w >> 5, owner = w & 31;
-    unsigned long long word = slot == 0 ? r0 : (slot == 1 ? r1 : (slot == 2 ? r2 : r3));
-    word = __shfl_sync(0xffffffffu, word, owner);
-    if (!((word >> (i & 63)) & 1ULL)) {
-      if (lane == 0) out[cnt] = i;
-      ++cnt;
-      const unsigned long long* row = mask + ((size_t)b * n + i) * words;
-      // only words >= w were written by kernel 1 (upper triangle)
-      int ww = lane;
-      if (ww >= w && ww < words) r0 |= row[ww];
-      ww = lane + 32; if (ww >= w && ww < words) r1 |= row[ww];
-      ww = lane + 64; if (ww >= w && ww < words) r2 |= row[ww];
-      ww = lane + 96; if (ww >= w && ww < words) r3 |= row[ww];
-    }
-  }
+  int written = 0;
+  const int cnt = nms_scan_chunks(mask + (size_t)b * n * words, nv, words, max_keep, lane, [&](int c, unsigned long long keep) {
+    // survivors of this chunk, in order: lane l owns rows l and l + 32
+    const unsigned lo = (unsigned)keep, hi = (unsigned)(keep >> 32);
+    if ((lo >> lane) & 1u) out[written + __popc(lo & ((1u << lane) - 1u))] = (c << 6) + lane;
+    if ((hi >> lane) & 1u) out[written + __popc(lo) + __popc(hi & ((1u << lane) - 1u))] = (c << 6) + 32 + lane;
+    written += __popcll(keep);
+  });
   for (int k = cnt + lane; k < max_keep; k += 32) out[k] = -1;
   if (lane == 0) keep_cnt[b] = cnt;
 }
@@ -180,24 +212,12 @@ __global__ void nms_scan_grouped_kernel(const unsigned long long* __restrict__ m
   const int b = blockIdx.x / ncat, c = blockIdx.x % ncat, lane = threadIdx.x;
   const int off = cat_off[(size_t)b * (kMaxCat + 1) + c], m = cat_off[(size_t)b * (kMaxCat + 1) + c + 1] - off;
   if (m <= 0) return;
-  const int wc = (m + 63) / 64;
-  unsigned long long r0 = 0, r1 = 0, r2 = 0, r3 = 0;     // removed bits: word w lives on lane w%32, slot w/32
-  int cnt = 0;
-  for (int i = 0; i < m && cnt < max_keep; ++i) {
-    const int w = i >> 6, slot = w >> 5, owner = w & 31;
-    unsigned long long word = slot == 0 ? r0 : (slot == 1 ? r1 : (slot == 2 ? r2 : r3));
-    word = __shfl_sync(0xffffffffu, word, owner);
-    if (!((word >> (i & 63)) & 1ULL)) {
-      if (lane == 0) keepflag[(size_t)b * n + perm[(size_t)b * n + off + i]] = 1;
-      ++cnt;
-      const unsigned long long* row = mask + ((size_t)b * n + off + i) * words;
-      int ww = lane;
-      if (ww >= w && ww < wc) r0 |= row[ww];
-      ww = lane + 32; if (ww >= w && ww < wc) r1 |= row[ww];
-      ww = lane + 64; if (ww >= w && ww < wc) r2 |= row[ww];
-      ww = lane + 96; if (ww >= w && ww < wc) r3 |= row[ww];
-    }
-  }
+  const int* pm = perm + (size_t)b * n + off;
+  unsigned char* kf = keepflag + (size_t)b * n;
+  nms_scan_chunks(mask + ((size_t)b * n + off) * words, m, words, max_keep, lane, [&](int c, unsigned long long keep) {
+    if ((keep >> lane) & 1ull) kf[pm[(c << 6) + lane]] = 1;
+    if ((keep >> (lane + 32)) & 1ull) kf[pm[(c << 6) + 32 + lane]] = 1;
+  });
 }
 
 __global__ void nms_compact_kernel(const unsigned char* __restrict__ keepflag, const int* __restrict__ nvalid, int n,

@@ -208,6 +208,7 @@ class FPN(nn.Module):
                 nn.init.constant_(m.bias, 0)
             self.add_module("fpn_lateral%d" % s, lat)
             self.add_module("fpn_output%d" % s, out)
+        self.split_backward, self.cut = False, None
         self.size_divisibility = bottom_up.strides[in_features[-1]]
         self._out_features = ["p%d" % s for s in self.stages]
         self.out_strides = {"p%d" % s: 2 ** s for s in self.stages}
@@ -216,6 +217,13 @@ class FPN(nn.Module):
 
     def forward(self, x):
         feats = self.bottom_up(x)
+        self.cut = None
+        if self.split_backward and torch.is_grad_enabled():
+            # FlatSGDTrainer's two-stage backward: the autograd graph is CUT at the bottom-up outputs — stage 1
+            # (loss.backward()) stops at detached leaves, stage 2 feeds their gradients into the backbone's own graph
+            leaves = {k: v.detach().requires_grad_(True) for k, v in feats.items()}
+            self.cut = (feats, leaves)
+            feats = leaves
         results, prev = {}, None
         for f, s in reversed(list(zip(self.in_features, self.stages))):
             lat, outc = getattr(self, "fpn_lateral%d" % s), getattr(self, "fpn_output%d" % s)

@@ -69,6 +69,24 @@ class RCNN3D(nn.Module):
     def device(self):
         return self.pixel_mean.device
 
+    late_parameter_prefix = "backbone.bottom_up."
+
+    def set_backward_cut(self, enable):
+        """FlatSGDTrainer (several ranks): cut the autograd graph at the bottom-up backbone's outputs so that
+        loss.backward() ends above the backbone and `backward_cut()` hands over the feature gradients for stage 2.
+        Never enable this without a trainer that runs stage 2 — the backbone would receive no gradient."""
+        self.backbone.split_backward = bool(enable)
+
+    def backward_cut(self):
+        """-> (bottom-up outputs, their gradients from stage 1) of the last forward, or None when the graph was not cut."""
+        cut = getattr(self.backbone, "cut", None)
+        if not cut:
+            return None
+        src, leaves = cut
+        self.backbone.cut = None
+        keys = [k for k in src if leaves[k].grad is not None]
+        return [src[k] for k in keys], [leaves[k].grad for k in keys]
+
     def preprocess_image(self, batched_inputs):
         st = self.stage_inputs(batched_inputs, with_gt=False)
         return self._normalize(st), st["sizes"]
@@ -131,7 +149,7 @@ class RCNN3D(nn.Module):
             if pre is not None:
                 torch.cuda.current_stream().wait_stream(self._side)
             proposals, l_rpn = self.proposal_generator(features, sizes, gt, sizes_dev=hw, prelabel=pre)
-            _, losses = self.roi_heads(features, proposals, sizes, Ks, ratios, gt, im_h=hw[:, 0])
+            _, losses = self.roi_heads(features, proposals, sizes, Ks, ratios, gt, im_h=hw[:, 0], meta=meta)
             losses.update(l_rpn)
             self.metrics = {**self.proposal_generator.stats, **self.roi_heads.stats}
             return losses

@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from ..nnfunc import LinearAct, ROIAlign
+from ..nnfunc import BoxLoss, CubeHeadLoss, LinearAct, ROIAlign, TwoHeadFC1
 from . import geometry as G
 from .registry import ROI_CUBE_HEAD_REGISTRY, ROI_HEADS_REGISTRY
 from .rpn import apply_deltas, get_deltas, gumbel_topk_sample, pairwise_ioa, pairwise_iou
@@ -37,8 +37,9 @@ def fc(x, lin, relu=False, chw=None, out_fp32=False):
 _zero_pad = {}
 
 
-def fused_predictors(h, lins, n_pad):
-    """several small nn.Linear predictors over the same features as ONE zero-padded GEMM -> list of fp32 outputs."""
+def fused_predictors(h, lins, n_pad, split=True):
+    """several small nn.Linear predictors over the same features as ONE zero-padded GEMM -> list of fp32 outputs
+    (split=False: the padded (rows, n_pad) fp32 output itself, columns in the order of `lins`)."""
     widths = [l.weight.shape[0] for l in lins]
     pad = n_pad - sum(widths)
     key = (pad, h.shape[1], h.device)
@@ -48,6 +49,8 @@ def fused_predictors(h, lins, n_pad):
     w = torch.cat([l.weight for l in lins] + [z[0]], 0)
     b = torch.cat([l.bias for l in lins] + [z[1]], 0)
     y = LinearAct.apply(h, w, b, False, True, None)
+    if not split:
+        return y
     out, o = [], 0
     for n in widths:
         out.append(y[:, o:o + n])
@@ -155,6 +158,7 @@ class ROIHeads3D(nn.Module):
         self.stats = {}
         self.fused_cube = True        # c3d_cube_loss_fwd/bwd; False = the batched torch fp32 formulation below
         self.fused_sampling = True    # c3d_label_sample_proposals; False = the batched torch formulation below
+        self.fused_head_losses = True  # c3d_box_loss_* / c3d_cube_gather|reduce|scatter; False = the torch loss assembly
         # torchvision.ops.batched_nms: coordinate trick up to this many box coordinates, per-class NMS above (CUDA value)
         self.nms_trick_max_numel = 20000
 
@@ -248,16 +252,27 @@ class ROIHeads3D(nn.Module):
         x = ROIAlign.apply(rois, tuple(self.strides), self.pooled, *feats)
         return x.reshape(B * S, -1)
 
-    def box_branch(self, x):
+    def box_branch(self, x, split=True, h1=None):
         C, P = self.in_channels, self.pooled
-        h = fc(x, self.box_head.fc1, relu=True, chw=(C, P * P))
+        h = fc(x, self.box_head.fc1, relu=True, chw=(C, P * P)) if h1 is None else h1
         k = 2
         while hasattr(self.box_head, "fc%d" % k):
             h = fc(h, getattr(self.box_head, "fc%d" % k), relu=True)
             k += 1
         n = self.box_predictor.cls_score.weight.shape[0] + self.box_predictor.bbox_pred.weight.shape[0]
-        scores, deltas = fused_predictors(h, [self.box_predictor.cls_score, self.box_predictor.bbox_pred], -(-n // 256) * 256)
-        return scores, deltas
+        out = fused_predictors(h, [self.box_predictor.cls_score, self.box_predictor.bbox_pred], -(-n // 256) * 256, split)
+        return out if not split else (out[0], out[1])
+
+    def box_losses_fused(self, pred, smp):
+        """BoxHead losses + logged accuracies from the fused predictor rows in one kernel each way (c3d_box_loss_*)."""
+        K = self.num_classes
+        o = BoxLoss.apply(pred, smp["classes"].reshape(-1), smp["valid"].reshape(-1), smp["boxes"].reshape(-1, 4),
+                          smp["gt_boxes"].reshape(-1, 4), K, self.box_weights)
+        with torch.no_grad():
+            d = o.detach()
+            self.stats["fast_rcnn/cls_accuracy"], self.stats["fast_rcnn/fg_cls_accuracy"] = d[2], d[3]
+            self.stats["fast_rcnn/false_negative"] = d[4]
+        return {"BoxHead/loss_cls": o[0], "BoxHead/loss_box_reg": o[1]}
 
     def box_losses(self, scores, deltas, smp):
         K = self.num_classes
@@ -298,6 +313,37 @@ class ROIHeads3D(nn.Module):
         ur = pick(outs[4], 1).squeeze(1)
         return dict(deltas=pick(outs[0], 2), dims=pick(outs[1], 3), pose6=pick(outs[2], 6),
                     z=pick(outs[3], 1).squeeze(1), uncert=ur.clip(0.01), uncert_raw=ur)
+
+    def cube_pred(self, x, h1=None):
+        """x (n, 7*7*C) bf16 -> the five K-way predictors as one fp32 (n, ld) GEMM output [deltas 2K | dims 3K | pose 6K | z K |
+        uncertainty K | pad] (cube_head.py:108-144 behind the shared FC stack :63-73)."""
+        ch, C, P = self.cube_head, self.in_channels, self.pooled
+        fg = ch.feature_generator
+        h = fc(x, fg.fc1, relu=True, chw=(C, P * P)) if h1 is None else h1
+        k = 2
+        while hasattr(fg, "fc%d" % k):
+            h = fc(h, getattr(fg, "fc%d" % k), relu=True)
+            k += 1
+        heads = [ch.bbox_3D_center_deltas, ch.bbox_3D_dims, ch.bbox_3D_pose, ch.bbox_3D_center_depth, ch.bbox_3D_uncertainty]
+        tot = sum(l.weight.shape[0] for l in heads)
+        return fused_predictors(h, heads, -(-tot // 256) * 256, split=False)
+
+    def cube_losses_kernel(self, pred, boxes, classes, valid, gt3, gtR, meta, per_image):
+        """the six Cube losses + logged statistics straight from the fused predictor output: gather / decode + disentangled
+        losses / masked finite means = 3 launches each way (CubeHeadLoss), instead of ~330 torch launches."""
+        w = self.w
+        prior = self.priors_dims_per_cat.detach()[0, :, 0, :]
+        o = CubeHeadLoss.apply(pred, classes, valid, boxes, meta, prior, gt3[:, :9], gtR.reshape(-1, 9), per_image,
+                               self.num_classes, float(self.virtual_focal))
+        w3 = w["w3d"]
+        losses = {"Cube/uncert": w["conf"] * o[0], "Cube/loss_dims": o[1] * (w["dims"] * w3), "Cube/loss_xy": o[2] * (w["xy"] * w3),
+                  "Cube/loss_z": o[3] * (w["z"] * w3), "Cube/loss_pose": o[4] * (w["pose"] * w3),
+                  "Cube/loss_joint": o[5] * (w["joint"] * w3)}
+        with torch.no_grad():
+            d = o.detach()
+            self.stats.update({"Cube/z_error": d[6], "Cube/dims_error": d[7], "Cube/xy_error": d[8], "Cube/z_close": d[9],
+                               "Cube/conf": d[10]})
+        return losses
 
     def decode(self, raw, boxes, classes, Kb, v2r):
         """roi_heads.py:409-525: 2D centre, dims (exp * prior), egocentric pose, metric depth."""
@@ -382,7 +428,7 @@ class ROIHeads3D(nn.Module):
         return rep(Ks_scaled), rep(v2r), rep(r)
 
     # -- forward ----------------------------------------------------------------------------------------
-    def forward(self, features, proposals, image_sizes, Ks, ratios, gt=None, im_h=None):
+    def forward(self, features, proposals, image_sizes, Ks, ratios, gt=None, im_h=None, meta=None):
         feats = [features[f] for f in self.in_features]
         prop_boxes, prop_scores, prop_count = proposals
         B = prop_boxes.shape[0]
@@ -392,16 +438,33 @@ class ROIHeads3D(nn.Module):
         if self.training:
             smp = self.label_and_sample_proposals(prop_boxes, prop_count, gt)
             x = self.pool(feats, smp["boxes"], smp["valid"])
-            scores, deltas = self.box_branch(x)
-            losses = self.box_losses(scores, deltas, smp)
-            Fc = smp["fcap"]
+            fused = self.fused_head_losses and meta is not None and self.fused_cube and x.is_cuda
+            Fc = min(smp["fcap"], smp["boxes"].shape[1])
+            hb1 = hc1 = None
+            if fused and self.share_pool and x.shape[0] == B * smp["boxes"].shape[1]:
+                # both heads' first FC layer on the ONE pooled tensor (the cube head's RoIs are rows [:Fc] of every image)
+                hb1, hc1 = TwoHeadFC1.apply(x, self.box_head.fc1.weight, self.box_head.fc1.bias,
+                                            self.cube_head.feature_generator.fc1.weight, self.cube_head.feature_generator.fc1.bias,
+                                            B, smp["boxes"].shape[1], Fc, (self.in_channels, self.pooled * self.pooled))
+            if fused:
+                losses = self.box_losses_fused(self.box_branch(x, split=False, h1=hb1), smp)
+            else:
+                scores, deltas = self.box_branch(x)
+                losses = self.box_losses(scores, deltas, smp)
             K = self.num_classes
             fb, fc_, fv = smp["boxes"][:, :Fc], smp["classes"][:, :Fc], smp["valid"][:, :Fc]
             fv = fv & (fc_ >= 0) & (fc_ < K)
-            if self.share_pool:
+            if hc1 is not None:
+                xc = None
+            elif self.share_pool:
                 xc = x.view(B, -1, x.shape[-1])[:, :Fc].reshape(B * Fc, -1)
             else:
                 xc = self.pool(feats, fb, fv)
+            if fused:
+                losses.update(self.cube_losses_kernel(self.cube_pred(xc, h1=hc1), fb.reshape(-1, 4), fc_.reshape(-1), fv.reshape(-1),
+                                                      smp["gt_boxes3D"][:, :Fc].reshape(-1, 9),
+                                                      smp["gt_poses"][:, :Fc].reshape(-1, 3, 3), meta, Fc))
+                return None, losses
             Kb, v2r, _ = self.per_box_camera(Ks, ratios, im_h, Fc, B, dev)
             raw = self.cube_outputs(xc, fc_.reshape(-1))
             cube_fn = self.cube_losses_fused if self.fused_cube else self.cube_losses

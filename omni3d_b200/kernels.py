@@ -37,7 +37,7 @@ def _bind():
         "c3d_bn_finalize": [vp, i32, i32, f64, f32, f32, vp, vp, vp, vp, vp, vp],
         "c3d_bn_apply": [vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i64, i64, vp],
         "c3d_bn_bwd_blocks": [i64, i32],
-        "c3d_bn_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, vp, vp],
+        "c3d_bn_bwd": [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, vp, vp],
         "c3d_maxpool2_fwd": [vp, vp, i32, i32, i32, i32, i64, i64, vp],
         "c3d_maxpool2_bwd": [vp, vp, vp, i32, i32, i32, i32, i64, i64, vp],
         "c3d_preprocess_image": [vp, i32, i32, vp, i32, i32, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), vp],
@@ -69,6 +69,12 @@ def _bind():
     sig["c3d_topk_segments"] = [ctypes.POINTER(TopkSeg), i32, i32, i32, vp, vp, vp, vp, vp]
     sig["c3d_label_sample_proposals"] = [ctypes.POINTER(LabelSampleArgs), vp]
     sig["c3d_anchor_sample_keys"] = [vp, vp, i32, i64, vp, vp, vp, vp]
+    sig["c3d_box_loss_fwd"] = [vp, i32, vp, vp, vp, vp, i32, i32, ctypes.POINTER(f32), vp, vp]
+    sig["c3d_box_loss_bwd"] = [vp, i32, vp, vp, vp, vp, i32, i32, ctypes.POINTER(f32), vp, vp, vp, vp]
+    sig["c3d_cube_gather"] = [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp]
+    sig["c3d_cube_reduce_fwd"] = [vp, vp, i32, vp, vp, vp]
+    sig["c3d_cube_reduce_bwd"] = [vp, vp, i32, vp, vp, vp, vp]
+    sig["c3d_cube_scatter"] = [vp, vp, i32, i32, i32, vp, vp]
     sig["c3d_det_candidates"] = [vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]
     sig["c3d_anchor_sample_finish"] = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, i32, i32, f32, vp, vp, vp]
     for name, args in sig.items():
@@ -123,7 +129,7 @@ def pixel_stride(t):
     return s
 
 
-def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres, frozen=False):
+def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres, frozen=False, beta=None):
     """-> dy (bf16, like y), dres (bf16 or None); dgamma/dbeta (fp32 [C]) are accumulated in place.  `dout` may be a
     channel slice of a wider NHWC gradient (read in place through its pixel stride)."""
     L = _bind()
@@ -138,7 +144,7 @@ def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres, froz
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
     scratch = torch.empty(128 * 2 * C, device=y.device, dtype=torch.float64)
-    _lib.check(L.c3d_bn_bwd(_p(dout), _p(out), _p(y), _p(mean), _p(rstd), _p(gamma), int(relu), int(frozen), _p(partial), _p(coef),
+    _lib.check(L.c3d_bn_bwd(_p(dout), _p(out), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), int(relu), int(frozen), _p(partial), _p(coef),
                             _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, ds, 0, 0, _p(scratch), _st()), launches=4)
     return dy, dres
 
@@ -508,3 +514,60 @@ def det_candidates(probs, boxes, prop_count, image_hw, score_thresh):
                                     _p(image_hw.contiguous().float()), B, P, K, float(score_thresh), _p(cs), _p(cb), _p(maxc),
                                     _p(total), _st()))
     return cs, cb, maxc, total
+
+
+# ---- head losses (head_loss_ops.cu) -----------------------------------------------------------------------------------
+def box_loss_fwd(pred, classes, valid, boxes, gt_boxes, K, weights):
+    """pred (R, ld) fp32 rows [K+1 scores | 4K deltas | pad] -> acc (8,) fp32 [sum CE, sum L1(fg), #valid, #fg, #correct,
+    #fg correct, #fg predicted background, 0] (fast_rcnn.py:145-194)."""
+    L = _bind()
+    R, ld = pred.shape
+    acc = torch.empty(8, dtype=torch.float32, device=pred.device)
+    w = (f32 * 4)(*[float(v) for v in weights])
+    _lib.check(L.c3d_box_loss_fwd(_p(pred), ld, _p(classes), _p(valid), _p(boxes), _p(gt_boxes), R, int(K), w, _p(acc), _st()))
+    return acc
+
+
+def box_loss_bwd(pred, classes, valid, boxes, gt_boxes, K, weights, acc, g2):
+    L = _bind()
+    R, ld = pred.shape
+    dpred = torch.empty_like(pred)
+    w = (f32 * 4)(*[float(v) for v in weights])
+    _lib.check(L.c3d_box_loss_bwd(_p(pred), ld, _p(classes), _p(valid), _p(boxes), _p(gt_boxes), R, int(K), w, _p(acc), _p(g2),
+                                  _p(dpred), _st()))
+    return dpred
+
+
+def cube_gather(pred, classes, boxes, meta, priors, gt3, gtR, per_image, K, virtual_focal):
+    """-> raw (n,13), aux (n,28): the inputs of c3d_cube_loss_fwd/bwd (roi_heads.py:372-461)."""
+    L = _bind()
+    n, ld = pred.shape
+    raw = torch.empty((n, 13), dtype=torch.float32, device=pred.device)
+    aux = torch.empty((n, 28), dtype=torch.float32, device=pred.device)
+    _lib.check(L.c3d_cube_gather(_p(pred), ld, _p(classes), _p(boxes), _p(meta), _p(priors), _p(gt3), _p(gtR), n, int(per_image),
+                                 int(K), float(virtual_focal), _p(raw), _p(aux), _st()))
+    return raw, aux
+
+
+def cube_reduce_fwd(rows, valid):
+    L = _bind()
+    sums = torch.empty(12, dtype=torch.float32, device=rows.device)
+    cnts = torch.empty(8, dtype=torch.float32, device=rows.device)
+    _lib.check(L.c3d_cube_reduce_fwd(_p(rows), _p(valid), rows.shape[0], _p(sums), _p(cnts), _st()))
+    return sums, cnts
+
+
+def cube_reduce_bwd(rows, valid, cnts, g6):
+    L = _bind()
+    n = rows.shape[0]
+    d = torch.empty((n, 6), dtype=torch.float32, device=rows.device)
+    _lib.check(L.c3d_cube_reduce_bwd(_p(rows), _p(valid), n, _p(cnts), _p(g6), _p(d), _st()))
+    return d
+
+
+def cube_scatter(draw, classes, K, ld):
+    L = _bind()
+    n = draw.shape[0]
+    dpred = torch.empty((n, ld), dtype=torch.float32, device=draw.device)
+    _lib.check(L.c3d_cube_scatter(_p(draw), _p(classes), n, int(K), int(ld), _p(dpred), _st()))
+    return dpred

@@ -149,8 +149,10 @@ class ConvBNAct(torch.autograd.Function):
         stride, pad, relu, training, has_res = ctx.cfg
         dgamma, ret_g = _grad_slot(gamma)
         dbeta, ret_b = _grad_slot(beta)
-        dy, dres = Kx.bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, has_res and ctx.needs_input_grad[6],
-                              frozen=not training)
+        # a ReLU layer without residual: its mask is recomputed from y inside the kernels (no read of `out`)
+        remask = relu and not has_res
+        dy, dres = Kx.bn_bwd(dout, None if remask else out, y, mean, rstd, gamma, relu, dgamma, dbeta,
+                              has_res and ctx.needs_input_grad[6], frozen=not training, beta=beta if remask else None)
         dx = _dgrad(dy, w, stride, pad, x.shape[1:3]) if ctx.needs_input_grad[0] else None
         dw = _wgrad_to_master(x, dy, w, stride, pad) if ctx.needs_input_grad[1] else None
         return (dx, dw, dgamma if ret_g else None, dbeta if ret_b else None, None, None, dres, None, None, None, None,
@@ -228,6 +230,52 @@ class LinearAct(torch.autograd.Function):
             else:
                 dw = K.linear_wgrad(x, dz, chw=chw)
         return dx, dw, dbias if ret_b else None, None, None, None
+
+
+class TwoHeadFC1(torch.autograd.Function):
+    """First FC layer of the box head over all B*S pooled RoIs and of the cube head over the first Fc RoIs of every image
+    (Base.yaml:66-68,78-80: same pooler => the cube head's RoIs are a prefix of the box head's sampled RoIs), sharing ONE
+    pooled tensor: the cube GEMM reads its rows in place (c3d_linear_fwd_blocks) and its data gradient is accumulated into
+    the box head's (c3d_linear_dgrad_blocks, in-place epilogue) — no gather copy forward, no zero-padded scatter + add
+    backward (~1 GB of HBM traffic per step at batch 32)."""
+
+    @staticmethod
+    def forward(ctx, x, wb, bb, wc, bc, B, S, Fc, chw):
+        x = x.contiguous()
+        wpb, wtb = _packed_linear(wb, chw)
+        wpc, wtc = _packed_linear(wc, chw)
+        hb = K.linear_fwd(x, wpb, bb.detach().float().contiguous(), relu=True)
+        hc = K.linear_fwd_blocks(x, B, Fc, S, wpc, bc.detach().float().contiguous(), relu=True)
+        ctx.save_for_backward(x, wb, bb, wc, bc, hb, hc, wtb, wtc)
+        ctx.cfg = (B, S, Fc, chw)
+        return hb, hc
+
+    @staticmethod
+    def backward(ctx, dhb, dhc):
+        x, wb, bb, wc, bc, hb, hc, wtb, wtc = ctx.saved_tensors
+        B, S, Fc, chw = ctx.cfg
+        if dhb is None:
+            dhb = torch.zeros_like(hb)
+        if dhc is None:
+            dhc = torch.zeros_like(hc)
+        gbb, rb = _grad_slot(bb)
+        gbc, rc = _grad_slot(bc)
+        dzb = Kx.bias_act_bwd(dhb, hb, True, gbb)
+        dzc = Kx.bias_act_bwd(dhc, hc, True, gbc)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = K.linear_dgrad(dzb, wtb)
+            K.linear_dgrad_blocks(dzc, wtc, dx, B, Fc, S, accumulate=True)
+
+        def wgrad(w, fn):
+            g = w.grad if w.is_leaf else None
+            if g is not None and g.dtype == torch.float32 and g.shape == w.shape and g.is_contiguous():
+                fn(g)
+                return None
+            return fn(None)
+        dwb = wgrad(wb, lambda g: K.linear_wgrad(x, dzb, dw=g, chw=chw))
+        dwc = wgrad(wc, lambda g: K.linear_wgrad_blocks(x, dzc, B, Fc, S, dw=g, chw=chw))
+        return dx, dwb, gbb if rb else None, dwc, gbc if rc else None, None, None, None, None
 
 
 class MaxPool2(torch.autograd.Function):
@@ -313,3 +361,56 @@ class RPNLossSums(torch.autograd.Function):
         dacc = dacc.contiguous().float()
         dl, dd = Kx.rpn_loss_bwd(logits, deltas, labels, matched_idx, gt_boxes, anchors, ctx.weights, dacc[0:1], dacc[1:2])
         return dl, dd, None, None, None, None, None
+
+
+class BoxLoss(torch.autograd.Function):
+    """FastRCNNOutputs.losses (fast_rcnn.py:145-194) on the fused predictor output rows [K+1 scores | 4K deltas | pad]:
+    -> (7,) [loss_cls, loss_box_reg, cls_accuracy, fg_cls_accuracy, false_negative, #valid, #fg]; gradients flow from the
+    first two entries (c3d_box_loss_fwd / _bwd, one launch each way)."""
+
+    @staticmethod
+    def forward(ctx, pred, classes, valid, boxes, gt_boxes, K, weights):
+        pred = pred.contiguous().float()
+        classes, valid = classes.contiguous().to(torch.int64), valid.contiguous().to(torch.uint8)
+        boxes, gt_boxes = boxes.contiguous().float(), gt_boxes.contiguous().float()
+        acc = Kx.box_loss_fwd(pred, classes, valid, boxes, gt_boxes, K, weights)
+        ctx.save_for_backward(pred, classes, valid, boxes, gt_boxes, acc)
+        ctx.cfg = (K, tuple(weights))
+        nv, nfg = acc[2].clamp(min=1.0), acc[3].clamp(min=1.0)
+        den = torch.stack([nv, nv, nv, nfg, nfg])
+        return torch.cat([acc[[0, 1, 4, 5, 6]] / den, acc[2:4]])
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, classes, valid, boxes, gt_boxes, acc = ctx.saved_tensors
+        K, weights = ctx.cfg
+        dpred = Kx.box_loss_bwd(pred, classes, valid, boxes, gt_boxes, K, weights, acc, g[:2].contiguous().float())
+        return dpred, None, None, None, None, None, None
+
+
+class CubeHeadLoss(torch.autograd.Function):
+    """fused cube-predictor output (n, ld) -> (11,) [Cube/uncert, loss_dims, loss_xy, loss_z, loss_pose, loss_joint (finite
+    means over valid RoIs, unweighted), z_error, dims_error, xy_error, z_close, conf]: gather of the predicted class's 13
+    outputs + the per-RoI constants (c3d_cube_gather), decode + disentangled losses (c3d_cube_loss_fwd), masked finite
+    means (c3d_cube_reduce_fwd); backward = the three adjoint kernels + scatter into the class's columns."""
+
+    @staticmethod
+    def forward(ctx, pred, classes, valid, boxes, meta, priors, gt3, gtR, per_image, K, virtual_focal):
+        pred = pred.contiguous().float()
+        classes, valid8 = classes.contiguous().to(torch.int64), valid.contiguous().to(torch.uint8)
+        raw, aux = Kx.cube_gather(pred, classes, boxes.contiguous().float(), meta.contiguous().float(), priors.contiguous().float(),
+                                  gt3.contiguous().float(), gtR.contiguous().float(), per_image, K, virtual_focal)
+        rows = Kx.cube_loss_fwd(raw, aux)
+        sums, cnts = Kx.cube_reduce_fwd(rows, valid8)
+        ctx.save_for_backward(raw, aux, rows, valid8, cnts, classes)
+        ctx.cfg = (K, pred.shape[1])
+        den = torch.cat([cnts[:6], cnts[6:7].expand(5)]).clamp(min=1.0)
+        return sums[:11] / den
+
+    @staticmethod
+    def backward(ctx, g):
+        raw, aux, rows, valid8, cnts, classes = ctx.saved_tensors
+        K, ld = ctx.cfg
+        drows = Kx.cube_reduce_bwd(rows, valid8, cnts, g[:6].contiguous().float())
+        draw = Kx.cube_loss_bwd(raw, aux, drows)
+        return Kx.cube_scatter(draw, classes, K, ld), None, None, None, None, None, None, None, None, None, None

@@ -90,6 +90,14 @@ class FlatSGDTrainer:
                 if wd not in (0.0, S.WEIGHT_DECAY):
                     raise NotImplementedError("per-group weight decay other than {0, WEIGHT_DECAY}")
                 groups["unused" if full in unused else ("decay" if wd > 0 else "nodecay")].append(p)
+        # gradient buckets for the overlapped all-reduce: parameters of the bottom-up backbone get their gradients LAST in the
+        # backward pass; everything else (FPN, RPN, heads: 2/3 of the bytes) is complete when the backbone's backward
+        # starts.  Arena = [decay early | decay late | nodecay late | nodecay early | unused] so that "late" is ONE range.
+        prefix = getattr(model, "late_parameter_prefix", "backbone.bottom_up.")
+        late = {p for n, p in model.named_parameters() if n.startswith(prefix)}
+        groups["decay"] = [p for p in groups["decay"] if p not in late] + [p for p in groups["decay"] if p in late]
+        groups["nodecay"] = [p for p in groups["nodecay"] if p in late] + [p for p in groups["nodecay"] if p not in late]
+        self._late = late
         order = groups["decay"] + groups["nodecay"] + groups["unused"]
         sizes = [p.numel() for p in order]
         pad = lambda n: (n + 63) // 64 * 64
@@ -102,6 +110,14 @@ class FlatSGDTrainer:
                 o += pad(p.numel())
             bounds[gname] = (start, o)
         self.bounds, total = bounds, o
+        pos = dict(zip(order, offs))
+        late_offs = [pos[p] for p in groups["decay"] + groups["nodecay"] if p in late]
+        d0, n1 = bounds["decay"][0], bounds["nodecay"][1]
+        lo = min(late_offs) if late_offs else n1
+        hi = max(pos[p] + pad(p.numel()) for p in late) if late_offs else n1
+        self.bucket_late = (lo, hi)                          # one contiguous range
+        self.bucket_early = [(d0, lo), (hi, n1)]             # decay-early | nodecay-early (usually empty)
+        self.early_params = [p for p in groups["decay"] + groups["nodecay"] if p not in late]
         self.flat_p = torch.zeros(total, device=dev)
         self.flat_g = torch.zeros(total, device=dev)
         self.flat_m = torch.zeros(total, device=dev)
@@ -143,6 +159,13 @@ class FlatSGDTrainer:
         self.graph_launches = 0
         self.recaptures = 0
         self.lr_dev = torch.zeros(1, device=dev)
+        # two-stage backward (gradient all-reduce of the early bucket overlapped with the backbone's backward): several ranks,
+        # or forced for tests; the model cuts its autograd graph at the bottom-up outputs when told to
+        self.split_backward = bool(late) and hasattr(model, "set_backward_cut") and \
+            (self.world > 1 or bool(os.environ.get("C3D_TRAIN_SPLIT_BACKWARD")))
+        if hasattr(model, "set_backward_cut"):
+            model.set_backward_cut(self.split_backward)
+        self._pending = self._works = self._graph_split = None
 
     # -------------------------------------------------------------------------------------------------
     def _seg_forward(self, staged):
@@ -165,7 +188,19 @@ class FlatSGDTrainer:
         losses = sum(loss_dict.values())
         losses = torch.where(diverging, losses.clip(0, 1), losses)
         losses.backward()
+        # with the backward cut enabled (several ranks) this was stage 1: everything above the bottom-up backbone — heads, RPN,
+        # FPN — whose gradients are final now; the backbone's backward (stage 2) runs while NCCL reduces them
+        cut = getattr(self.model, "backward_cut", None)
+        self._pending = cut() if (cut is not None and self.split_backward) else None
         return total_reduced, recent, diverging
+
+    def _seg_backward_late(self):
+        """stage 2: the backbone's backward, fed with the feature gradients of stage 1."""
+        if self._pending is not None:
+            feats, grads = self._pending
+            self._pending = None
+            if feats:
+                torch.autograd.backward(feats, grads)
 
     def _seg_update(self, vec, total_reduced, recent, diverging, lr):
         """segment C (gradients already summed over ranks): finite scan, fused SGD, controller state, status vector."""
@@ -191,9 +226,26 @@ class FlatSGDTrainer:
             dist.all_reduce(vec)
             vec /= self.world
 
+    def _reduce_grads_early(self):
+        """all-reduce of the early bucket, launched asynchronously: NCCL runs on its own stream while the backbone's
+        backward (stage 2) occupies the compute stream."""
+        self._works = []
+        if self.world > 1 and self._pending is not None:
+            for a, b in self.bucket_early:
+                if b > a:
+                    self._works.append(dist.all_reduce(self.flat_g[a:b], async_op=True))
+
     def _reduce_grads(self):
-        if self.world > 1:                              # C1: one gradient all-reduce (sum; the update divides) over NVLink
-            dist.all_reduce(self.flat_g[:self.n_update])
+        if self.world > 1:                              # gradient all-reduce (sum; the update divides) over NVLink
+            if getattr(self, "_works", None):
+                a, b = self.bucket_late
+                if b > a:
+                    dist.all_reduce(self.flat_g[a:b])
+                for w in self._works:
+                    w.wait()
+                self._works = []
+            else:
+                dist.all_reduce(self.flat_g[:self.n_update])
 
     def _body(self, staged, lr):
         """zero grads, forward, loss all-reduce, stabiliser, backward, gradient all-reduce, finite check, SGD — device
@@ -203,6 +255,8 @@ class FlatSGDTrainer:
         loss_dict, vec = self._seg_forward(staged)
         self._reduce_losses(vec)
         tr, recent, div = self._seg_backward(loss_dict, vec)
+        self._reduce_grads_early()
+        self._seg_backward_late()
         self._reduce_grads()
         self._seg_update(vec, tr, recent, div, lr)
         return loss_dict
@@ -273,10 +327,14 @@ class FlatSGDTrainer:
         if len(self.graph) == 1:
             self.graph[0].replay()
             return
-        gA, gB, gC = self.graph
+        gA, gB, gB2, gC = self.graph
         gA.replay()
         self._reduce_losses(self.graph_vec)
         gB.replay()
+        self._pending = self._graph_split              # (only a flag here: the tensors live inside the graphs)
+        self._reduce_grads_early()
+        gB2.replay()
+        self._pending = None
         self._reduce_grads()
         gC.replay()
 
@@ -298,14 +356,17 @@ class FlatSGDTrainer:
                 graphs = [g]
             else:
                 pool = torch.cuda.graph_pool_handle()
-                gA, gB, gC = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                gA, gB, gB2, gC = (torch.cuda.CUDAGraph() for _ in range(4))
                 with torch.cuda.graph(gA, pool=pool, **mode):
                     losses, vec = self._seg_forward(self.static)
                 with torch.cuda.graph(gB, pool=pool, **mode):
                     tr, recent, div = self._seg_backward(losses, vec)
+                self._graph_split = True if self._pending is not None else None
+                with torch.cuda.graph(gB2, pool=pool, **mode):
+                    self._seg_backward_late()
                 with torch.cuda.graph(gC, pool=pool, **mode):
                     self._seg_update(vec, tr, recent, div, self.lr_dev)
-                graphs, self.graph_vec = [gA, gB, gC], vec
+                graphs, self.graph_vec = [gA, gB, gB2, gC], vec
             self.graph_launches = _lib.LAUNCHES["n"] - n0
             self.graph, self.graph_sig, self.graph_losses = graphs, sig, losses
             self._replay()          # recording does not execute: run the step that was just recorded
