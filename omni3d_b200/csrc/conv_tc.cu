@@ -51,18 +51,15 @@ struct ConvSmem {
   static constexpr int kTileBytes = ((kStageBytes + 1023) / 1024) * 1024;
   static constexpr int kBarOffset = STAGES * kTileBytes;
   static constexpr int kRedOffset = kBarOffset + 256;                      // BatchNorm partial sums [4 warps][2][32] fp32
-  static constexpr int kStgOffset = kRedOffset + 4 * 32 * 2 * 4;           // epilogue staging: 4 warps x 32 rows x 128 B
-  static constexpr int kTotal = kStgOffset + 4 * 4096 + 1024 /*align slack*/;
+  static constexpr int kStgOffset = kRedOffset + 4 * 32 * 2 * 4;           // epilogue staging (BatchNorm transposes)
+  static constexpr int kTotal = kStgOffset + 4 * 16 * 33 * 4 + 1024 /*align slack*/;   // staging: 4 warps x 16 x 33 floats
 };
 
 // ------------------------------------------------------------------------------------------------
 // Epilogue of one 128-pixel x BLOCK_N accumulator tile, run by the 4 epilogue warps (warp q owns TMEM lanes 32q..32q+31 =
 // tile rows = output pixels): tcgen05.ld 16 columns at a time -> BatchNorm partial sums -> bias / addend / ReLU ->
-// bf16|fp32 NHWC store.  bf16 outputs with BLOCK_N >= 64 are written through a per-warp shared-memory transpose: a thread
-// owns one pixel, i.e. one 2*Cout-byte ROW of the output, so direct stores put the 32 lanes of every store instruction in
-// 32 different 128-byte lines (16 useful bytes each); staged, the warp writes 4 complete 128-byte row segments per
-// instruction (8x fewer LSU wavefronts) — what bounds the small-K layers (1x1 laterals / roots / projections, 64-channel
-// 3x3s), whose tiles spend longer in the epilogue than in the MMA loop.
+// bf16|fp32 NHWC store (a thread owns one pixel = one row of the output and writes its 16 channels as 2 x 16 bytes).
+// Shared by the one-tile-per-CTA and the persistent kernel.
 template <int BLOCK_N>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& P, const uint32_t tacc /*TMEM address incl. lane*/,
                                                    const int q, const int lane, const int img, const int ho0, const int wo0,
@@ -76,11 +73,6 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& P, const u
   long long apix = 0;
   if (P.add_mode == 1) apix = lpix;
   else if (P.add_mode == 2) apix = ((long long)img * (P.Ho >> 1) + (ho >> 1)) * (P.Wo >> 1) + (wo >> 1);
-  // measured (profiles/r02): the staged store is SLOWER than direct 2 x 16-byte row stores (1x1 64->256 @160: 0.38 -> 0.72 ms;
-  // the write path merges the two half-sector stores, the extra shuffles / shared-memory round trip only add latency to a
-  // latency-bound epilogue) — compiled out, kept for the record
-  constexpr bool kStaged = false && BLOCK_N >= 64;
-  uint8_t* stg = stg_all + q * 4096;
   constexpr int kChunks = (BLOCK_N + 15) / 16;
 #pragma unroll 1
   for (int ch = 0; ch < kChunks; ++ch) {
@@ -92,32 +84,24 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& P, const u
     for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
     const int c0 = n0 + ch * 16;
     if (P.stats) {
-      // per-channel sum / sum-of-squares over the valid rows of this tile (raw fp32 accumulators): log-step exchange
-      // keeping 16 -> 8 -> 4 -> 2 -> 1 values per lane, then the two 16-lane halves, fixed order => deterministic
-      float s[16], s2[16];
+      // per-channel sum / sum-of-squares over the valid rows of this tile (raw fp32 accumulators).  Each warp transposes its
+      // 32 rows x 16 channels through a private 16 x 33-word shared-memory tile (row r writes column r: conflict-free; lane
+      // (c = l & 15, h = l >> 4) then sums rows 16h..16h+15 of channel c: banks (c + 16h + j) mod 32 are all distinct) —
+      // 16 st.shared + 16 ld.shared per thread instead of the 62 shuffles + 62 selects of a register butterfly, which made the
+      // epilogue the bottleneck of the 64/128-channel layers (ncu: stall_short_sb on the FADDs behind SHFL, profiles/r02).
+      // Fixed summation order => deterministic.
+      float* tr = reinterpret_cast<float*>(stg_all) + q * (16 * 33);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { float x = valid ? f[i] : 0.f; s[i] = x; s2[i] = x * x; }
+      for (int i = 0; i < 16; ++i) tr[i * 33 + lane] = valid ? f[i] : 0.f;
+      __syncwarp();
+      const int c = lane & 15, h = lane >> 4;
+      float sa = 0.f, sb = 0.f;
 #pragma unroll
-      for (int step = 0; step < 4; ++step) {
-        const int half = 8 >> step;
-        const int mask = 1 << step;
-        const bool upper = (lane & mask) != 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (i < half) {
-            float send = upper ? s[i] : s[i + half];
-            float keep = upper ? s[i + half] : s[i];
-            float send2 = upper ? s2[i] : s2[i + half];
-            float keep2 = upper ? s2[i + half] : s2[i];
-            s[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, mask);
-          }
-        }
-      }
-      s[0] += __shfl_xor_sync(0xffffffffu, s[0], 16);
-      s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 16);
-      const int cidx = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
-      if (lane < 16) { red[(q * 2 + 0) * 16 + cidx] = s[0]; red[(q * 2 + 1) * 16 + cidx] = s2[0]; }
+      for (int j = 0; j < 16; ++j) { const float x = tr[c * 33 + h * 16 + j]; sa += x; sb += x * x; }
+      sa += __shfl_xor_sync(0xffffffffu, sa, 16);
+      sb += __shfl_xor_sync(0xffffffffu, sb, 16);
+      __syncwarp();
+      if (lane < 16) { red[(q * 2 + 0) * 16 + lane] = sa; red[(q * 2 + 1) * 16 + lane] = sb; }
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
       if (q == 0 && lane < 16 && (c0 + lane) < P.Cout) {
         float a = 0.f, b = 0.f;
@@ -164,32 +148,13 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& P, const u
       __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
       pk[i] = *reinterpret_cast<uint32_t*>(&h);
     }
-    if constexpr (!kStaged) {
-      if (live) {
-        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + pix * P.out_pix_stride + c0);
-        op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
-    } else {
-      // stage my row's 32 bytes: 16-byte slots XOR-swizzled by the row so that neither phase has bank conflicts
-      const int j0 = (ch & 3) * 2;
-      *reinterpret_cast<uint4*>(stg + lane * 128 + (((j0) ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(stg + lane * 128 + (((j0 + 1) ^ (lane & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      if ((ch & 3) == 3) {                     // 64 columns staged: write 4 complete 128-byte row segments per instruction
-        __syncwarp();
-        const int gcol = n0 + (ch - 3) * 16;
-        const int j = lane & 7;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = it * 4 + (lane >> 3);
-          const long long prow = __shfl_sync(0xffffffffu, pix, row);
-          const int vrow = __shfl_sync(0xffffffffu, (int)valid, row);
-          const uint4 val = *reinterpret_cast<const uint4*>(stg + row * 128 + ((j ^ (row & 7)) << 4));
-          if (vrow && gcol < P.Cout)
-            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + prow * P.out_pix_stride + gcol + j * 8) = val;
-        }
-        __syncwarp();
-      }
+    // direct 2 x 16-byte row stores (measured, profiles/r02: staging the tile through shared memory to write complete
+    // 128-byte row segments is SLOWER — 1x1 64->256 @160: 0.38 -> 0.72 ms; the write path already merges the two half-sector
+    // stores and the extra shared-memory round trip only lengthens a latency-bound epilogue)
+    if (live) {
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + pix * P.out_pix_stride + c0);
+      op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
   }
 }
@@ -762,6 +727,15 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   }
 #define C3D_CONV_CASE(bn, bk, stg) \
   if (BN == bn && BK == bk) return launch_conv<bn, bk, stg>(mx, mw, P, grid, st);
+  // one K block per tile (1x1 convs with Cin <= 64: FPN lateral 64->256, DLA projections): these CTAs live for one
+  // TMA -> MMA -> epilogue round trip (~7 us, ncu) and the layer is bound by how many of them an SM holds — a single
+  // pipeline stage (35 KB instead of 99 KB of shared memory) lets the 512 TMEM columns, not shared memory, set the limit
+  if (d->KH * d->KW * P.kc_blocks == 1) {
+    C3D_CONV_CASE(128, 64, 1)
+    C3D_CONV_CASE(64, 64, 1)
+    C3D_CONV_CASE(128, 32, 1)
+    C3D_CONV_CASE(64, 32, 1)
+  }
   C3D_CONV_CASE(128, 64, 3)
   C3D_CONV_CASE(64, 64, 4)
   C3D_CONV_CASE(32, 64, 4)

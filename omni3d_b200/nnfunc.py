@@ -378,7 +378,8 @@ class BoxLoss(torch.autograd.Function):
         ctx.cfg = (K, tuple(weights))
         nv, nfg = acc[2].clamp(min=1.0), acc[3].clamp(min=1.0)
         den = torch.stack([nv, nv, nv, nfg, nfg])
-        return torch.cat([acc[[0, 1, 4, 5, 6]] / den, acc[2:4]])
+        # (no python-list indexing: that would be a host->device copy of the index, illegal inside a CUDA-graph capture)
+        return torch.cat([torch.cat([acc[0:2], acc[4:7]]) / den, acc[2:4]])
 
     @staticmethod
     def backward(ctx, g):

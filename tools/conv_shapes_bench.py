@@ -82,7 +82,9 @@ for name, H, W, Cin, Cout, k, s, p, rc, count, has_dgrad in SHAPES:
     flop = 2.0 * N * Ho * Wo * Cout * k * k * rc
     rec = {"shape": name, "count": count, "gflop": flop / 1e9}
     if "fwd" in kind:
-        t = timeit(lambda: K.conv2d_fwd(x, w, stride=s, pad=p, want_stats=True))
+        bn_layer = not name.startswith(("fpn", "rpn"))          # backbone convs feed BatchNorm (partial statistics in the epilogue)
+        bias = None if bn_layer else torch.zeros(Cout, device="cuda")
+        t = timeit(lambda: K.conv2d_fwd(x, w, bias, stride=s, pad=p, want_stats=bn_layer))
         rec.update(fwd_ms=t, fwd_tflops=flop / t / 1e9); tot["fwd"] += t * count
     if "dgrad" in kind and has_dgrad:
         nnfunc._dgrad(dy, w32, s, p, (H, W))           # fills the pack caches (packing is not part of the timed launch)
