@@ -409,6 +409,18 @@ int32_t c3d_cube_reduce_bwd(const float* rows10, const uint8_t* valid, int32_t n
 int32_t c3d_cube_scatter(const float* draw13, const int64_t* classes, int32_t n, int32_t K, int32_t ld, float* dpred,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Input pipeline, image part (omni3d_b200/csrc/augment_ops.cu): Pillow-exact 8-bit bilinear resize + horizontal flip +
+ * HWC -> CHW — what detectron2's ResizeShortestEdge / RandomFlip do on the CPU inside DatasetMapper3D
+ * (cubercnn/data/dataset_mapper.py:22-35).  img_hwc [H][W][C] uint8 -> out_chw [C][new_h][new_w] uint8.
+ * bounds_* [out][2] = (first input index, tap count), kk_* [out][ksize] = 22-bit fixed-point weights, computed on the host
+ * like Pillow's precompute_coeffs / normalize_coeffs_8bpc; row_first/row_last = input rows the vertical pass reads;
+ * tmp_hwc [H][new_w][C] scratch.  Bit-identical to Image.resize((new_w,new_h), BILINEAR) (+ [:, ::-1] when flip). */
+int32_t c3d_resize_bilinear_u8(const uint8_t* img_hwc, int32_t H, int32_t W, int32_t C, const int32_t* bounds_h,
+                               const int32_t* kk_h, int32_t ksize_h, const int32_t* bounds_v, const int32_t* kk_v,
+                               int32_t ksize_v, int32_t new_h, int32_t new_w, int32_t row_first, int32_t row_last,
+                               int32_t flip, uint8_t* tmp_hwc, uint8_t* out_chw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
