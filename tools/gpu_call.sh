@@ -8,11 +8,7 @@ timeout 600 python bench.py --config resnet34 --steps 10 --warmup 3 --skip-cpu-b
 timeout 300 python bench.py --batch 16 --steps 10 --warmup 3 --skip-cpu-baseline --skip-iou --skip-torch-baseline > gpurun_out/bench_b16_$TAG.json 2> gpurun_out/bench_b16_$TAG.err
 timeout 600 python tools/conv_shapes_bench.py > gpurun_out/conv_shapes_$TAG.log 2>&1
 cp gpurun_out/conv_shapes.json gpurun_out/conv_shapes_$TAG.json 2>/dev/null
-timeout 300 python tools/linear_bench.py > gpurun_out/linear_bench_$TAG.log 2>&1
 timeout 300 python tools/bench_iou3d.py > gpurun_out/iou3d_sweep_$TAG.log 2>&1
-ONLY=fpn_lat_64 KIND=fwd ITERS=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 2 -f -o gpurun_out/ncu_fpnlat_$TAG python tools/conv_shapes_bench.py > gpurun_out/ncu_fpnlat_$TAG.log 2>&1
-ONLY=l4_256 KIND=wgrad ITERS=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_wgrad -c 2 -f -o gpurun_out/ncu_wgrad_l4_$TAG python tools/conv_shapes_bench.py > gpurun_out/ncu_wgrad_l4_$TAG.log 2>&1
-ONLY=l2_64-\>64 KIND=fwd ITERS=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tc_persistent -c 2 -f -o gpurun_out/ncu_l2fwd_$TAG python tools/conv_shapes_bench.py > gpurun_out/ncu_l2fwd_$TAG.log 2>&1
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
   --log-file gpurun_out/launches_$TAG.csv python tools/profile_step.py > gpurun_out/profile_step_$TAG.log 2>&1
 grep -E 'passed|failed|FAILED|Error' gpurun_out/pytest_$TAG.log | tail -30; head -c 600 gpurun_out/bench_$TAG.json; echo; head -c 300 gpurun_out/bench_resnet34_$TAG.json; echo; head -c 300 gpurun_out/bench_b16_$TAG.json; tail -3 gpurun_out/bench_$TAG.err
