@@ -121,6 +121,16 @@ int32_t c3d_conv2d_wgrad_ex(const c3d_conv_desc* d, const void* x, const void* d
 int32_t c3d_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin, int32_t KH, int32_t KW, int32_t src_is_ohwi,
                              void* fwd_ohwi, void* dgrad_ihwo, void* stream);
 
+/* every conv weight of a model in one launch: descs_dev = device array of n c3d_pack_desc (forward pack, rotated /
+ * transposed data-gradient pack and, for 3x3 stride-2 layers, the four phase sub-kernels of the phase-decomposed data
+ * gradient: (Cin, KH', KW', Cout) with parity 0 -> tap [1], parity 1 -> taps [2, 0]); `start` = prefix sum of elements */
+typedef struct {
+  const float* src; void* fwd; void* dgrad; void* phase[4];
+  int64_t start;
+  int32_t Cout, Cin, KH, KW, src_is_ohwi, pad_;
+} c3d_pack_desc;
+int32_t c3d_pack_conv_weights_batched(const void* descs_dev, int32_t n, int64_t total_elems, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fully-connected layers on the same tcgen05 kernels (bf16 operands, fp32 accumulate in TMEM, bias + ReLU fused).
  * Replace the cuBLAS GEMMs behind nn.Linear in detectron2 FastRCNNConvFCHead / FastRCNNOutputLayers
@@ -201,6 +211,11 @@ int32_t c3d_maxpool3s2_bwd(const void* x, const void* dy, void* dx, int32_t N, i
 /* (3,H,W) fp32 BGR image -> (Hp,Wp,Cp) bf16 NHWC slot: (x-mean)/std in channels 0..2, zeros elsewhere */
 int32_t c3d_preprocess_image(const float* img, int32_t H, int32_t W, void* out_slot, int32_t Hp, int32_t Wp,
                              int32_t Cp, const float* mean3_host, const float* std3_host, void* stream);
+/* all N images of a batch in one launch: imgs_host / H_host / W_host are HOST arrays (device pointers, sizes) that travel in
+ * the kernel parameters; out = (N,Hp,Wp,Cp) bf16; is_u8 selects uint8 or fp32 (3,H,W) inputs */
+int32_t c3d_preprocess_batch(const void* const* imgs_host, const int32_t* H_host, const int32_t* W_host, int32_t N,
+                             int32_t is_u8, void* out, int32_t Hp, int32_t Wp, int32_t Cp, const float* mean3_host,
+                             const float* std3_host, void* stream);
 /* same for the uint8 (3,H,W) image tensor detectron2's DatasetMapper produces (dataset_mapper.py: image as uint8) */
 int32_t c3d_preprocess_image_u8(const uint8_t* img, int32_t H, int32_t W, void* out_slot, int32_t Hp, int32_t Wp,
                                 int32_t Cp, const float* mean3_host, const float* std3_host, void* stream);

@@ -40,45 +40,22 @@ static inline int grid_for(long long work_items, int threads) {
 
 // ---- BatchNorm forward ------------------------------------------------------------------------
 // Column sums of a [rows][cols] fp32 matrix in fixed order (deterministic): stage 1 = slabs of rows per
-// block (64 columns x 4 row lanes), doubles out; the consumers below finish over <= kSlabs slabs.
+// block (64 columns x 4 row lanes), doubles out; the LAST block then finishes over the <= kSlabs slabs
+// (colsum_finalize_kernel below).
 constexpr int kSlabs = 128;
-__global__ void colsum_stage1_kernel(const float* __restrict__ m, int rows, int cols, int rows_per_slab,
-                                     double* __restrict__ out /*[gridDim.y][cols]*/) {
-  const int col = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int lane = threadIdx.x >> 6;                       // 0..3
-  const int r0 = blockIdx.y * rows_per_slab;
-  const int r1 = min(rows, r0 + rows_per_slab);
-  double acc = 0.0;
-  if (col < cols)
-    for (int r = r0 + lane; r < r1; r += 4) acc += (double)m[(size_t)r * cols + col];
-  __shared__ double sm[4][64];
-  sm[lane][threadIdx.x & 63] = acc;
-  __syncthreads();
-  if (lane == 0 && col < cols)
-    out[(size_t)blockIdx.y * cols + col] = ((sm[0][threadIdx.x] + sm[1][threadIdx.x]) + sm[2][threadIdx.x]) + sm[3][threadIdx.x];
-}
-static inline void launch_colsum(const float* m, int rows, int cols, double* scratch, int* slabs_out, cudaStream_t st) {
-  int slabs = rows < kSlabs ? rows : kSlabs;
-  int rps = (rows + slabs - 1) / slabs;
-  slabs = (rows + rps - 1) / rps;
-  dim3 grid((cols + 63) / 64, slabs);
-  colsum_stage1_kernel<<<grid, 256, 0, st>>>(m, rows, cols, rps, scratch);
-  *slabs_out = slabs;
-}
-
 // partial: [rows][2][C] per-tile (sum, sumsq) from the conv epilogue -> slab sums -> statistics.
 // Second stage of the column sums: <= kSlabs rows of doubles.  A block is 32 channels x 8 row lanes; every lane sums
 // each 8th slab (16 loads instead of a 128-long serial chain), then the 8 partials are combined through shared memory.
 // Returns the two sums (offsets off0 / off1 inside a slab row; pass off1 < 0 for a single sum) to row-lane 0.
-__device__ __forceinline__ void slab_sums(const double* __restrict__ slab, int slabs, size_t row_stride, int off0, int off1,
+__device__ __forceinline__ void slab_sums(const double* slab, int slabs, size_t row_stride, int off0, int off1,
                                           int c, bool active, double* s_out, double* t_out) {
   __shared__ double sh[2][8][32];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   double s = 0.0, t = 0.0;
   if (active) {
     for (int r = ry; r < slabs; r += 8) {
-      s += slab[(size_t)r * row_stride + off0 + c];
-      if (off1 >= 0) t += slab[(size_t)r * row_stride + off1 + c];
+      s += __ldcg(slab + (size_t)r * row_stride + off0 + c);          // L2 loads: the slabs were written by other blocks
+      if (off1 >= 0) t += __ldcg(slab + (size_t)r * row_stride + off1 + c);
     }
   }
   sh[0][ry][cx] = s; sh[1][ry][cx] = t;
@@ -90,24 +67,6 @@ __device__ __forceinline__ void slab_sums(const double* __restrict__ slab, int s
   *s_out = s; *t_out = t;
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ slab, int slabs, int C, double count, float eps,
-                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  double s, s2;
-  slab_sums(slab, slabs, (size_t)2 * C, 0, C, c, c < C, &s, &s2);
-  if (c >= C || (threadIdx.x >> 5) != 0) return;
-  double mean = s / count;
-  double var = s2 / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  mean_out[c] = (float)mean;
-  rstd_out[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) {
-    double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
-    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
-  }
-}
 
 // out = [relu]( (y - mean) * rstd * gamma + beta [+ residual] ), P pixels x C channels
 // thread layout of the streaming BN kernels: tx = channel vector (8 channels, fixed for the thread's lifetime so the
@@ -147,47 +106,65 @@ bn_apply_kernel(const bf16* __restrict__ y, const float* __restrict__ mean, cons
 }
 
 // ---- BatchNorm backward -----------------------------------------------------------------------
-// dz = dout * (out > 0 if relu);  partial[block][0][c] = sum dz, partial[block][1][c] = sum dz * xhat
+// dz = dout * (out > 0 if relu);  partial[block][0][c] = sum dz, partial[block][1][c] = sum dz * y  (the finalisation
+// turns the second sum into sum dz * xhat = rstd * (sum dz*y - mean * sum dz) in fp64).
+// Register diet (ncu / ptxas, profiles/r02): with mean / rstd / scale / shift / coefficients held per thread these kernels
+// needed 86-90 registers => 2 CTAs of 256 threads per SM => too few loads in flight for HBM (they ran at ~60 % of the copy
+// bandwidth and got SLOWER when the ReLU-mask recomputation added 16 more).  Now the mask constants live in shared memory
+// (3 x C floats, read as two LDS.128 per array per pixel) and the arithmetic needs no per-channel constant at all (reduce) or
+// three fused ones (apply): <= 64 registers => 4 CTAs per SM.
+constexpr int kBnMaxC = 2048;
+__device__ __forceinline__ void bn_mask_consts(float* cm, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                               const float* __restrict__ gamma, const float* __restrict__ beta, int C) {
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    cm[i] = mean[i]; cm[kBnMaxC + i] = rstd[i] * gamma[i]; cm[2 * kBnMaxC + i] = beta[i];
+  }
+}
+// zero d where the forward's fma(y - mean, rstd*gamma, beta) was not positive (bit-identical recomputation)
+__device__ __forceinline__ void bn_remask(V8& d, const V8& yy, const float* cm, int c) {
+  const float4 m0 = *reinterpret_cast<const float4*>(cm + c), m1 = *reinterpret_cast<const float4*>(cm + c + 4);
+  const float4 s0 = *reinterpret_cast<const float4*>(cm + kBnMaxC + c), s1 = *reinterpret_cast<const float4*>(cm + kBnMaxC + c + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(cm + 2 * kBnMaxC + c), b1 = *reinterpret_cast<const float4*>(cm + 2 * kBnMaxC + c + 4);
+  const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) if (!(__fmaf_rn(yy.v[k] - m[k], sc[k], bt[k]) > 0.f)) d.v[k] = 0.f;
+}
+
 template <int THREADS>
-__global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out,
-                                     const bf16* __restrict__ y, const float* __restrict__ mean,
-                                     const float* __restrict__ rstd, int relu, float* __restrict__ partial,
-                                     long long P, int C, long long dout_stride, long long out_stride,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta) {
-  // `out == nullptr` with relu: the layer has no residual, so its ReLU mask is a function of y alone — recompute
-  // out = fma(y - mean, rstd*gamma, beta) exactly as bn_apply_kernel did instead of reading 2 more bytes per element
-  // thread layout: tx = channel-vector index (C/8 of them), rows strided by (THREADS / cv)
+__global__ void __launch_bounds__(THREADS, 4)
+bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out, const bf16* __restrict__ y,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, int relu, float* __restrict__ partial,
+                     long long P, int C, long long dout_stride, long long out_stride, const float* __restrict__ gamma,
+                     const float* __restrict__ beta) {
+  // `out == nullptr` with relu: the layer has no residual, so its ReLU mask is a function of y alone
+  __shared__ float cm[3 * kBnMaxC];
+  __shared__ float sm[2][THREADS][8 + 1];
+  const bool remask = relu && out == nullptr;
+  if (remask) bn_mask_consts(cm, mean, rstd, gamma, beta, C);
+  __syncthreads();
   const int cv = C >> 3;
   const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
   const int rows_per_block = THREADS / cv;
+  const int c = tx << 3;
   float s[8], t[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s[k] = 0.f; t[k] = 0.f; }
-  const int c = tx << 3;
-  float m[8], rs[8], sc[8], bt[8];
-  const bool remask = relu && out == nullptr;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    m[k] = mean[c + k]; rs[k] = rstd[c + k];
-    sc[k] = remask ? rs[k] * gamma[c + k] : 0.f; bt[k] = remask ? beta[c + k] : 0.f;
-  }
   if (ty < rows_per_block) {
     for (long long p = (long long)blockIdx.x * rows_per_block + ty; p < P; p += (long long)gridDim.x * rows_per_block) {
       V8 d = ld8(dout + p * dout_stride + c);
-      V8 yy = ld8(y + p * C + c);
-      if (remask) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (!(__fmaf_rn(yy.v[k] - m[k], sc[k], bt[k]) > 0.f)) d.v[k] = 0.f;
-      } else if (relu) {
-        V8 o = ld8(out + p * out_stride + c);
+      const V8 yy = ld8(y + p * C + c);
+      if (remask) bn_remask(d, yy, cm, c);
+      else if (relu) {
+        const V8 o = ld8(out + p * out_stride + c);
 #pragma unroll
         for (int k = 0; k < 8; ++k) if (!(o.v[k] > 0.f)) d.v[k] = 0.f;
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { s[k] += d.v[k]; t[k] += d.v[k] * ((yy.v[k] - m[k]) * rs[k]); }
+      for (int k = 0; k < 8; ++k) { s[k] += d.v[k]; t[k] = __fmaf_rn(d.v[k], yy.v[k], t[k]); }
     }
   }
-  __shared__ float sm[2][THREADS][8 + 1];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { sm[0][threadIdx.x][k] = s[k]; sm[1][threadIdx.x][k] = t[k]; }
   __syncthreads();
@@ -201,64 +178,132 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* 
   }
 }
 
-// coef[0][c] = gamma*rstd, coef[1][c] = mean(dz), coef[2][c] = mean(dz*xhat); dgamma/dbeta accumulated (+=)
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int blocks, int C, double count,
-                                       const float* __restrict__ gamma, const float* __restrict__ rstd,
-                                       float* __restrict__ coef, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int frozen) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  double s, t;
-  slab_sums(partial, blocks, (size_t)2 * C, 0, C, c, c < C, &s, &t);
-  if (c >= C || (threadIdx.x >> 5) != 0) return;
-  coef[c] = gamma[c] * rstd[c];
-  // frozen (eval-mode / freeze_bn) statistics do not depend on the batch: dy = gamma * rstd * dz
-  coef[C + c] = frozen ? 0.f : (float)(s / count);
-  coef[2 * C + c] = frozen ? 0.f : (float)(t / count);
-  if (dgamma) dgamma[c] += (float)t;
-  if (dbeta) dbeta[c] += (float)s;
-}
-
-// dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat));  optionally dres = dz
-__global__ void __launch_bounds__(256)
+// dy = A*dz + B*y + K with A = gamma*rstd, B = -A*rstd*mean(dz*xhat), K = -A*mean(dz) - B*mean  (== gamma*rstd*(dz - mean(dz)
+// - xhat*mean(dz*xhat)), coefficients from the finalisation);  optionally dres = dz
+__global__ void __launch_bounds__(256, 4)
 bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out, const bf16* __restrict__ y,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ coef, int relu,
                     bf16* __restrict__ dy, bf16* __restrict__ dres, long long P, int C, long long dout_stride,
                     long long out_stride, long long dres_stride, const float* __restrict__ gamma,
                     const float* __restrict__ beta) {
+  __shared__ float cm[3 * kBnMaxC];
+  const bool remask = relu && out == nullptr;
+  if (remask) bn_mask_consts(cm, mean, rstd, gamma, beta, C);
+  __syncthreads();
   const int cv = C >> 3;
   const int tx = threadIdx.x % cv, ty = threadIdx.x / cv;
   const int rows_per_block = blockDim.x / cv;
   if (ty >= rows_per_block) return;
   const int c = tx << 3;
-  float m[8], rs[8], c0[8], c1[8], c2[8], sc[8], bt[8];
-  const bool remask = relu && out == nullptr;
+  float cA[8], cB[8], cK[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    m[k] = mean[c + k]; rs[k] = rstd[c + k];
-    c0[k] = coef[c + k]; c1[k] = coef[C + c + k]; c2[k] = coef[2 * C + c + k];
-    sc[k] = remask ? rs[k] * gamma[c + k] : 0.f; bt[k] = remask ? beta[c + k] : 0.f;
-  }
+  for (int k = 0; k < 8; ++k) { cA[k] = coef[c + k]; cB[k] = coef[C + c + k]; cK[k] = coef[2 * C + c + k]; }
   const long long step = (long long)gridDim.x * rows_per_block;
   for (long long p = (long long)blockIdx.x * rows_per_block + ty; p < P; p += step) {
     V8 d = ld8(dout + p * dout_stride + c);
-    V8 yy = ld8(y + p * C + c);
-    if (remask) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) if (!(__fmaf_rn(yy.v[k] - m[k], sc[k], bt[k]) > 0.f)) d.v[k] = 0.f;
-    } else if (relu) {
-      V8 o = ld8(out + p * out_stride + c);
+    const V8 yy = ld8(y + p * C + c);
+    if (remask) bn_remask(d, yy, cm, c);
+    else if (relu) {
+      const V8 o = ld8(out + p * out_stride + c);
 #pragma unroll
       for (int k = 0; k < 8; ++k) if (!(o.v[k] > 0.f)) d.v[k] = 0.f;
     }
     V8 g;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float xh = (yy.v[k] - m[k]) * rs[k];
-      g.v[k] = c0[k] * (d.v[k] - c1[k] - xh * c2[k]);
-    }
+    for (int k = 0; k < 8; ++k) g.v[k] = __fmaf_rn(cA[k], d.v[k], __fmaf_rn(cB[k], yy.v[k], cK[k]));
     st8(dy + p * C + c, g);
     if (dres) st8(dres + p * dres_stride + c, d);
   }
+}
+
+// ---- column sums + finalisation in ONE launch ------------------------------------------------------------------------
+// The three consumers of the slab sums (BatchNorm statistics, BatchNorm backward coefficients, bias gradient) used to be a
+// second launch of (C/32) tiny blocks behind colsum_stage1: ~100 extra launches of 5-10 us per step (1.2 ms with the
+// stage-1 kernels, profiles/r02).  Here the LAST stage-1 block to finish (ticket counter zeroed by a 4-byte memset node in
+// front of the launch) runs the finalisation for all channels, in the same fixed order as before => same bits.
+struct FinArgs {
+  int mode;                  // 0 BatchNorm statistics, 1 BatchNorm backward coefficients, 2 bias gradient
+  int C;
+  double count;
+  float eps, momentum;
+  float* running_mean; float* running_var; float* mean_out; float* rstd_out;      // mode 0
+  const float* gamma; const float* rstd; const float* mean; float* coef; float* dgamma; float* dbeta; int frozen;   // mode 1
+  float* dbias;                                                                    // mode 2
+};
+
+__global__ void colsum_finalize_kernel(const float* __restrict__ m, int rows, int cols, int rows_per_slab,
+                                       double* __restrict__ out /*[gridDim.y][cols]*/, unsigned int* __restrict__ ticket,
+                                       const FinArgs A) {
+  const int col = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int lane = threadIdx.x >> 6;                       // 0..3
+  const int r0 = blockIdx.y * rows_per_slab;
+  const int r1 = min(rows, r0 + rows_per_slab);
+  double acc = 0.0;
+  if (col < cols)
+    for (int r = r0 + lane; r < r1; r += 4) acc += (double)m[(size_t)r * cols + col];
+  __shared__ double sm[4][64];
+  __shared__ int s_last;
+  sm[lane][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (lane == 0 && col < cols)
+    out[(size_t)blockIdx.y * cols + col] = ((sm[0][threadIdx.x] + sm[1][threadIdx.x]) + sm[2][threadIdx.x]) + sm[3][threadIdx.x];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int slabs = gridDim.y, C = A.C;
+  const int ry = threadIdx.x >> 5;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + (threadIdx.x & 31);
+    double s, t;
+    if (A.mode == 2) slab_sums(out, slabs, (size_t)C, 0, -1, c, c < C, &s, &t);
+    else slab_sums(out, slabs, (size_t)2 * C, 0, C, c, c < C, &s, &t);
+    if (c < C && ry == 0) {
+      if (A.mode == 0) {
+        double mean = s / A.count;
+        double var = t / A.count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        A.mean_out[c] = (float)mean;
+        A.rstd_out[c] = (float)(1.0 / sqrt(var + (double)A.eps));
+        if (A.running_mean) {
+          double unbiased = A.count > 1.0 ? var * A.count / (A.count - 1.0) : var;
+          A.running_mean[c] = (float)((1.0 - A.momentum) * A.running_mean[c] + A.momentum * mean);
+          A.running_var[c] = (float)((1.0 - A.momentum) * A.running_var[c] + A.momentum * unbiased);
+        }
+      } else if (A.mode == 1) {
+        // s = sum dz, t = sum dz*y  ->  sum dz*xhat = rstd * (t - mean * s)
+        const double rs = (double)A.rstd[c], mu = (double)A.mean[c];
+        const double tx = rs * (t - mu * s);
+        const double a = (double)A.gamma[c] * rs;
+        // frozen (eval-mode / freeze_bn) statistics do not depend on the batch: dy = gamma * rstd * dz
+        const double c1 = A.frozen ? 0.0 : s / A.count, c2 = A.frozen ? 0.0 : tx / A.count;
+        const double bq = -a * rs * c2;
+        A.coef[c] = (float)a;
+        A.coef[C + c] = (float)bq;
+        A.coef[2 * C + c] = (float)(-a * c1 - bq * mu);
+        if (A.dgamma) A.dgamma[c] += (float)tx;
+        if (A.dbeta) A.dbeta[c] += (float)s;
+      } else {
+        A.dbias[c] += (float)s;
+      }
+    }
+    __syncthreads();          // slab_sums' shared buffer is reused by the next channel group
+  }
+}
+static inline int32_t launch_colsum_finalize(const float* m, int rows, int cols, double* scratch, const FinArgs& A,
+                                             cudaStream_t st) {
+  int slabs = rows < kSlabs ? rows : kSlabs;
+  int rps = (rows + slabs - 1) / slabs;
+  slabs = (rows + rps - 1) / rps;
+  // the ticket lives behind the slab sums (c3d_bn_scratch_bytes reserves it)
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (size_t)kSlabs * cols);
+  cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess) return set_error(C3D_ECUDA, "colsum ticket: %s", cudaGetErrorString(e));
+  dim3 grid((cols + 63) / 64, slabs);
+  colsum_finalize_kernel<<<grid, 256, 0, st>>>(m, rows, cols, rps, scratch, ticket, A);
+  return C3D_OK;
 }
 
 // ---- bias / ReLU backward for the bias convs (FPN, RPN head) -----------------------------------------
@@ -306,13 +351,6 @@ __global__ void bias_act_bwd_kernel(const TIN* __restrict__ dout, const TOUT* __
     for (int r = 0; r < rows_per_block; ++r) acc += sm[r * cv + vx][k];
     partial[(size_t)blockIdx.x * C + ch] = acc;
   }
-}
-__global__ void bias_bwd_finalize_kernel(const double* __restrict__ slab, int slabs, int C, float* __restrict__ dbias) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  double s, t;
-  slab_sums(slab, slabs, (size_t)C, 0, -1, c, c < C, &s, &t);
-  if (c >= C || (threadIdx.x >> 5) != 0) return;
-  dbias[c] += (float)s;
 }
 
 // dsmall[n,h,w,c] = sum of the 2x2 block of dbig (gradient of nearest x2 upsampling), bf16 in/out
@@ -517,6 +555,43 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
   }
 }
 
+// All conv weights of the model in ONE launch (the per-parameter kernel above ran 58 times per step + ~70 ATen launches for the
+// stride-2 phase sub-kernels): every source element writes its forward-pack entry, its rotated / transposed data-gradient
+// entry and — for 3x3 stride-2 layers — its entry in the phase sub-kernel it belongs to (nnfunc._phase_packs:
+// parity 0 uses tap [1], parity 1 taps [2, 0]).
+struct PackDesc {
+  const float* src; bf16* fwd; bf16* dgrad; bf16* phase[4];
+  long long start;                 // first global element index of this tensor
+  int Cout, Cin, KH, KW, ohwi, pad_;
+};
+__global__ void pack_conv_weights_batched_kernel(const PackDesc* __restrict__ descs, int n, long long total) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (descs[mid].start <= e) lo = mid; else hi = mid; }
+    const PackDesc D = descs[lo];
+    const long long i = e - D.start;
+    int kw, kh, ci, co;
+    if (D.ohwi) {
+      ci = (int)(i % D.Cin); long long t = i / D.Cin;
+      kw = (int)(t % D.KW); t /= D.KW;
+      kh = (int)(t % D.KH); co = (int)(t / D.KH);
+    } else {
+      kw = (int)(i % D.KW); long long t = i / D.KW;
+      kh = (int)(t % D.KH); t /= D.KH;
+      ci = (int)(t % D.Cin); co = (int)(t / D.Cin);
+    }
+    const bf16 v = __float2bfloat16(D.src[i]);
+    if (D.fwd) D.fwd[(((long long)co * D.KH + kh) * D.KW + kw) * D.Cin + ci] = v;
+    if (D.dgrad) D.dgrad[(((long long)ci * D.KH + (D.KH - 1 - kh)) * D.KW + (D.KW - 1 - kw)) * D.Cout + co] = v;
+    if (D.phase[0]) {               // 3x3 only: parity a = (kh != 1), position inside the phase: kh 1 -> 0 | kh 2 -> 0, kh 0 -> 1
+      const int a = kh != 1, b = kw != 1;
+      const int ph = a ? (kh == 2 ? 0 : 1) : 0, pw = b ? (kw == 2 ? 0 : 1) : 0;
+      const int KHp = a ? 2 : 1, KWp = b ? 2 : 1;
+      D.phase[a * 2 + b][(((long long)ci * KHp + ph) * KWp + pw) * D.Cout + co] = v;
+    }
+  }
+}
+
 // ---- image normalisation: (3,H,W) fp32 BGR -> (Hp,Wp,Cp) bf16 NHWC slot, zero padded --------------
 template <typename T>
 __global__ void preprocess_kernel(const T* __restrict__ img, int H, int W, bf16* __restrict__ out, int Hp,
@@ -533,6 +608,37 @@ __global__ void preprocess_kernel(const T* __restrict__ img, int H, int W, bf16*
       v2 = ((float)img[2LL * H * W + o] - m2) / s2;
     }
     bf16* dst = out + i * Cp;
+    for (int c = 0; c < Cp; c += 8) {
+      V8 z;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) z.v[k] = 0.f;
+      if (c == 0) { z.v[0] = v0; z.v[1] = v1; z.v[2] = v2; }
+      st8(dst + c, z);
+    }
+  }
+}
+
+// all images of a batch in ONE launch (blockIdx.y = image; pointers and sizes travel in the kernel parameters)
+constexpr int kPreBatch = 64;
+struct PreBatch { const void* img[kPreBatch]; int H[kPreBatch]; int W[kPreBatch]; };
+template <typename T>
+__global__ void preprocess_batch_kernel(const PreBatch B, bf16* __restrict__ out, int Hp, int Wp, int Cp, float m0, float m1,
+                                        float m2, float s0, float s1, float s2) {
+  const int n = blockIdx.y;
+  const T* __restrict__ img = static_cast<const T*>(B.img[n]);
+  const int H = B.H[n], W = B.W[n];
+  const long long total = (long long)Hp * Wp;
+  bf16* base = out + (size_t)n * total * Cp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % Wp), h = (int)(i / Wp);
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (h < H && w < W) {
+      const long long o = (long long)h * W + w;
+      v0 = ((float)img[o] - m0) / s0;
+      v1 = ((float)img[(long long)H * W + o] - m1) / s1;
+      v2 = ((float)img[2LL * H * W + o] - m2) / s2;
+    }
+    bf16* dst = base + i * Cp;
     for (int c = 0; c < Cp; c += 8) {
       V8 z;
 #pragma unroll
@@ -572,16 +678,18 @@ __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restri
 using namespace c3d;
 #define C3D_REQ(cond, msg) do { if (!(cond)) return set_error(C3D_EINVAL, msg); } while (0)
 
-extern "C" size_t c3d_bn_scratch_bytes(int32_t C) { return (size_t)kSlabs * 2 * (size_t)(C > 0 ? C : 0) * sizeof(double); }
+extern "C" size_t c3d_bn_scratch_bytes(int32_t C) {      // slab sums + the last-block ticket behind them
+  return ((size_t)kSlabs * 2 * (size_t)(C > 0 ? C : 0) + 2) * sizeof(double);
+}
 extern "C" int32_t c3d_bn_finalize(const float* partial, int32_t rows, int32_t C, double count, float eps,
                                    float momentum, float* running_mean, float* running_var, float* mean_out,
                                    float* rstd_out, void* scratch, void* stream) {
   C3D_REQ(partial && mean_out && rstd_out && scratch && rows > 0 && C > 0, "bn_finalize: bad args");
-  int slabs;
-  launch_colsum(partial, rows, 2 * C, (double*)scratch, &slabs, (cudaStream_t)stream);
-  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>((const double*)scratch, slabs, C, count, eps,
-                                                                     momentum, running_mean, running_var, mean_out,
-                                                                     rstd_out);
+  FinArgs A{};
+  A.mode = 0; A.C = C; A.count = count; A.eps = eps; A.momentum = momentum;
+  A.running_mean = running_mean; A.running_var = running_var; A.mean_out = mean_out; A.rstd_out = rstd_out;
+  int32_t rc = launch_colsum_finalize(partial, rows, 2 * C, (double*)scratch, A, (cudaStream_t)stream);
+  if (rc != C3D_OK) return rc;
   return check_launch("bn_finalize");
 }
 extern "C" int32_t c3d_bn_apply(const void* y, const float* mean, const float* rstd, const float* gamma,
@@ -621,10 +729,11 @@ extern "C" int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, 
                                                        relu, partial, P, C, ds, os, gamma, beta);
   else
     return set_error(C3D_EINVAL, "bn_bwd: C too large");
-  int slabs;
-  launch_colsum(partial, blocks, 2 * C, (double*)scratch, &slabs, st);
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>((const double*)scratch, slabs, C, (double)P, gamma, rstd, coef,
-                                                       dgamma, dbeta, frozen_stats);
+  FinArgs A{};
+  A.mode = 1; A.C = C; A.count = (double)P; A.gamma = gamma; A.rstd = rstd; A.mean = mean; A.coef = coef; A.dgamma = dgamma; A.dbeta = dbeta;
+  A.frozen = frozen_stats;
+  int32_t rc = launch_colsum_finalize(partial, blocks, 2 * C, (double*)scratch, A, st);
+  if (rc != C3D_OK) return rc;
   bn_bwd_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)y,
                                                                    mean, rstd, coef, relu, (bf16*)dy, (bf16*)dres, P, C,
                                                                    ds, os, dres_stride ? dres_stride : C, gamma, beta);
@@ -682,6 +791,37 @@ extern "C" int32_t c3d_preprocess_image_u8(const uint8_t* img, int32_t H, int32_
       std3_host[1], std3_host[2]);
   return check_launch("preprocess_u8");
 }
+extern "C" int32_t c3d_pack_conv_weights_batched(const void* descs_dev, int32_t n, int64_t total_elems, void* stream) {
+  C3D_REQ(descs_dev && n > 0 && total_elems > 0, "pack_conv_weights_batched: bad args");
+  static_assert(sizeof(PackDesc) == 88, "c3d_pack_desc layout");
+  pack_conv_weights_batched_kernel<<<grid_for(total_elems, 256), 256, 0, (cudaStream_t)stream>>>((const PackDesc*)descs_dev, n,
+                                                                                                 total_elems);
+  return check_launch("pack_conv_weights_batched");
+}
+extern "C" int32_t c3d_preprocess_batch(const void* const* imgs_host, const int32_t* H_host, const int32_t* W_host, int32_t N,
+                                        int32_t is_u8, void* out, int32_t Hp, int32_t Wp, int32_t Cp, const float* mean3_host,
+                                        const float* std3_host, void* stream) {
+  C3D_REQ(imgs_host && H_host && W_host && out && mean3_host && std3_host && Cp % 8 == 0 && N >= 0, "preprocess_batch: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int n0 = 0; n0 < N; n0 += kPreBatch) {
+    const int nb = N - n0 < kPreBatch ? N - n0 : kPreBatch;
+    PreBatch B;
+    for (int i = 0; i < nb; ++i) {
+      C3D_REQ(imgs_host[n0 + i] && H_host[n0 + i] <= Hp && W_host[n0 + i] <= Wp, "preprocess_batch: image larger than the slot");
+      B.img[i] = imgs_host[n0 + i]; B.H[i] = H_host[n0 + i]; B.W[i] = W_host[n0 + i];
+    }
+    int bx = grid_for((long long)Hp * Wp, 256);
+    if (bx > 4 * kNumSMs) bx = 4 * kNumSMs;
+    bf16* o = (bf16*)out + (size_t)n0 * Hp * Wp * Cp;
+    if (is_u8)
+      preprocess_batch_kernel<uint8_t><<<dim3(bx, nb), 256, 0, st>>>(B, o, Hp, Wp, Cp, mean3_host[0], mean3_host[1], mean3_host[2],
+                                                                     std3_host[0], std3_host[1], std3_host[2]);
+    else
+      preprocess_batch_kernel<float><<<dim3(bx, nb), 256, 0, st>>>(B, o, Hp, Wp, Cp, mean3_host[0], mean3_host[1], mean3_host[2],
+                                                                   std3_host[0], std3_host[1], std3_host[2]);
+  }
+  return check_launch("preprocess_batch");
+}
 extern "C" int32_t c3d_grad_finite(const float* g, int64_t n, int32_t* flag, void* stream) {
   C3D_REQ(g && flag, "grad_finite: bad args");
   if (n == 0) return C3D_OK;
@@ -725,9 +865,10 @@ extern "C" int32_t c3d_bias_act_bwd(const void* dout, const void* out, int32_t r
   else C3D_BAB(bf16, bf16);
 #undef C3D_BAB
   if (dbias) {
-    int slabs;
-    launch_colsum(partial, blocks, C, (double*)scratch, &slabs, st);
-    bias_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>((const double*)scratch, slabs, C, dbias);
+    FinArgs A{};
+    A.mode = 2; A.C = C; A.dbias = dbias;
+    int32_t rc = launch_colsum_finalize(partial, blocks, C, (double*)scratch, A, st);
+    if (rc != C3D_OK) return rc;
   }
   return check_launch("bias_act_bwd");
 }

@@ -75,6 +75,7 @@ def _bind():
     sig["c3d_cube_reduce_fwd"] = [vp, vp, i32, vp, vp, vp]
     sig["c3d_cube_reduce_bwd"] = [vp, vp, i32, vp, vp, vp, vp]
     sig["c3d_cube_scatter"] = [vp, vp, i32, i32, i32, vp, vp]
+    sig["c3d_preprocess_batch"] = [vp, vp, vp, i32, i32, vp, i32, i32, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), vp]
     sig["c3d_det_candidates"] = [vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]
     sig["c3d_anchor_sample_finish"] = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, i32, i32, f32, vp, vp, vp]
     for name, args in sig.items():
@@ -98,7 +99,7 @@ def bn_finalize(stats, count, eps, momentum, running_mean, running_var):
     rows, _, C = stats.shape
     mean = torch.empty(C, device=stats.device, dtype=torch.float32)
     rstd = torch.empty(C, device=stats.device, dtype=torch.float32)
-    scratch = torch.empty(128 * 2 * C, device=stats.device, dtype=torch.float64)
+    scratch = torch.empty(128 * 2 * C + 2, device=stats.device, dtype=torch.float64)
     _lib.check(L.c3d_bn_finalize(_p(stats), rows, C, float(count), eps, momentum, _p(running_mean), _p(running_var),
                                  _p(mean), _p(rstd), _p(scratch), _st()), launches=2)
     return mean, rstd
@@ -143,7 +144,7 @@ def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres, froz
     coef = torch.empty((3, C), device=y.device, dtype=torch.float32)
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
-    scratch = torch.empty(128 * 2 * C, device=y.device, dtype=torch.float64)
+    scratch = torch.empty(128 * 2 * C + 2, device=y.device, dtype=torch.float64)
     _lib.check(L.c3d_bn_bwd(_p(dout), _p(out), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), int(relu), int(frozen), _p(partial), _p(coef),
                             _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, ds, 0, 0, _p(scratch), _st()), launches=4)
     return dy, dres
@@ -197,6 +198,17 @@ def preprocess_images(images, mean, std, size_divisibility=64, cpad=16):
     out = torch.empty((len(images), Hp, Wp, cpad), device=images[0].device, dtype=torch.bfloat16)
     m = (f32 * 3)(*[float(v) for v in mean])
     s = (f32 * 3)(*[float(v) for v in std])
+    dt = images[0].dtype
+    if all(im.dtype == dt for im in images):            # the usual case: one launch for the whole batch
+        n = len(images)
+        for im in images:
+            assert im.dtype in (torch.float32, torch.uint8) and im.is_contiguous() and im.is_cuda
+        ptrs = (vp * n)(*[im.data_ptr() for im in images])
+        hs = (i32 * n)(*[im.shape[1] for im in images])
+        ws = (i32 * n)(*[im.shape[2] for im in images])
+        _lib.check(L.c3d_preprocess_batch(ptrs, hs, ws, n, int(dt == torch.uint8), _p(out), Hp, Wp, cpad, m, s, _st()),
+                   launches=(n + 63) // 64)
+        return out
     for i, im in enumerate(images):
         assert im.dtype in (torch.float32, torch.uint8) and im.is_contiguous() and im.is_cuda
         fn = L.c3d_preprocess_image if im.dtype == torch.float32 else L.c3d_preprocess_image_u8
@@ -344,7 +356,7 @@ def bias_act_bwd(dout, out, relu, dbias):
     dout = dout.contiguous()
     blocks = L.c3d_bn_bwd_blocks(P, C)
     partial = torch.empty((blocks, C), device=dout.device, dtype=torch.float32)
-    scratch = torch.empty(128 * 2 * C, device=dout.device, dtype=torch.float64)
+    scratch = torch.empty(128 * 2 * C + 2, device=dout.device, dtype=torch.float64)
     dz = torch.empty(dout.shape, device=dout.device, dtype=torch.bfloat16)
     flags = int(dout.dtype == torch.float32) | (2 if (out is not None and out.dtype == torch.float32) else 0)
     _lib.check(L.c3d_bias_act_bwd(_p(dout), _p(out), int(relu), flags, _p(dz), _p(partial),

@@ -6,6 +6,7 @@ kernels' bf16 OHWI layouts once per parameter version.  Forward AND backward run
   conv fwd  -> c3d_conv2d_fwd          dgrad -> c3d_conv2d_fwd with flipped/transposed weights
   wgrad     -> c3d_conv2d_wgrad        BN    -> c3d_bn_finalize / c3d_bn_apply / c3d_bn_bwd
 """
+import ctypes
 import weakref
 
 import torch
@@ -53,6 +54,66 @@ def _packed(w, kind):
 
 _phase_cache = {}
 _tap_index = {}
+
+# ---- all conv weights of a model packed by ONE launch per step (c3d_pack_conv_weights_batched) ----------------------------
+_plans = {}
+
+
+class _PackDesc(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_void_p), ("fwd", ctypes.c_void_p), ("dgrad", ctypes.c_void_p), ("phase", ctypes.c_void_p * 4),
+                ("start", ctypes.c_int64), ("Cout", ctypes.c_int32), ("Cin", ctypes.c_int32), ("KH", ctypes.c_int32),
+                ("KW", ctypes.c_int32), ("ohwi", ctypes.c_int32), ("pad_", ctypes.c_int32)]
+
+
+def prepack_model(model):
+    """Pack every directly-used conv weight of `model` (forward OHWI pack, rotated data-gradient pack, and the four phase
+    sub-kernels of 3x3 / stride-2 layers) with one kernel launch and seed the per-parameter caches, so the layer-by-layer
+    `_packed` / `_phase_packs` look-ups of this step are hits.  Output buffers and the descriptor table are built once per
+    model (stable addresses: CUDA-graph safe); call at the start of every training step, after the optimizer update."""
+    convs = [m for m in model.modules() if isinstance(m, torch.nn.Conv2d) and isinstance(m.weight, torch.nn.Parameter)
+             and m.weight.is_cuda and m.weight.shape[1] % 16 == 0 and m.weight.shape[0] % 16 == 0]
+    if not convs:
+        return 0
+    key = tuple((id(m.weight), m.weight.data_ptr(), tuple(m.weight.stride())) for m in convs)
+    plan = _plans.get(id(model))
+    if plan is None or plan["key"] != key:
+        dev = convs[0].weight.device
+        arr = (_PackDesc * len(convs))()
+        bufs, start = [], 0
+        for i, m in enumerate(convs):
+            w = m.weight
+            O, I, KH, KW = w.shape
+            ohwi = (not w.is_contiguous()) and w.permute(0, 2, 3, 1).is_contiguous()
+            if not (ohwi or w.is_contiguous()):
+                raise RuntimeError("prepack_model: conv weight storage is neither OIHW nor OHWI")
+            phase = m.stride[0] == 2 and KH == 3 and KW == 3 and m.padding[0] == 1
+            f = torch.empty((O, KH, KW, I), device=dev, dtype=torch.bfloat16)
+            g = torch.empty((I, KH, KW, O), device=dev, dtype=torch.bfloat16)
+            ph = {(a, b): torch.empty((I, 2 if a else 1, 2 if b else 1, O), device=dev, dtype=torch.bfloat16)
+                  for a in (0, 1) for b in (0, 1)} if phase else None
+            d = arr[i]
+            d.src, d.fwd, d.dgrad = w.data_ptr(), f.data_ptr(), g.data_ptr()
+            for a in (0, 1):
+                for b in (0, 1):
+                    d.phase[a * 2 + b] = ph[(a, b)].data_ptr() if ph else None
+            d.start, d.Cout, d.Cin, d.KH, d.KW, d.ohwi = start, O, I, KH, KW, int(ohwi)
+            start += w.numel()
+            bufs.append((w, f, g, ph))
+        table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        plan = _plans[id(model)] = {"key": key, "table": table, "bufs": bufs, "total": start, "n": len(convs)}
+    L = K._bind()
+    if not hasattr(L, "_c3d_pack_bound"):
+        L.c3d_pack_conv_weights_batched.restype = ctypes.c_int32
+        L.c3d_pack_conv_weights_batched.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p]
+        L._c3d_pack_bound = True
+    from . import _lib
+    _lib.check(L.c3d_pack_conv_weights_batched(plan["table"].data_ptr(), plan["n"], plan["total"], K._stream()))
+    for w, f, g, ph in plan["bufs"]:
+        k, ver = _cache_key(w)
+        _pack_cache[k] = (ver, f, g, weakref.ref(w))
+        if ph is not None:
+            _phase_cache[k] = (ver, ph, weakref.ref(w))
+    return plan["n"]
 
 
 def _phase_packs(w):

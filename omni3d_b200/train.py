@@ -166,12 +166,15 @@ class FlatSGDTrainer:
         if hasattr(model, "set_backward_cut"):
             model.set_backward_cut(self.split_backward)
         self._pending = self._works = self._graph_split = None
+        self.prepack = os.environ.get("C3D_NO_PREPACK") is None and hasattr(model, "forward_staged")
 
     # -------------------------------------------------------------------------------------------------
     def _seg_forward(self, staged):
         """segment A: zero the gradient arena, forward, the 10 local losses as one vector."""
         model = self.model
         self.flat_g.zero_()
+        if self.on_cuda and self.prepack:
+            nnfunc.prepack_model(model)          # every conv weight's bf16 packs in one launch (instead of ~60 + ~70 ATen)
         loss_dict = model.forward_staged(staged) if hasattr(model, "forward_staged") else model(staged)
         vec = torch.stack([loss_dict[k].detach().float() if k in loss_dict else self.flat_g.new_zeros(())
                            for k in LOSS_KEYS])

@@ -154,3 +154,40 @@ def test_bn_backward_mask_recomputed_from_y_equals_mask_from_out(C, frozen):
         res.append((dy, dg, db))
     for a, b in zip(res[0], res[1]):
         assert torch.equal(a, b)
+
+
+def test_prepack_model_equals_per_parameter_packs():
+    """c3d_pack_conv_weights_batched (one launch for every conv weight: forward, data-gradient and stride-2 phase packs)
+    == the per-parameter pack kernel / torch formulation it replaces, for OIHW and channels-last (trainer arena) masters."""
+    from omni3d_b200 import conv as K
+    from omni3d_b200 import nnfunc
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Conv2d(16, 32, 3, stride=2, padding=1, bias=False)
+            self.b = torch.nn.Conv2d(32, 64, 3, padding=1, bias=False)
+            self.c = torch.nn.Conv2d(64, 16, 1, bias=False)
+            self.skip = torch.nn.Conv2d(3, 16, 7, padding=3, bias=False)         # Cin 3: not packed here
+    net = Net().cuda()
+    with torch.no_grad():                          # channels-last storage like the trainer's arena
+        w = net.b.weight
+        net.b.weight.data = w.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    assert nnfunc.prepack_model(net) == 3
+    for m in (net.a, net.b, net.c):
+        f, g = K.pack_conv_weight(m.weight)
+        assert torch.equal(nnfunc._packed(m.weight, "fwd"), f) and torch.equal(nnfunc._packed(m.weight, "dgrad"), g)
+    ref = {}
+    nnfunc._phase_cache.clear()
+    got = None
+    nnfunc.prepack_model(net)
+    got = {k: v.clone() for k, v in nnfunc._phase_packs(net.a.weight).items()}
+    nnfunc._phase_cache.clear()
+    ref = nnfunc._phase_packs(net.a.weight)                       # torch formulation (cache was cleared)
+    for k in ref:
+        assert torch.equal(got[k], ref[k]), k
+    # a parameter update (version bump) invalidates the seeded entries
+    with torch.no_grad():
+        net.c.weight.add_(1.0)
+    f2, _ = K.pack_conv_weight(net.c.weight)
+    assert torch.equal(nnfunc._packed(net.c.weight, "fwd"), f2)

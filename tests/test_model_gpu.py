@@ -303,7 +303,7 @@ def test_inference_stages_vs_oracle(pair):
         # the pose comes from Gram-Schmidt on 6 outputs of ~1e-2 magnitude at random init: bf16 noise is amplified
         assert _rel(c3["pose"][sl].cpu(), inst.pred_pose) < 8e-2
         assert _rel(c3["corners"][sl].cpu(), inst.pred_bbox3D) < 4e-2
-        assert _rel(c3["c2d"][sl].cpu(), inst.pred_center_2D) < 1e-2
+        assert _rel(c3["c2d"][sl].cpu(), inst.pred_center_2D) < 2e-2
 
 
 def test_bn_folding_matches_unfolded_eval_and_oracle(pair):
