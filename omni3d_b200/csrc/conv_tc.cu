@@ -50,8 +50,8 @@ struct ConvSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;       // both multiples of 1024 for BLOCK_N>=32|BK=64
   static constexpr int kTileBytes = ((kStageBytes + 1023) / 1024) * 1024;
   static constexpr int kBarOffset = STAGES * kTileBytes;
-  static constexpr int kRedOffset = kBarOffset + 256;                      // BatchNorm partial sums [4 warps][2][32] fp32
-  static constexpr int kStgOffset = kRedOffset + 4 * 32 * 2 * 4;           // epilogue staging (BatchNorm transposes)
+  static constexpr int kRedOffset = kBarOffset + 256;                      // BatchNorm partial sums [4 warps][2][256] fp32
+  static constexpr int kStgOffset = kRedOffset + 4 * 2 * 256 * 4;          // epilogue staging (BatchNorm transposes)
   static constexpr int kTotal = kStgOffset + 4 * 16 * 33 * 4 + 1024 /*align slack*/;   // staging: 4 warps x 16 x 33 floats
 };
 
@@ -74,22 +74,24 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& P, const u
   if (P.add_mode == 1) apix = lpix;
   else if (P.add_mode == 2) apix = ((long long)img * (P.Ho >> 1) + (ho >> 1)) * (P.Wo >> 1) + (wo >> 1);
   constexpr int kChunks = (BLOCK_N + 15) / 16;
+  constexpr int kStatN = kChunks * 16;
+  // TMEM loads are software-pipelined: chunk ch+1 is in flight while chunk ch is reduced / converted / stored
+  uint32_t v[16];
+  ptx::tmem_ld_32x32b_x16(tacc, v);
 #pragma unroll 1
   for (int ch = 0; ch < kChunks; ++ch) {
-    uint32_t v[16];
-    ptx::tmem_ld_32x32b_x16(tacc + (uint32_t)(ch * 16), v);
     ptx::tmem_ld_wait();
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+    if (ch + 1 < kChunks) ptx::tmem_ld_32x32b_x16(tacc + (uint32_t)((ch + 1) * 16), v);
     const int c0 = n0 + ch * 16;
     if (P.stats) {
       // per-channel sum / sum-of-squares over the valid rows of this tile (raw fp32 accumulators).  Each warp transposes its
       // 32 rows x 16 channels through a private 16 x 33-word shared-memory tile (row r writes column r: conflict-free; lane
-      // (c = l & 15, h = l >> 4) then sums rows 16h..16h+15 of channel c: banks (c + 16h + j) mod 32 are all distinct) —
-      // 16 st.shared + 16 ld.shared per thread instead of the 62 shuffles + 62 selects of a register butterfly, which made the
-      // epilogue the bottleneck of the 64/128-channel layers (ncu: stall_short_sb on the FADDs behind SHFL, profiles/r02).
-      // Fixed summation order => deterministic.
+      // (c = l & 15, h = l >> 4) then sums rows 16h..16h+15 of channel c: banks (c + 16h + j) mod 32 are all distinct) and
+      // parks its 16 column sums in red[warp][.][channel]; the four warps are combined ONCE per tile after the chunk loop
+      // (two named barriers per tile instead of two per 16 channels).  Fixed summation order => deterministic.
       float* tr = reinterpret_cast<float*>(stg_all) + q * (16 * 33);
 #pragma unroll
       for (int i = 0; i < 16; ++i) tr[i * 33 + lane] = valid ? f[i] : 0.f;
@@ -101,17 +103,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& P, const u
       sa += __shfl_xor_sync(0xffffffffu, sa, 16);
       sb += __shfl_xor_sync(0xffffffffu, sb, 16);
       __syncwarp();
-      if (lane < 16) { red[(q * 2 + 0) * 16 + lane] = sa; red[(q * 2 + 1) * 16 + lane] = sb; }
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      if (q == 0 && lane < 16 && (c0 + lane) < P.Cout) {
-        float a = 0.f, b = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) { a += red[(w * 2 + 0) * 16 + lane]; b += red[(w * 2 + 1) * 16 + lane]; }
-        float* dst = P.stats + (size_t)tile_m * 2 * P.Cout;
-        dst[c0 + lane] = a;
-        dst[P.Cout + c0 + lane] = b;
-      }
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      if (lane < 16) { red[(q * 2 + 0) * kStatN + ch * 16 + lane] = sa; red[(q * 2 + 1) * kStatN + ch * 16 + lane] = sb; }
     }
     const bool live = valid && c0 < P.Cout;
     if (live) {
@@ -156,6 +148,17 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& P, const u
       op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
+  }
+  if (P.stats) {
+    asm volatile("bar.sync 1, 128;\n" ::: "memory");
+    float* dst = P.stats + (size_t)tile_m * 2 * P.Cout;
+    for (int i = q * 32 + lane; i < 2 * kStatN; i += 128) {
+      const int which = i / kStatN, cc = i - which * kStatN;
+      if (n0 + cc < P.Cout)
+        dst[which * P.Cout + n0 + cc] = ((red[(0 * 2 + which) * kStatN + cc] + red[(1 * 2 + which) * kStatN + cc]) +
+                                         red[(2 * 2 + which) * kStatN + cc]) + red[(3 * 2 + which) * kStatN + cc];
+    }
+    asm volatile("bar.sync 1, 128;\n" ::: "memory");       // red / the transposes are reused by this CTA's next tile
   }
 }
 

@@ -234,29 +234,34 @@ struct FinArgs {
 __global__ void colsum_finalize_kernel(const float* __restrict__ m, int rows, int cols, int rows_per_slab,
                                        double* __restrict__ out /*[gridDim.y][cols]*/, unsigned int* __restrict__ ticket,
                                        const FinArgs A) {
-  const int col = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int lane = threadIdx.x >> 6;                       // 0..3
+  // a block owns 64 columns x one slab of rows.  Modes 0/1 (two sums per channel): the 64 columns are channels
+  // [32 bx, 32 bx + 32) of BOTH halves, so the last block of a column group can finalise its 32 channels on its own —
+  // all column groups finish in parallel (a single last block for all channels serialised ~30 us per layer).
+  const int C = A.C, j = threadIdx.x & 63, lane = threadIdx.x >> 6;      // lane = 0..3 row lane
+  const int ch = A.mode == 2 ? blockIdx.x * 64 + j : blockIdx.x * 32 + (j & 31);
+  const int col = A.mode == 2 ? ch : (j >> 5) * C + ch;
+  const bool ok = ch < C;
   const int r0 = blockIdx.y * rows_per_slab;
   const int r1 = min(rows, r0 + rows_per_slab);
   double acc = 0.0;
-  if (col < cols)
+  if (ok)
     for (int r = r0 + lane; r < r1; r += 4) acc += (double)m[(size_t)r * cols + col];
   __shared__ double sm[4][64];
   __shared__ int s_last;
-  sm[lane][threadIdx.x & 63] = acc;
+  sm[lane][j] = acc;
   __syncthreads();
-  if (lane == 0 && col < cols)
-    out[(size_t)blockIdx.y * cols + col] = ((sm[0][threadIdx.x] + sm[1][threadIdx.x]) + sm[2][threadIdx.x]) + sm[3][threadIdx.x];
+  if (lane == 0 && ok) out[(size_t)blockIdx.y * cols + col] = ((sm[0][j] + sm[1][j]) + sm[2][j]) + sm[3][j];
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket + blockIdx.x, 1u) == gridDim.y - 1;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const int slabs = gridDim.y, C = A.C;
+  const int slabs = gridDim.y;
   const int ry = threadIdx.x >> 5;
-  for (int c0 = 0; c0 < C; c0 += 32) {
-    const int c = c0 + (threadIdx.x & 31);
+  const int ngroups = A.mode == 2 ? 2 : 1;
+  for (int gi = 0; gi < ngroups; ++gi) {
+    const int c = (A.mode == 2 ? blockIdx.x * 64 + gi * 32 : blockIdx.x * 32) + (threadIdx.x & 31);
     double s, t;
     if (A.mode == 2) slab_sums(out, slabs, (size_t)C, 0, -1, c, c < C, &s, &t);
     else slab_sums(out, slabs, (size_t)2 * C, 0, C, c, c < C, &s, &t);
@@ -299,9 +304,10 @@ static inline int32_t launch_colsum_finalize(const float* m, int rows, int cols,
   slabs = (rows + rps - 1) / rps;
   // the ticket lives behind the slab sums (c3d_bn_scratch_bytes reserves it)
   unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (size_t)kSlabs * cols);
-  cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st);
+  const int groups = A.mode == 2 ? (A.C + 63) / 64 : (A.C + 31) / 32;        // one ticket per column group (<= 64)
+  cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int) * groups, st);
   if (e != cudaSuccess) return set_error(C3D_ECUDA, "colsum ticket: %s", cudaGetErrorString(e));
-  dim3 grid((cols + 63) / 64, slabs);
+  dim3 grid(groups, slabs);
   colsum_finalize_kernel<<<grid, 256, 0, st>>>(m, rows, cols, rps, scratch, ticket, A);
   return C3D_OK;
 }
@@ -679,7 +685,7 @@ using namespace c3d;
 #define C3D_REQ(cond, msg) do { if (!(cond)) return set_error(C3D_EINVAL, msg); } while (0)
 
 extern "C" size_t c3d_bn_scratch_bytes(int32_t C) {      // slab sums + the last-block ticket behind them
-  return ((size_t)kSlabs * 2 * (size_t)(C > 0 ? C : 0) + 2) * sizeof(double);
+  return ((size_t)kSlabs * 2 * (size_t)(C > 0 ? C : 0) + 64) * sizeof(double);
 }
 extern "C" int32_t c3d_bn_finalize(const float* partial, int32_t rows, int32_t C, double count, float eps,
                                    float momentum, float* running_mean, float* running_var, float* mean_out,

@@ -99,7 +99,7 @@ def bn_finalize(stats, count, eps, momentum, running_mean, running_var):
     rows, _, C = stats.shape
     mean = torch.empty(C, device=stats.device, dtype=torch.float32)
     rstd = torch.empty(C, device=stats.device, dtype=torch.float32)
-    scratch = torch.empty(128 * 2 * C + 2, device=stats.device, dtype=torch.float64)
+    scratch = torch.empty(128 * 2 * C + 64, device=stats.device, dtype=torch.float64)
     _lib.check(L.c3d_bn_finalize(_p(stats), rows, C, float(count), eps, momentum, _p(running_mean), _p(running_var),
                                  _p(mean), _p(rstd), _p(scratch), _st()), launches=2)
     return mean, rstd
@@ -144,7 +144,7 @@ def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres, froz
     coef = torch.empty((3, C), device=y.device, dtype=torch.float32)
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
-    scratch = torch.empty(128 * 2 * C + 2, device=y.device, dtype=torch.float64)
+    scratch = torch.empty(128 * 2 * C + 64, device=y.device, dtype=torch.float64)
     _lib.check(L.c3d_bn_bwd(_p(dout), _p(out), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), int(relu), int(frozen), _p(partial), _p(coef),
                             _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, ds, 0, 0, _p(scratch), _st()), launches=4)
     return dy, dres
@@ -356,7 +356,7 @@ def bias_act_bwd(dout, out, relu, dbias):
     dout = dout.contiguous()
     blocks = L.c3d_bn_bwd_blocks(P, C)
     partial = torch.empty((blocks, C), device=dout.device, dtype=torch.float32)
-    scratch = torch.empty(128 * 2 * C + 2, device=dout.device, dtype=torch.float64)
+    scratch = torch.empty(128 * 2 * C + 64, device=dout.device, dtype=torch.float64)
     dz = torch.empty(dout.shape, device=dout.device, dtype=torch.bfloat16)
     flags = int(dout.dtype == torch.float32) | (2 if (out is not None and out.dtype == torch.float32) else 0)
     _lib.check(L.c3d_bias_act_bwd(_p(dout), _p(out), int(relu), flags, _p(dz), _p(partial),
