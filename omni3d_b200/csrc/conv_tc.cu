@@ -26,6 +26,7 @@ namespace c3d {
 using bf16 = __nv_bfloat16;
 
 struct ConvKParams {
+  int dbg;                     // lab switches (C3D_CONV_DBG): 1 no MMA, 2 no TMA, 4 no B, 8 no A, 16 no epilogue
   int N, Ho, Wo, Cout;
   int KH, KW, stride, pad;
   int TH, TW, tiles_h, tiles_w;
@@ -312,9 +313,10 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
           const int kh = tap / P.KW, kw = tap - kh * P.KW;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kTileBytes;
-          ptx::mbar_expect_tx(&full_bar[stage], a_bytes + (uint32_t)S::kBBytes);
-          ptx::tma_load_4d(sa, &tmap_x, &full_bar[stage], kc * BLOCK_K, wi0 + kw, hi0 + kh, img);
-          ptx::tma_load_2d(sa + S::kABytes, &tmap_w, &full_bar[stage], tap * P.Cin + kc * BLOCK_K, n0);
+          if (P.dbg & 2) { ptx::mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
+          ptx::mbar_expect_tx(&full_bar[stage], ((P.dbg & 8) ? 0u : a_bytes) + ((P.dbg & 4) ? 0u : (uint32_t)S::kBBytes));
+          if (!(P.dbg & 8)) ptx::tma_load_4d(sa, &tmap_x, &full_bar[stage], kc * BLOCK_K, wi0 + kw, hi0 + kh, img);
+          if (!(P.dbg & 4)) ptx::tma_load_2d(sa + S::kABytes, &tmap_w, &full_bar[stage], tap * P.Cin + kc * BLOCK_K, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -331,6 +333,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         const uint32_t tacc = tmem_base + (uint32_t)acc * kAccCols;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
+          if (P.dbg & 1) { ptx::mbar_arrive(&empty_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
           ptx::tcgen05_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * S::kTileBytes);
           const uint64_t da = ptx::make_smem_desc(sa, 16, 8 * kSwizzle, lt);
@@ -354,6 +357,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
       const int img = tile_m / (P.tiles_w * P.tiles_h);
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tcgen05_fence_after();
+      if (!(P.dbg & 16))
       conv_epilogue_tile<BLOCK_N>(P, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccCols, q, lane, img,
                                   th_i * P.TH, tw_i * P.TW, n0, tile_m, red, smem + S::kStgOffset);
       // this warp is done reading the accumulator: hand it back to the MMA issuer
@@ -438,6 +442,7 @@ struct WgradKParams {
   int ca, a_chunks_max;                      // A boxes: width ca channels
   float* dw;                                 // fp32, accumulated with atomics
   int oihw;                                  // 0: dw is [Cout][KH][KW][Cin]; 1: [Cout][Cin][KH][KW] (master layout)
+  int dbg;                                   // lab switches (C3D_WGRAD_DBG): 1 no MMA, 2 no TMA, 4 no B loads, 8 no A loads
   int lin;                                   // 1: fully-connected layer (c3d_linear_wgrad): x is (rows, KH*KW*Cin) with the
                                              // features in (tap, ci) order — box b reads channels [b*cw, (b+1)*cw) with no
                                              // spatial shift; KH/KW/Cin only drive the epilogue's master-layout index
@@ -446,20 +451,20 @@ struct WgradKParams {
 // PIX = pixels (GEMM K) per pipeline stage: 128 px x 2 stages or 64 px x 4 stages (same 192 KB).  The deeper pipeline
 // hides the TMA latency (a 128-px stage is only ~0.5 us of MMA work, less than one L2/HBM round trip), the larger
 // box fits feature maps whose rows do not tile into 64-pixel boxes (20x20 -> 4x20).
-template <int STAGES, int PIX>
+template <int STAGES, int PIX, int NCOLS = 256>
 struct WgradSmem {
   static constexpr int kABytes = PIX * 128 * 2;            // up to two [PIX px][64 ch] chunks (or narrower)
-  static constexpr int kBBytes = PIX * 256 * 2;            // 256 columns x PIX pixels
+  static constexpr int kBBytes = PIX * NCOLS * 2;          // NCOLS columns x PIX pixels
   static constexpr int kStageBytes = kABytes + kBBytes;    // 96 KB (PIX 128) / 48 KB (PIX 64)
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;
 };
 
-template <int STAGES, int PIX>
+template <int STAGES, int PIX, int NCOLS = 256>
 __global__ void __launch_bounds__(192)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                      const WgradKParams P) {
-  using S = WgradSmem<STAGES, PIX>;
+  using S = WgradSmem<STAGES, PIX, NCOLS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
@@ -496,16 +501,21 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
     if (warp == 0) {
       if (ptx::elect_one()) {
         int stage = 0; uint32_t phase = 0;
-        const uint32_t bytes = (uint32_t)(R * 2 * (a_chunks * P.ca + nb * P.cw));
+        uint32_t bytes = (uint32_t)(R * 2 * (a_chunks * P.ca + nb * P.cw));
+        if (P.dbg & 4) bytes = (uint32_t)(R * 2 * (a_chunks * P.ca));
+        if (P.dbg & 8) bytes = (uint32_t)(R * 2 * (nb * P.cw));
         for (int t = t_begin; t < t_end; ++t) {
           const int tw_i = t % P.tiles_w, th_i = (t / P.tiles_w) % P.tiles_h, img = t / (P.tiles_w * P.tiles_h);
           const int ho0 = th_i * P.RH, wo0 = tw_i * P.RW;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
+          if (P.dbg & 2) { ptx::mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
           ptx::mbar_expect_tx(&full_bar[stage], bytes);
+          if (!(P.dbg & 8))
           for (int c = 0; c < a_chunks; ++c)
             ptx::tma_load_4d(sa + c * a_box_bytes, &tmap_dy, &full_bar[stage], co0 + P.ca * c, wo0, ho0, img);
+          if (!(P.dbg & 4))
           for (int b = 0; b < nb; ++b) {
             const int box = box0 + b;
             const int tap = box / P.nci, chunk = box - tap * P.nci;
@@ -530,6 +540,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
         const uint32_t a_kstep = (16 * P.ca * 2) >> 4, b_kstep = (16 * P.cw * 2) >> 4;
         for (int t = t_begin; t < t_end; ++t) {
           ptx::mbar_wait(&full_bar[stage], phase);
+          if (P.dbg & 1) { ptx::mbar_arrive(&empty_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
           ptx::tcgen05_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * S::kStageBytes);
           const uint32_t sb = sa + S::kABytes;
@@ -669,6 +680,7 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
 
   ConvKParams P;
   P.N = d->N; P.Ho = Ho; P.Wo = Wo; P.Cout = Cout; P.KH = d->KH; P.KW = d->KW; P.stride = d->stride; P.pad = d->pad;
+  { const char* e = getenv("C3D_CONV_DBG"); P.dbg = e ? atoi(e) : 0; }
   pick_tile(Ho, Wo, d->stride, &P.TH, &P.TW);
   P.tiles_h = (Ho + P.TH - 1) / P.TH; P.tiles_w = (Wo + P.TW - 1) / P.TW;
   P.kc_blocks = Cin / BK; P.Cin = Cin;
@@ -784,6 +796,7 @@ static int32_t wgrad_impl(const c3d_conv_desc* d, const void* x, const void* dy,
   P.N = d->N; P.Ho = Ho; P.Wo = Wo; P.Cout = Cout; P.Cin = Cin;
   P.KH = d->KH; P.KW = d->KW; P.stride = d->stride; P.pad = d->pad;
   P.lin = lin_c > 0;
+  { const char* e = getenv("C3D_WGRAD_DBG"); P.dbg = e ? atoi(e) : 0; }
   if (P.lin) {
     if (d->KH != 1 || d->KW != 1 || d->stride != 1 || d->pad != 0 || lin_c % 16 != 0 || (long long)lin_c * lin_pp != Cin)
       return set_error(C3D_EINVAL, "linear wgrad: bad feature factorisation %d x %d != %d", lin_c, lin_pp, Cin);
@@ -804,7 +817,8 @@ static int32_t wgrad_impl(const c3d_conv_desc* d, const void* x, const void* dy,
   const int Cin_e = P.Cin;                       // channels per tap in the epilogue's index space
   P.cw = (Cin_e % 64 == 0) ? 64 : (Cin_e % 32 == 0 ? 32 : 16);
   P.nci = Cin_e / P.cw;
-  P.boxes_per_cta = 256 / P.cw;
+  static const bool n128 = getenv("C3D_WGRAD_N128") != nullptr;
+  P.boxes_per_cta = (n128 ? 128 : 256) / P.cw;
   P.total_boxes = taps * P.nci;
   P.ca = (Cout % 64 == 0) ? 64 : (Cout % 32 == 0 ? 32 : 16);
   P.a_chunks_max = 128 / P.ca;                  // chunks beyond Cout are not loaded (those D rows are never stored)
@@ -854,10 +868,14 @@ static int32_t wgrad_impl(const c3d_conv_desc* d, const void* x, const void* dy,
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                WgradSmem<4, 64>::kTotal);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<3, 128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               WgradSmem<3, 128, 128>::kTotal);
     if (e != cudaSuccess) return set_error(C3D_ECUDA, "wgrad smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  if (pix64) conv_wgrad_tc_kernel<4, 64><<<grid, 192, WgradSmem<4, 64>::kTotal, st>>>(mdy, mx, P);
+  if (n128 && !pix64) conv_wgrad_tc_kernel<3, 128, 128><<<grid, 192, WgradSmem<3, 128, 128>::kTotal, st>>>(mdy, mx, P);
+  else if (pix64) conv_wgrad_tc_kernel<4, 64><<<grid, 192, WgradSmem<4, 64>::kTotal, st>>>(mdy, mx, P);
   else conv_wgrad_tc_kernel<2, 128><<<grid, 192, WgradSmem<2, 128>::kTotal, st>>>(mdy, mx, P);
   return check_launch("conv_wgrad_tc_kernel");
 }

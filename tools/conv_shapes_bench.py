@@ -70,7 +70,7 @@ def timeit(fn):
 out = []
 tot = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0, "gflop": 0.0}
 for name, H, W, Cin, Cout, k, s, p, rc, count, has_dgrad in SHAPES:
-    if only and only not in name:
+    if only and not any(o in name for o in only.split(",")):
         continue
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.randn(N, H, W, Cin, device="cuda", generator=g).bfloat16()
