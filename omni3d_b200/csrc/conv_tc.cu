@@ -21,6 +21,14 @@
 #include "c3d_common.cuh"
 #include "ptx_sm100.cuh"
 
+// lab switches (tools/conv_lab.sh, tools/wgrad_lab.sh): compiled in only with -DC3D_LAB (libc3d_lab.so) — even a uniform
+// branch on a kernel parameter inside the pipeline loops cost the persistent kernel 14 % (profiles/r02_summary.md)
+#ifdef C3D_LAB
+#define C3D_DBG(P, bit) ((P).dbg & (bit))
+#else
+#define C3D_DBG(P, bit) (0)
+#endif
+
 namespace c3d {
 
 using bf16 = __nv_bfloat16;
@@ -313,10 +321,10 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
           const int kh = tap / P.KW, kw = tap - kh * P.KW;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kTileBytes;
-          if (P.dbg & 2) { ptx::mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
-          ptx::mbar_expect_tx(&full_bar[stage], ((P.dbg & 8) ? 0u : a_bytes) + ((P.dbg & 4) ? 0u : (uint32_t)S::kBBytes));
-          if (!(P.dbg & 8)) ptx::tma_load_4d(sa, &tmap_x, &full_bar[stage], kc * BLOCK_K, wi0 + kw, hi0 + kh, img);
-          if (!(P.dbg & 4)) ptx::tma_load_2d(sa + S::kABytes, &tmap_w, &full_bar[stage], tap * P.Cin + kc * BLOCK_K, n0);
+          if C3D_DBG(P, 2) { ptx::mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
+          ptx::mbar_expect_tx(&full_bar[stage], (C3D_DBG(P, 8) ? 0u : a_bytes) + (C3D_DBG(P, 4) ? 0u : (uint32_t)S::kBBytes));
+          if (!C3D_DBG(P, 8)) ptx::tma_load_4d(sa, &tmap_x, &full_bar[stage], kc * BLOCK_K, wi0 + kw, hi0 + kh, img);
+          if (!C3D_DBG(P, 4)) ptx::tma_load_2d(sa + S::kABytes, &tmap_w, &full_bar[stage], tap * P.Cin + kc * BLOCK_K, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -333,7 +341,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
         const uint32_t tacc = tmem_base + (uint32_t)acc * kAccCols;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
-          if (P.dbg & 1) { ptx::mbar_arrive(&empty_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
+          if C3D_DBG(P, 1) { ptx::mbar_arrive(&empty_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
           ptx::tcgen05_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * S::kTileBytes);
           const uint64_t da = ptx::make_smem_desc(sa, 16, 8 * kSwizzle, lt);
@@ -357,7 +365,7 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
       const int img = tile_m / (P.tiles_w * P.tiles_h);
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tcgen05_fence_after();
-      if (!(P.dbg & 16))
+      if (!C3D_DBG(P, 16))
       conv_epilogue_tile<BLOCK_N>(P, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccCols, q, lane, img,
                                   th_i * P.TH, tw_i * P.TW, n0, tile_m, red, smem + S::kStgOffset);
       // this warp is done reading the accumulator: hand it back to the MMA issuer
@@ -442,6 +450,7 @@ struct WgradKParams {
   int ca, a_chunks_max;                      // A boxes: width ca channels
   float* dw;                                 // fp32, accumulated with atomics
   int oihw;                                  // 0: dw is [Cout][KH][KW][Cin]; 1: [Cout][Cin][KH][KW] (master layout)
+  int big, mc;                               // 1: 5-D tensor maps — ONE box carries all channel chunks of dY (and mc chunks of X)
   int dbg;                                   // lab switches (C3D_WGRAD_DBG): 1 no MMA, 2 no TMA, 4 no B loads, 8 no A loads
   int lin;                                   // 1: fully-connected layer (c3d_linear_wgrad): x is (rows, KH*KW*Cin) with the
                                              // features in (tap, ci) order — box b reads channels [b*cw, (b+1)*cw) with no
@@ -483,7 +492,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
   const int R = P.RH * P.RW;
   int a_chunks = (P.Cout - co0 + P.ca - 1) / P.ca;
   if (a_chunks > P.a_chunks_max) a_chunks = P.a_chunks_max;
-  const uint32_t a_box_bytes = (uint32_t)(PIX * P.ca * 2), b_box_bytes = (uint32_t)(PIX * P.cw * 2);
+  // distance between channel chunks in shared memory: a full PIX-pixel slot per box, or (5-D boxes) the dense box pitch
+  const uint32_t a_box_bytes = (uint32_t)((P.big ? R : PIX) * P.ca * 2), b_box_bytes = (uint32_t)((P.big ? R : PIX) * P.cw * 2);
 
   if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&tmap_dy); ptx::prefetch_tensormap(&tmap_x); }
   if (warp == 1 && lane == 0) {
@@ -501,21 +511,37 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
     if (warp == 0) {
       if (ptx::elect_one()) {
         int stage = 0; uint32_t phase = 0;
-        uint32_t bytes = (uint32_t)(R * 2 * (a_chunks * P.ca + nb * P.cw));
-        if (P.dbg & 4) bytes = (uint32_t)(R * 2 * (a_chunks * P.ca));
-        if (P.dbg & 8) bytes = (uint32_t)(R * 2 * (nb * P.cw));
+        uint32_t bytes = (uint32_t)(R * 2 * ((P.big ? P.a_chunks_max : a_chunks) * P.ca + nb * P.cw));
+        if C3D_DBG(P, 4) bytes = (uint32_t)(R * 2 * (a_chunks * P.ca));
+        if C3D_DBG(P, 8) bytes = (uint32_t)(R * 2 * (nb * P.cw));
         for (int t = t_begin; t < t_end; ++t) {
           const int tw_i = t % P.tiles_w, th_i = (t / P.tiles_w) % P.tiles_h, img = t / (P.tiles_w * P.tiles_h);
           const int ho0 = th_i * P.RH, wo0 = tw_i * P.RW;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
-          if (P.dbg & 2) { ptx::mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
+          if C3D_DBG(P, 2) { ptx::mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
           ptx::mbar_expect_tx(&full_bar[stage], bytes);
-          if (!(P.dbg & 8))
+          if (P.big) {
+            if (!C3D_DBG(P, 8)) ptx::tma_load_5d(sa, &tmap_dy, &full_bar[stage], 0, wo0, ho0, co0 / P.ca, img);
+            if (!C3D_DBG(P, 4))
+            for (int b = 0; b < nb; b += P.mc) {
+              const int box = box0 + b;
+              const int tap = box / P.nci, chunk = box - tap * P.nci;
+              const int kh = tap / P.KW, kw = tap - kh * P.KW;
+              if (P.lin)
+                ptx::tma_load_5d(sb + b * b_box_bytes, &tmap_x, &full_bar[stage], 0, wo0, ho0, box, img);
+              else
+                ptx::tma_load_5d(sb + b * b_box_bytes, &tmap_x, &full_bar[stage], 0, wo0 * P.stride + kw - P.pad,
+                                 ho0 * P.stride + kh - P.pad, chunk, img);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          if (!C3D_DBG(P, 8))
           for (int c = 0; c < a_chunks; ++c)
             ptx::tma_load_4d(sa + c * a_box_bytes, &tmap_dy, &full_bar[stage], co0 + P.ca * c, wo0, ho0, img);
-          if (!(P.dbg & 4))
+          if (!C3D_DBG(P, 4))
           for (int b = 0; b < nb; ++b) {
             const int box = box0 + b;
             const int tap = box / P.nci, chunk = box - tap * P.nci;
@@ -540,7 +566,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
         const uint32_t a_kstep = (16 * P.ca * 2) >> 4, b_kstep = (16 * P.cw * 2) >> 4;
         for (int t = t_begin; t < t_end; ++t) {
           ptx::mbar_wait(&full_bar[stage], phase);
-          if (P.dbg & 1) { ptx::mbar_arrive(&empty_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
+          if C3D_DBG(P, 1) { ptx::mbar_arrive(&empty_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
           ptx::tcgen05_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * S::kStageBytes);
           const uint32_t sb = sa + S::kABytes;
@@ -680,7 +706,10 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
 
   ConvKParams P;
   P.N = d->N; P.Ho = Ho; P.Wo = Wo; P.Cout = Cout; P.KH = d->KH; P.KW = d->KW; P.stride = d->stride; P.pad = d->pad;
+  P.dbg = 0;
+#ifdef C3D_LAB
   { const char* e = getenv("C3D_CONV_DBG"); P.dbg = e ? atoi(e) : 0; }
+#endif
   pick_tile(Ho, Wo, d->stride, &P.TH, &P.TW);
   P.tiles_h = (Ho + P.TH - 1) / P.TH; P.tiles_w = (Wo + P.TW - 1) / P.TW;
   P.kc_blocks = Cin / BK; P.Cin = Cin;
@@ -796,7 +825,10 @@ static int32_t wgrad_impl(const c3d_conv_desc* d, const void* x, const void* dy,
   P.N = d->N; P.Ho = Ho; P.Wo = Wo; P.Cout = Cout; P.Cin = Cin;
   P.KH = d->KH; P.KW = d->KW; P.stride = d->stride; P.pad = d->pad;
   P.lin = lin_c > 0;
+  P.dbg = 0;
+#ifdef C3D_LAB
   { const char* e = getenv("C3D_WGRAD_DBG"); P.dbg = e ? atoi(e) : 0; }
+#endif
   if (P.lin) {
     if (d->KH != 1 || d->KW != 1 || d->stride != 1 || d->pad != 0 || lin_c % 16 != 0 || (long long)lin_c * lin_pp != Cin)
       return set_error(C3D_EINVAL, "linear wgrad: bad feature factorisation %d x %d != %d", lin_c, lin_pp, Cin);
@@ -838,6 +870,37 @@ static int32_t wgrad_impl(const c3d_conv_desc* d, const void* x, const void* dy,
   const long long xps = d->x_pix_stride ? d->x_pix_stride : Cin;
   const long long yps = d->y_pix_stride ? d->y_pix_stride : Cout;
   CUtensorMap mdy, mx;
+  // 5-D maps (channel-chunk axis OUTSIDE the pixel axes): one box = [chunks][RH][RW][64 ch], the MN-major operand layout
+  // with LBO = RH*RW*128 B — a third of the TMA instructions per stage (the loop is bound by boxes issued, not bytes)
+  static const bool no_big = getenv("C3D_WGRAD_NO_BIGBOX") != nullptr;
+  P.big = 0; P.mc = 1;
+  if (!no_big && !C3D_DBG(P, 12)) {
+    const int nchunks_x = P.lin ? P.total_boxes : P.nci;
+    int mc = P.boxes_per_cta;
+    while (mc > 1 && nchunks_x % mc != 0) mc >>= 1;
+    const int nca = (Cout + P.ca - 1) / P.ca;
+    const long long ximg = d->x_img_stride ? d->x_img_stride : (long long)d->W * d->H;
+    cuuint64_t dy_dims[5] = {(cuuint64_t)P.ca, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)nca, (cuuint64_t)d->N};
+    cuuint64_t dy_str[4] = {(cuuint64_t)yps * 2, (cuuint64_t)yps * 2 * Wo, (cuuint64_t)P.ca * 2, (cuuint64_t)yps * 2 * Wo * Ho};
+    cuuint32_t dy_box[5] = {(cuuint32_t)P.ca, (cuuint32_t)P.RW, (cuuint32_t)P.RH, (cuuint32_t)P.a_chunks_max, 1};
+    cuuint32_t one5[5] = {1, 1, 1, 1, 1};
+    cuuint64_t x_dims[5] = {(cuuint64_t)P.cw, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)nchunks_x, (cuuint64_t)d->N};
+    cuuint64_t x_str[4] = {(cuuint64_t)xps * 2, (cuuint64_t)xps * 2 * d->W, (cuuint64_t)P.cw * 2, (cuuint64_t)xps * 2 * ximg};
+    cuuint32_t x_box[5] = {(cuuint32_t)P.cw, (cuuint32_t)(P.RW * d->stride), (cuuint32_t)(P.RH * d->stride), (cuuint32_t)mc, 1};
+    cuuint32_t x_es[5] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1, 1};
+    CUresult r1 = enc(&mdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), dy_dims, dy_str, dy_box, one5,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz(P.ca * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), x_dims, x_str, x_box, x_es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz(P.cw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS) { P.big = 1; P.mc = mc; }
+    else {
+      static bool warned = false;
+      if (!warned) { fprintf(stderr, "c3d wgrad: 5-D tensor map rejected (%d, %d), using per-chunk boxes\n", (int)r1, (int)r2); warned = true; }
+    }
+  }
+  if (!P.big) {
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)d->N};
     cuuint64_t strides[3] = {(cuuint64_t)yps * 2, (cuuint64_t)yps * 2 * Wo, (cuuint64_t)yps * 2 * Wo * Ho};
@@ -858,6 +921,7 @@ static int32_t wgrad_impl(const c3d_conv_desc* d, const void* x, const void* dy,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz(P.cw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(C3D_ECUDA, "encode x tensormap failed: %d", (int)r);
+  }
   }
   dim3 grid((unsigned)splits, (unsigned)groups, (unsigned)co_tiles);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
