@@ -460,20 +460,23 @@ struct WgradKParams {
 // PIX = pixels (GEMM K) per pipeline stage: 128 px x 2 stages or 64 px x 4 stages (same 192 KB).  The deeper pipeline
 // hides the TMA latency (a 128-px stage is only ~0.5 us of MMA work, less than one L2/HBM round trip), the larger
 // box fits feature maps whose rows do not tile into 64-pixel boxes (20x20 -> 4x20).
-template <int STAGES, int PIX, int NCOLS = 256>
+template <int STAGES, int PIX, int NCOLS = 256, int MT = 1>
 struct WgradSmem {
-  static constexpr int kABytes = PIX * 128 * 2;            // up to two [PIX px][64 ch] chunks (or narrower)
+  static constexpr int kABytes = PIX * 128 * MT * 2;       // MT x (up to two [PIX px][64 ch] chunks (or narrower))
   static constexpr int kBBytes = PIX * NCOLS * 2;          // NCOLS columns x PIX pixels
   static constexpr int kStageBytes = kABytes + kBBytes;    // 96 KB (PIX 128) / 48 KB (PIX 64)
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;
 };
 
-template <int STAGES, int PIX, int NCOLS = 256>
+// MT = 128-row output-channel tiles per CTA: with MT = 2 one X tile feeds two accumulators (2 x 256 TMEM columns), so a
+// stage moves 64 KB for 2 x 4 MMAs instead of 96 KB for 8 — a third less L2 -> SM traffic per FLOP (the L2 port, ~42 B/clk/SM,
+// is what bounds this loop) and three pipeline stages instead of two.
+template <int STAGES, int PIX, int NCOLS = 256, int MT = 1>
 __global__ void __launch_bounds__(192)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                      const WgradKParams P) {
-  using S = WgradSmem<STAGES, PIX, NCOLS>;
+  using S = WgradSmem<STAGES, PIX, NCOLS, MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
@@ -483,7 +486,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int split = blockIdx.x, group = blockIdx.y, co_tile = blockIdx.z;
-  const int co0 = co_tile * 128;
+  const int co0 = co_tile * 128 * MT;
   const int box0 = group * P.boxes_per_cta;
   const int nb = min(P.boxes_per_cta, P.total_boxes - box0);       // boxes (taps x ci chunks) of this CTA
   const int ncols = nb * P.cw;                                     // UMMA N (multiple of 16, <= 256)
@@ -501,7 +504,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc<256>(tmem_ptr);
+  if (warp == 2) ptx::tmem_alloc<256 * MT>(tmem_ptr);
   ptx::tcgen05_fence_before();
   __syncthreads();
   ptx::tcgen05_fence_after();
@@ -572,9 +575,14 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
           const uint32_t sb = sa + S::kABytes;
           const uint64_t da = ptx::make_smem_desc(sa, a_box_bytes, a_sbo, lt_a);
           const uint64_t db = ptx::make_smem_desc(sb, b_box_bytes, b_sbo, lt_b);
-          for (int k = 0; k < ksteps; ++k)
-            ptx::umma_bf16(tmem_base, da + (uint64_t)(a_kstep * k), db + (uint64_t)(b_kstep * k), idesc,
-                           (t != t_begin || k != 0) ? 1u : 0u);
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            // output-channel tile m = chunks [m * 128 / ca, (m + 1) * 128 / ca) of the dY box
+            const uint64_t dam = da + (uint64_t)((m * (128 / P.ca) * a_box_bytes) >> 4);
+            for (int k = 0; k < ksteps; ++k)
+              ptx::umma_bf16(tmem_base + (uint32_t)(m * 256), dam + (uint64_t)(a_kstep * k), db + (uint64_t)(b_kstep * k), idesc,
+                             (t != t_begin || k != 0) ? 1u : 0u);
+          }
           ptx::umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -582,14 +590,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
       }
     } else {
       const int q = warp & 3;
-      const int co = co0 + q * 32 + lane;
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tcgen05_fence_after();
       const int taps = P.KH * P.KW;
 #pragma unroll 1
-      for (int ch = 0; ch * 16 < ncols; ++ch) {
+      for (int mch = 0; mch * 16 < ncols * MT; ++mch) {
+        const int m = MT == 1 ? 0 : (mch * 16) / ncols, ch = mch - m * (ncols / 16);
+        const int co = co0 + m * 128 + q * 32 + lane;
         uint32_t v[16];
-        ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), v);
+        ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * 256 + ch * 16), v);
         ptx::tmem_ld_wait();
         const int n = ch * 16;
         const int box = box0 + n / P.cw;
@@ -615,7 +624,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
   __syncthreads();
   if (warp == 2) {
     ptx::tcgen05_fence_after();
-    ptx::tmem_dealloc<256>(tmem_base);
+    ptx::tmem_dealloc<256 * MT>(tmem_base);
   }
 }
 
@@ -841,7 +850,12 @@ static int32_t wgrad_impl(const c3d_conv_desc* d, const void* x, const void* dy,
   // measured (profiles/r02): the 4 x 64-pixel pipeline is SLOWER (fpn 3x3 @160: 0.92 -> 1.83 ms) — the loop is bound by the
   // per-stage barrier round trip of the single MMA-issuing lane, not by TMA latency; kept as an opt-in experiment
   static const bool want64 = getenv("C3D_WGRAD_PIX64") != nullptr;
-  const bool pix64 = want64 && eff64 >= 0.93 * eff128;
+  static const bool n128 = getenv("C3D_WGRAD_N128") != nullptr;
+  static const bool no_mt2 = getenv("C3D_WGRAD_NO_MT2") != nullptr;
+  // two output-channel tiles per CTA (M = 256 through two accumulators) over 3 x 64-pixel stages: wide layers whose map tiles
+  // into 64-pixel boxes
+  const bool mt2 = !no_mt2 && !n128 && Cout >= 256 && eff64 >= 0.93 * eff128;
+  const bool pix64 = mt2 || (want64 && eff64 >= 0.93 * eff128);
   if (pix64) { P.RH = rh64; P.RW = rw64; }
   P.tiles_h = (Ho + P.RH - 1) / P.RH; P.tiles_w = (Wo + P.RW - 1) / P.RW;
   P.num_tiles = d->N * P.tiles_h * P.tiles_w;
@@ -849,13 +863,12 @@ static int32_t wgrad_impl(const c3d_conv_desc* d, const void* x, const void* dy,
   const int Cin_e = P.Cin;                       // channels per tap in the epilogue's index space
   P.cw = (Cin_e % 64 == 0) ? 64 : (Cin_e % 32 == 0 ? 32 : 16);
   P.nci = Cin_e / P.cw;
-  static const bool n128 = getenv("C3D_WGRAD_N128") != nullptr;
   P.boxes_per_cta = (n128 ? 128 : 256) / P.cw;
   P.total_boxes = taps * P.nci;
   P.ca = (Cout % 64 == 0) ? 64 : (Cout % 32 == 0 ? 32 : 16);
-  P.a_chunks_max = 128 / P.ca;                  // chunks beyond Cout are not loaded (those D rows are never stored)
+  P.a_chunks_max = (mt2 ? 256 : 128) / P.ca;    // chunks beyond Cout are not loaded (those D rows are never stored)
   const int groups = (P.total_boxes + P.boxes_per_cta - 1) / P.boxes_per_cta;
-  const int co_tiles = (Cout + 127) / 128;
+  const int co_tiles = mt2 ? (Cout + 255) / 256 : (Cout + 127) / 128;
   // split-K over pixels (1 CTA/SM): every split costs 128 x N fp32 atomics, so big weight tensors get exactly one
   // wave of CTAs (<= 148) while small ones (<= 64K elements: the pixel-heavy early layers) get ~4 waves for balance
   long long base = (long long)groups * co_tiles;
@@ -935,10 +948,14 @@ static int32_t wgrad_impl(const c3d_conv_desc* d, const void* x, const void* dy,
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<3, 128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                WgradSmem<3, 128, 128>::kTotal);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<3, 64, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               WgradSmem<3, 64, 256, 2>::kTotal);
     if (e != cudaSuccess) return set_error(C3D_ECUDA, "wgrad smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  if (n128 && !pix64) conv_wgrad_tc_kernel<3, 128, 128><<<grid, 192, WgradSmem<3, 128, 128>::kTotal, st>>>(mdy, mx, P);
+  if (mt2) conv_wgrad_tc_kernel<3, 64, 256, 2><<<grid, 192, WgradSmem<3, 64, 256, 2>::kTotal, st>>>(mdy, mx, P);
+  else if (n128 && !pix64) conv_wgrad_tc_kernel<3, 128, 128><<<grid, 192, WgradSmem<3, 128, 128>::kTotal, st>>>(mdy, mx, P);
   else if (pix64) conv_wgrad_tc_kernel<4, 64><<<grid, 192, WgradSmem<4, 64>::kTotal, st>>>(mdy, mx, P);
   else conv_wgrad_tc_kernel<2, 128><<<grid, 192, WgradSmem<2, 128>::kTotal, st>>>(mdy, mx, P);
   return check_launch("conv_wgrad_tc_kernel");

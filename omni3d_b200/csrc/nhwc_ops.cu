@@ -42,7 +42,7 @@ static inline int grid_for(long long work_items, int threads) {
 // Column sums of a [rows][cols] fp32 matrix in fixed order (deterministic): stage 1 = slabs of rows per
 // block (64 columns x 4 row lanes), doubles out; the LAST block then finishes over the <= kSlabs slabs
 // (colsum_finalize_kernel below).
-constexpr int kSlabs = 128;
+constexpr int kSlabs = 64;
 // partial: [rows][2][C] per-tile (sum, sumsq) from the conv epilogue -> slab sums -> statistics.
 // Second stage of the column sums: <= kSlabs rows of doubles.  A block is 32 channels x 8 row lanes; every lane sums
 // each 8th slab (16 loads instead of a 128-long serial chain), then the 8 partials are combined through shared memory.
@@ -53,10 +53,18 @@ __device__ __forceinline__ void slab_sums(const double* slab, int slabs, size_t 
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   double s = 0.0, t = 0.0;
   if (active) {
-    for (int r = ry; r < slabs; r += 8) {
-      s += __ldcg(slab + (size_t)r * row_stride + off0 + c);          // L2 loads: the slabs were written by other blocks
-      if (off1 >= 0) t += __ldcg(slab + (size_t)r * row_stride + off1 + c);
+    // L2 loads (the slabs were written by other blocks), all of a lane's <= kSlabs / 8 rows in flight at once: this runs in
+    // the ONE last block of a column group, so its load latency is the tail of every BatchNorm layer
+    double vs[kSlabs / 8], vt[kSlabs / 8];
+#pragma unroll
+    for (int i = 0; i < kSlabs / 8; ++i) {
+      const int r = ry + 8 * i;
+      const bool in = r < slabs;
+      vs[i] = in ? __ldcg(slab + (size_t)r * row_stride + off0 + c) : 0.0;
+      vt[i] = (in && off1 >= 0) ? __ldcg(slab + (size_t)r * row_stride + off1 + c) : 0.0;
     }
+#pragma unroll
+    for (int i = 0; i < kSlabs / 8; ++i) { s += vs[i]; t += vt[i]; }
   }
   sh[0][ry][cx] = s; sh[1][ry][cx] = t;
   __syncthreads();

@@ -193,14 +193,30 @@ __global__ void roi_align_fwd_sep_kernel(RoiLevels L, const float* __restrict__ 
       for (int k = 0; k < 8; ++k) a[k] = 0.f;
       if (fits && !none) {
         const int nr = ymax - ybase + 1, nc = xmax - xbase + 1;
+        // four footprint columns per step: the loads of a step are independent (and unconditional: columns past the
+        // footprint re-read its last column with weight 0), so a warp keeps 4 x 512 B in flight per row instead of 1
         for (int rr = 0; rr < nr; ++rr) {
           const float wr = __shfl_sync(0xffffffffu, wy, rr);
           if (wr == 0.f) continue;
-          const bf16* rowp = base + ((size_t)(ybase + rr) * W + xbase) * C + c;
-          for (int q = 0; q < nc; ++q) {
-            const float w = wr * __shfl_sync(0xffffffffu, wx, q);
-            if (w == 0.f || !cin) continue;
-            acc8(a, rowp + (size_t)q * C, w);
+          const bf16* rowp = base + ((size_t)(ybase + rr) * W + xbase) * C + (cin ? c : 0);
+          for (int q0 = 0; q0 < nc; q0 += 4) {
+            float w4[4];
+            uint4 u4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int q = q0 + j;
+              w4[j] = q < nc ? wr * __shfl_sync(0xffffffffu, wx, q & 31) : 0.f;
+              u4[j] = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)min(q, nc - 1) * C));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u4[j]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float2 f = __bfloat1622float2(h[i]);
+                a[2 * i] += w4[j] * f.x; a[2 * i + 1] += w4[j] * f.y;
+              }
+            }
           }
         }
       } else if (!fits && cin) {
