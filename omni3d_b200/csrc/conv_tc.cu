@@ -383,6 +383,185 @@ conv_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// "Swapped" persistent kernel for layers with <= 128 output channels.  A tcgen05.mma with M = 128, K = 16 streams its A tile
+// (128 x 32 B) from shared memory in ~128 cycles whatever N is (measured with the pipeline lab, profiles/r02_summary.md: the
+// MMA-only loop costs ~520 cycles per 64-deep K block for N = 64, 128 and 256 alike), so D[pixels][Cout] with N = Cout = 128
+// (64) runs the tensor pipe at 50 % (25 %).  Here the roles are swapped: D[Cout (M = 128)][256 pixels (N)] — A = the weight
+// tile, B = a 256-pixel input tile — full rate for Cout = 128 and twice the old rate for Cout = 64 (rows 64..127 of A are
+// never loaded nor read back).  The accumulator is transposed (TMEM lane = output channel, column = pixel): an epilogue
+// thread owns ONE channel, so the BatchNorm partial sums need no cross-thread reduction, and for every pixel the 32 lanes of
+// a warp write 32 consecutive channels (64 B).
+struct ConvSwapSmem {
+  static constexpr int kStages = 4;
+  static constexpr int kWBytes = 128 * 64 * 2;        // weights  [128 co][64 k]
+  static constexpr int kXBytes = 256 * 64 * 2;        // pixels   [256 px][64 k]
+  static constexpr int kTileBytes = kWBytes + kXBytes;
+  static constexpr int kBarOffset = kStages * kTileBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(192)
+conv_tc_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                    const ConvKParams P, const int tiles_m) {
+  using S = ConvSwapSmem;
+  constexpr int STAGES = S::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;          // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;              // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = P.KH * P.KW * P.kc_blocks;
+  const int wrows = P.Cout < 128 ? P.Cout : 128;
+
+  if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&tmap_x); ptx::prefetch_tensormap(&tmap_w); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<512>(tmem_ptr);
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      const uint32_t bytes = (uint32_t)(P.TH * P.TW * 64 * 2) + (uint32_t)(wrows * 64 * 2);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x) {
+        const int tw_i = tile % P.tiles_w, th_i = (tile / P.tiles_w) % P.tiles_h;
+        const int img = tile / (P.tiles_w * P.tiles_h);
+        const int hi0 = th_i * P.TH * P.stride - P.pad, wi0 = tw_i * P.TW * P.stride - P.pad;
+        int tap = 0, kc = 0, kh = 0, kw = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sw = smem + stage * S::kTileBytes;
+          ptx::mbar_expect_tx(&full_bar[stage], bytes);
+          ptx::tma_load_4d(sw + S::kWBytes, &tmap_x, &full_bar[stage], kc * 64, wi0 + kw, hi0 + kh, img);
+          ptx::tma_load_2d(sw, &tmap_w, &full_bar[stage], tap * P.Cin + kc * 64, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++kc == P.kc_blocks) { kc = 0; ++tap; if (++kw == P.KW) { kw = 0; ++kh; } }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 256, 0, 0);
+      constexpr uint32_t lt = ptx::swizzle_layout_type(128);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        ptx::tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tcgen05_fence_after();
+          const uint32_t sw = ptx::smem_u32(smem + stage * S::kTileBytes);
+          const uint64_t da = ptx::make_smem_desc(sw, 16, 8 * 128, lt);
+          const uint64_t db = ptx::make_smem_desc(sw + S::kWBytes, 16, 8 * 128, lt);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = q * 32 + lane;                      // TMEM lane = output channel
+    const bool cvalid = co < P.Cout;
+    const float bias = (P.bias && cvalid) ? __ldg(P.bias + co) : 0.f;
+    const int npix = P.TH * P.TW;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x) {
+      const int tw_i = tile % P.tiles_w, th_i = (tile / P.tiles_w) % P.tiles_h;
+      const int img = tile / (P.tiles_w * P.tiles_h);
+      const int ho0 = th_i * P.TH, wo0 = tw_i * P.TW;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+      float ssum = 0.f, ssq = 0.f;
+      uint32_t v[16];
+      ptx::tmem_ld_32x32b_x16(tacc, v);
+#pragma unroll 1
+      for (int ch = 0; ch < 16; ++ch) {
+        ptx::tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        if (ch + 1 < 16) ptx::tmem_ld_32x32b_x16(tacc + (uint32_t)((ch + 1) * 16), v);
+        const int p0 = ch * 16;
+        if (p0 >= npix) continue;                       // (warp-uniform) tile smaller than 256 pixels
+        int ty = p0 / P.TW, tx = p0 - ty * P.TW;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int ho = ho0 + ty, wo = wo0 + tx;
+          const bool valid = (p0 + i < npix) && ho < P.Ho && wo < P.Wo;      // warp-uniform
+          if (valid) {
+            float x = f[i];
+            ssum += x; ssq += x * x;
+            if (cvalid) {
+              const long long pix = (long long)img * P.out_img_stride + (long long)ho * P.out_h_stride +
+                                    (long long)wo * P.out_w_stride + P.out_off;
+              x += bias;
+              if (P.add_mode == 1)
+                x += __bfloat162float(P.addend[(((long long)img * P.Ho + ho) * P.Wo + wo) * P.add_pix_stride + co]);
+              else if (P.add_mode == 2)
+                x += __bfloat162float(P.addend[(((long long)img * (P.Ho >> 1) + (ho >> 1)) * (P.Wo >> 1) + (wo >> 1)) * P.add_pix_stride + co]);
+              else if (P.add_mode == 3)
+                x += __bfloat162float(reinterpret_cast<const bf16*>(P.out)[pix * P.out_pix_stride + co]);
+              if (P.relu) x = fmaxf(x, 0.f);
+              if (P.out_fp32) reinterpret_cast<float*>(P.out)[pix * P.out_pix_stride + co] = x;
+              else reinterpret_cast<bf16*>(P.out)[pix * P.out_pix_stride + co] = __float2bfloat16_rn(x);
+            }
+          }
+          if (++tx == P.TW) { tx = 0; ++ty; }
+        }
+      }
+      if (P.stats && cvalid) {
+        float* dst = P.stats + (size_t)tile * 2 * P.Cout;
+        dst[co] = ssum; dst[P.Cout + co] = ssq;
+      }
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// 256-pixel tile for the swapped kernel
+static double pick_tile256(int Ho, int Wo, int stride, int* TH, int* TW) {
+  double best = -1; int bth = 1, btw = 1;
+  for (int tw = 1; tw <= 256 && tw <= Wo; ++tw) {
+    if (tw * stride > 256) break;
+    int th = 256 / tw; if (th > Ho) th = Ho;
+    if (th * stride > 256) th = 256 / stride;
+    if (th < 1) continue;
+    long long tiles = (long long)((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
+    double eff = (double)Ho * Wo / (double)(tiles * 256);
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > btw)) { best = eff; bth = th; btw = tw; }
+  }
+  *TH = bth; *TW = btw;
+  return best;
+}
+
 // ---- host side --------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -669,6 +848,20 @@ static int32_t launch_conv_p(const CUtensorMap& mx, const CUtensorMap& mw, const
 
 using namespace c3d;
 
+// swapped (Cout-as-M) kernel: 64 or 128 output channels, 64-deep K blocks, the layers the persistent kernel takes
+static bool swap_fwd_eligible(const c3d_conv_desc* d, int Ho, int Wo, int* th, int* tw) {
+  static const bool off = getenv("C3D_CONV_NO_SWAP") != nullptr || getenv("C3D_CONV_NONPERSISTENT") != nullptr;
+  if (off || halo_fwd_eligible(d)) return false;
+  if (d->Cin % 64 != 0 || (d->Cout != 64 && d->Cout != 128) || (d->KH == 1 && d->Cin <= 64)) return false;
+  if (d->stride < 1 || d->stride > 2) return false;
+  int th128, tw128;
+  pick_tile(Ho, Wo, d->stride, &th128, &tw128);
+  const long long t128 = (long long)((Ho + th128 - 1) / th128) * ((Wo + tw128 - 1) / tw128);
+  const double eff128 = (double)Ho * Wo / (double)(t128 * 128);
+  const double eff256 = pick_tile256(Ho, Wo, d->stride, th, tw);
+  return eff256 >= 0.85 * eff128;
+}
+
 extern "C" int32_t c3d_conv2d_tiles(const c3d_conv_desc* d, int32_t* tiles_m, int32_t* TH, int32_t* TW) {
   if (!d) return set_error(C3D_EINVAL, "null desc");
   int Ho = d->out_h > 0 ? d->out_h : (d->H + 2 * d->pad - d->KH) / d->stride + 1;
@@ -680,7 +873,7 @@ extern "C" int32_t c3d_conv2d_tiles(const c3d_conv_desc* d, int32_t* tiles_m, in
     return C3D_OK;
   }
   int th, tw;
-  pick_tile(Ho, Wo, d->stride, &th, &tw);
+  if (!swap_fwd_eligible(d, Ho, Wo, &th, &tw)) pick_tile(Ho, Wo, d->stride, &th, &tw);
   if (TH) *TH = th;
   if (TW) *TW = tw;
   if (tiles_m) *tiles_m = d->N * ((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
@@ -719,7 +912,9 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
 #ifdef C3D_LAB
   { const char* e = getenv("C3D_CONV_DBG"); P.dbg = e ? atoi(e) : 0; }
 #endif
-  pick_tile(Ho, Wo, d->stride, &P.TH, &P.TW);
+  const bool swap = swap_fwd_eligible(d, Ho, Wo, &P.TH, &P.TW);
+  if (swap) BN = Cout;                                   // weight box rows
+  else pick_tile(Ho, Wo, d->stride, &P.TH, &P.TW);
   P.tiles_h = (Ho + P.TH - 1) / P.TH; P.tiles_w = (Wo + P.TW - 1) / P.TW;
   P.kc_blocks = Cin / BK; P.Cin = Cin;
   P.bias = bias; P.relu = d->relu; P.out_fp32 = d->out_fp32; P.add_mode = d->add_mode;
@@ -759,6 +954,17 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   }
   dim3 grid((unsigned)(d->N * P.tiles_h * P.tiles_w), (unsigned)(Cout / BN));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (swap) {
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(conv_tc_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSwapSmem::kTotal);
+      if (e != cudaSuccess) return set_error(C3D_ECUDA, "conv swap smem attr: %s", cudaGetErrorString(e));
+      attr = true;
+    }
+    const int tiles_m = d->N * P.tiles_h * P.tiles_w;
+    conv_tc_swap_kernel<<<(unsigned)(tiles_m < kNumSMs ? tiles_m : kNumSMs), 192, ConvSwapSmem::kTotal, st>>>(mx, mw, P, tiles_m);
+    return check_launch("conv_tc_swap_kernel");
+  }
   if (persistent) {
     const int tiles_m = d->N * P.tiles_h * P.tiles_w, n_tiles = Cout / BN;
 #define C3D_CONV_P(bn, bk, stg, cps) \
@@ -854,7 +1060,9 @@ static int32_t wgrad_impl(const c3d_conv_desc* d, const void* x, const void* dy,
   static const bool no_mt2 = getenv("C3D_WGRAD_NO_MT2") != nullptr;
   // two output-channel tiles per CTA (M = 256 through two accumulators) over 3 x 64-pixel stages: wide layers whose map tiles
   // into 64-pixel boxes
-  const bool mt2 = !no_mt2 && !n128 && Cout >= 256 && eff64 >= 0.93 * eff128;
+  // (not the small weight tensors below, <= 64K elements: those run ~4 waves of short CTAs and lose from halving the CTA count)
+  const bool mt2 = !no_mt2 && !n128 && Cout >= 256 && eff64 >= 0.93 * eff128 &&
+                   (long long)Cout * P.KH * P.KW * P.Cin > 65536;
   const bool pix64 = mt2 || (want64 && eff64 >= 0.93 * eff128);
   if (pix64) { P.RH = rh64; P.RW = rw64; }
   P.tiles_h = (Ho + P.RH - 1) / P.RH; P.tiles_w = (Wo + P.RW - 1) / P.RW;

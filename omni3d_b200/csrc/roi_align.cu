@@ -135,113 +135,6 @@ __device__ __forceinline__ bool axis_tap(float v, int n, int* lo, int* hi, float
   return true;
 }
 
-// Forward with the same separable tables: a bin reads its (rows x cols) pixel footprint once, weight wy(r) * wx(q),
-// instead of 4 taps per sample (gh x gw samples): 9 instead of 16 vector loads for 2x2 grids, 25 instead of 64 for 4x4.
-// Same value as the per-sample sum up to fp32 summation order (test tolerance vs torchvision unchanged).
-__global__ void roi_align_fwd_sep_kernel(RoiLevels L, const float* __restrict__ rois, int R, int C, int PH, int PW,
-                                         bf16* __restrict__ out) {
-  const int warps_per_block = blockDim.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long nbins = (long long)R * PH * PW;
-  for (long long bin = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); bin < nbins;
-       bin += (long long)gridDim.x * warps_per_block) {
-    const int pw = (int)(bin % PW), ph = (int)((bin / PW) % PH), r = (int)(bin / ((long long)PW * PH));
-    const float* roi = rois + (size_t)r * 6;
-    const float fb = roi[0], fl = roi[1];
-    const bool sane = fb >= 0.f && (L.num_images <= 0 || fb < (float)L.num_images) && fl >= 0.f && fl < (float)L.num_levels &&
-                      isfinite(roi[2]) && isfinite(roi[3]) && isfinite(roi[4]) && isfinite(roi[5]);
-    bf16* obin = out + (size_t)bin * C;
-    if (!sane) {
-      for (int c = lane * 8; c < C; c += 256) *reinterpret_cast<uint4*>(obin + c) = make_uint4(0, 0, 0, 0);
-      continue;
-    }
-    const int b = (int)fb, lvl = (int)fl;
-    const float sc = L.scale[lvl];
-    const int H = L.H[lvl], W = L.W[lvl];
-    const float sw = roi[2] * sc - 0.5f, sh = roi[3] * sc - 0.5f;
-    const float rw = roi[4] * sc - 0.5f - sw, rh = roi[5] * sc - 0.5f - sh;
-    const float bh = rh / PH, bw = rw / PW;
-    const int gh = (int)ceilf(rh / PH), gw = (int)ceilf(rw / PW);
-    const float inv = 1.f / fmaxf((float)(gh * gw), 1.f);
-    const bf16* base = L.feat[lvl] + (size_t)b * H * W * C;
-    int ybase = -1, xbase = -1, ymax = -1, xmax = -1;
-    float wy = 0.f, wx = 0.f;
-    bool fits = true;
-    for (int iy = 0; iy < gh; ++iy) {
-      int lo, hi; float wl, wh;
-      if (!axis_tap(sh + ph * bh + (iy + 0.5f) * bh / (float)gh, H, &lo, &hi, &wl, &wh)) continue;
-      if (ybase < 0) ybase = lo;
-      if (hi - ybase > 31) { fits = false; break; }
-      ymax = hi;
-      if (lane == lo - ybase) wy += wl;
-      if (lane == hi - ybase) wy += wh;
-    }
-    for (int ix = 0; ix < gw && fits; ++ix) {
-      int lo, hi; float wl, wh;
-      if (!axis_tap(sw + pw * bw + (ix + 0.5f) * bw / (float)gw, W, &lo, &hi, &wl, &wh)) continue;
-      if (xbase < 0) xbase = lo;
-      if (hi - xbase > 31) { fits = false; break; }
-      xmax = hi;
-      if (lane == lo - xbase) wx += wl;
-      if (lane == hi - xbase) wx += wh;
-    }
-    const bool none = fits && (ybase < 0 || xbase < 0);          // no valid sample: the bin pools zero
-    for (int c = lane * 8; c < ((C + 255) / 256) * 256; c += 256) {   // uniform trip count (shuffles below)
-      const bool cin = c < C;
-      float a[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) a[k] = 0.f;
-      if (fits && !none) {
-        const int nr = ymax - ybase + 1, nc = xmax - xbase + 1;
-        // four footprint columns per step: the loads of a step are independent (and unconditional: columns past the
-        // footprint re-read its last column with weight 0), so a warp keeps 4 x 512 B in flight per row instead of 1
-        for (int rr = 0; rr < nr; ++rr) {
-          const float wr = __shfl_sync(0xffffffffu, wy, rr);
-          if (wr == 0.f) continue;
-          const bf16* rowp = base + ((size_t)(ybase + rr) * W + xbase) * C + (cin ? c : 0);
-          for (int q0 = 0; q0 < nc; q0 += 4) {
-            float w4[4];
-            uint4 u4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int q = q0 + j;
-              w4[j] = q < nc ? wr * __shfl_sync(0xffffffffu, wx, q & 31) : 0.f;
-              u4[j] = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)min(q, nc - 1) * C));
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u4[j]);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float2 f = __bfloat1622float2(h[i]);
-                a[2 * i] += w4[j] * f.x; a[2 * i + 1] += w4[j] * f.y;
-              }
-            }
-          }
-        }
-      } else if (!fits && cin) {
-        for (int iy = 0; iy < gh; ++iy) {
-          const float y = sh + ph * bh + (iy + 0.5f) * bh / (float)gh;
-          for (int ix = 0; ix < gw; ++ix) {
-            const float x = sw + pw * bw + (ix + 0.5f) * bw / (float)gw;
-            Tap t = make_tap(y, x, H, W);
-            if (!t.valid) continue;
-            acc8(a, base + ((size_t)t.y0 * W + t.x0) * C + c, t.w1); acc8(a, base + ((size_t)t.y0 * W + t.x1) * C + c, t.w2);
-            acc8(a, base + ((size_t)t.y1 * W + t.x0) * C + c, t.w3); acc8(a, base + ((size_t)t.y1 * W + t.x1) * C + c, t.w4);
-          }
-        }
-      }
-      if (cin) {
-        uint4 u;
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(a[2 * i] * inv, a[2 * i + 1] * inv);
-        *reinterpret_cast<uint4*>(obin + c) = u;
-      }
-    }
-  }
-}
-
 __global__ void roi_align_bwd_sep_kernel(RoiLevels L, const float* __restrict__ rois, int R, int C, int PH, int PW,
                                          const bf16* __restrict__ dout) {
   const int warps_per_block = blockDim.x >> 5;
@@ -352,7 +245,6 @@ static int32_t run(bool bwd, const c3d_roi_levels* lv, const float* rois, int R,
   static const bool per_sample = getenv("C3D_ROI_PER_SAMPLE") != nullptr;
   if (bwd && !per_sample) roi_align_bwd_sep_kernel<<<(unsigned)blocks, 256, 0, st>>>(L, rois, R, C, PH, PW, (const bf16*)dout);
   else if (bwd) roi_align_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(L, rois, R, C, PH, PW, nullptr, (const bf16*)dout);
-  else if (!per_sample) roi_align_fwd_sep_kernel<<<(unsigned)blocks, 256, 0, st>>>(L, rois, R, C, PH, PW, (bf16*)out);
   else roi_align_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(L, rois, R, C, PH, PW, (bf16*)out, nullptr);
   return check_launch("roi_align");
 }

@@ -344,3 +344,44 @@ def test_fused_proposal_decode_matches_torch_formulation():
     for a, b, name in zip(out[True], out[False], ("boxes", "scores", "count")):
         assert torch.equal(a, b), name
     assert int(out[True][2].min()) > 100
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,s", [(2, 23, 37, 64, 128, 3, 1), (3, 24, 36, 128, 64, 3, 1), (2, 46, 30, 64, 128, 3, 2),
+                                                (1, 80, 80, 192, 128, 1, 1), (2, 9, 11, 64, 64, 3, 1)])
+@pytest.mark.parametrize("mode", ["stats", "relu_add", "up2", "fp32"])
+def test_conv_swapped_kernel_epilogue_modes(N, H, W, Cin, Cout, k, s, mode):
+    """Layers with 64 / 128 output channels run the swapped kernel (Cout is the MMA's M, a 256-pixel tile its N; the
+    accumulator is transposed): every epilogue mode on ragged maps (partial tiles in both directions) vs fp32 torch."""
+    from omni3d_b200 import conv as K
+    torch.backends.cudnn.allow_tf32 = False
+    p = k // 2
+    x = _r(N, H, W, Cin).bfloat16()
+    w = (_r(Cout, k, k, Cin, seed=1) / (k * k * Cin) ** 0.5).bfloat16()
+    b = _r(Cout, seed=2)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), None, s, p)      # NCHW fp32
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    tol = 1.2e-2 * ref.abs().max().item() + 1e-3
+    if mode == "stats":
+        y, stats = K.conv2d_fwd(x, w, None, stride=s, pad=p, want_stats=True)
+        tot = stats.double().sum(0)
+        s1, s2 = ref.double().sum((0, 2, 3)), (ref.double() ** 2).sum((0, 2, 3))
+        assert (tot[0] - s1).abs().max().item() <= 1e-3 * ref.abs().sum((0, 2, 3)).max().item()
+        assert (tot[1] - s2).abs().max().item() <= 1e-3 * s2.max().item()
+        assert (y.float() - ref.permute(0, 2, 3, 1)).abs().max().item() <= tol
+    elif mode == "relu_add":
+        add = _r(N, Ho, Wo, Cout, seed=4).bfloat16()
+        y = K.conv2d_fwd(x, w, b, stride=s, pad=p, relu=True, addend=add)
+        want = F.relu(ref.permute(0, 2, 3, 1) + b + add.float())
+        assert (y.float() - want).abs().max().item() <= tol + 1.2e-2 * add.float().abs().max().item()
+    elif mode == "up2":
+        if Ho % 2 or Wo % 2:
+            pytest.skip("nearest-x2 addend needs an even output")
+        add = _r(N, Ho // 2, Wo // 2, Cout, seed=4).bfloat16()
+        y = K.conv2d_fwd(x, w, b, stride=s, pad=p, addend=add, up2=True)
+        up = add.float().repeat_interleave(2, 1).repeat_interleave(2, 2)
+        want = ref.permute(0, 2, 3, 1) + b + up
+        assert (y.float() - want).abs().max().item() <= tol + 1.2e-2 * add.float().abs().max().item()
+    else:
+        y = K.conv2d_fwd(x, w, b, stride=s, pad=p, out_fp32=True)
+        assert y.dtype == torch.float32
+        assert (y - (ref.permute(0, 2, 3, 1) + b)).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-4
