@@ -83,14 +83,26 @@ C3D_HD void plane_from_quad(V3 q0, V3 q1, V3 q2, V3 q3, V3 bc, V3* pc_out, V3* n
 }
 
 C3D_HD V3 plane_edge_intersection(V3 pc, V3 n, V3 p0, V3 p1) {
-  V3 direc = p1 - p0;
-  direc = direc / fmaxf(norm(direc), kEps);
+  // The reference normalises the edge direction only to test |dot(direc, n)| >= dEps (edge not parallel to the plane).
+  // Conservative shortcut with the outcome of that test unchanged: with dd = p1 - p0, bot = dot(dd, n) and |n| = 1 the
+  // tested quantity is |bot| / |dd| up to a few ulp (~1e-6 absolute); when bot^2 >= 4e-6 |dd|^2 (|bot|/|dd| >= 2e-3, twice
+  // the threshold) and |dd| is far above kEps, the exact evaluation is certainly >= 1e-3 and the square root + three
+  // divisions are skipped; everything closer to the threshold takes the reference's arithmetic.
+  V3 dd = p1 - p0;
+  float bot = dot(dd, n);
+  float len2 = dot(dd, dd);
+  bool not_parallel;
+  if (len2 > 1e-12f && bot * bot >= 4e-6f * len2) {
+    not_parallel = true;
+  } else {
+    V3 direc = dd / fmaxf(norm(dd), kEps);
+    not_parallel = fabsf(dot(direc, n)) >= dEps;
+  }
   V3 p = (p1 + p0) / 2.0f;
-  if (fabsf(dot(direc, n)) >= dEps) {
+  if (not_parallel) {
     float top = -1.0f * dot(p0 - pc, n);
-    float bot = dot(p1 - p0, n);
     float a = top / bot;
-    p = p0 + a * (p1 - p0);
+    p = p0 + a * dd;
   }
   return p;
 }
@@ -138,24 +150,34 @@ C3D_HD int clip_tri(const Tri& t, V3 pc, V3 n, const V3* q, Tri* o0, Tri* o1) {
   int nin = (int)in0 + (int)in1 + (int)in2;
   if (cop || nin == 3) { *o0 = t; return 1; }
   if (nin == 0) return 0;
-  if (nin == 2) {
-    // one vertex out: (vout, vin1, vin2) = (v2,v0,v1) | (v1,v0,v2) | (v0,v1,v2)
+  // nin == 2, one vertex out:  (vout, vin1, vin2) = (v2,v0,v1) | (v1,v0,v2) | (v0,v1,v2); p1 = [vin1,vout], p2 = [vin2,vout]
+  //                            -> (vin1, p1, vin2), (p1, p2, vin2)
+  // nin == 1, two vertices out: (vin, vout1, vout2) = (v0,v1,v2) | (v2,v0,v1) | (v1,v0,v2); p1 = [vin,vout1], p2 = [vin,vout2]
+  //                            -> (vin, p1, p2)
+  // Both cases intersect two edges: the end points are selected first and the two intersections are evaluated in code
+  // common to both (a warp's lanes in different cases stay converged through the expensive part); same operations on
+  // the same operands as the two-branch form, hence the same bits.
+  const bool two_in = (nin == 2);
+  V3 a0, a1, b0, b1;
+  if (two_in) {
     V3 vout = !in2 ? t.c : (!in1 ? t.b : t.a);
-    V3 vin1 = !in0 ? t.b : t.a;
-    V3 vin2 = !in2 ? t.b : t.c;
-    V3 p1 = plane_edge_intersection(pc, n, vin1, vout);
-    V3 p2 = plane_edge_intersection(pc, n, vin2, vout);
-    o0->a = vin1; o0->b = p1; o0->c = vin2;
-    o1->a = p1;   o1->b = p2; o1->c = vin2;
+    a0 = !in0 ? t.b : t.a;   // vin1
+    b0 = !in2 ? t.b : t.c;   // vin2
+    a1 = vout; b1 = vout;
+  } else {
+    V3 vin = in0 ? t.a : (in2 ? t.c : t.b);
+    a0 = vin; b0 = vin;
+    a1 = in0 ? t.b : t.a;    // vout1
+    b1 = in2 ? t.b : t.c;    // vout2
+  }
+  V3 p1 = plane_edge_intersection(pc, n, a0, a1);
+  V3 p2 = plane_edge_intersection(pc, n, b0, b1);
+  if (two_in) {
+    o0->a = a0; o0->b = p1; o0->c = b0;
+    o1->a = p1; o1->b = p2; o1->c = b0;
     return 2;
   }
-  // two vertices out: (vin, vout1, vout2) = (v0,v1,v2) | (v2,v0,v1) | (v1,v0,v2)
-  V3 vin = in0 ? t.a : (in2 ? t.c : t.b);
-  V3 vo1 = in0 ? t.b : t.a;
-  V3 vo2 = in2 ? t.b : t.c;
-  V3 p1 = plane_edge_intersection(pc, n, vin, vo1);
-  V3 p2 = plane_edge_intersection(pc, n, vin, vo2);
-  o0->a = vin; o0->b = p1; o0->c = p2;
+  o0->a = a0; o0->b = p1; o0->c = p2;
   return 1;
 }
 

@@ -6,13 +6,17 @@
 // Design (not the one-thread-per-pair layout of the stock CUDA op):
 //   prep kernel   one thread per box: 256-byte record (corners, 6 inward face planes, centre,
 //                 volume) + a padded bounding sphere + the dt-row validity flags.
-//   pair kernel   persistent warps pull chunks of 32 consecutive pairs from an atomic counter.
-//                 Each lane sphere-tests one pair (disjoint spheres => exactly vol=iou=0, 0 faces,
-//                 written coalesced); surviving pairs are then processed ONE PAIR PER WARP:
-//                 lanes 0-15 clip box1's triangles by box2's planes while lanes 16-31 clip
-//                 box2's triangles by box1's planes, triangle lists live in shared memory
-//                 (SoA, conflict-free), compaction by ballot/popc keeps the serial order, so
-//                 face counts, vol and iou are bit-identical to the serial CPU algorithm.
+//   filter kernel one thread per 4 consecutive pairs: bounding-sphere test (+ dt-row validity); disjoint
+//                 spheres => exactly vol=iou=0, 0 faces, written with 16-byte stores at HBM rate; the
+//                 surviving pair indices are appended to a queue (one atomic per warp).  Paired mode fuses
+//                 prep + filter: the raw corners are staged through shared memory with coalesced loads
+//                 and a rejected pair costs 192 B in + 4..12 B out, nothing else.
+//   clip kernel   persistent warps walk the survivor queue with a static stride, ONE PAIR PER WARP (so
+//                 1 000 live pairs already occupy 1 000 warps): lanes 0-15 clip box1's triangles by
+//                 box2's planes while lanes 16-31 clip box2's triangles by box1's planes, triangle
+//                 lists live in shared memory (SoA, conflict-free), compaction by ballot/popc keeps
+//                 the serial order, so face counts, vol and iou are bit-identical to the serial CPU
+//                 algorithm.
 //   overflow      pairs whose intermediate list exceeds the shared-memory capacity (P≈1e-5 on
 //                 random dense boxes) are queued and redone by a small kernel with
 //                 global-memory lists.
@@ -29,23 +33,21 @@ constexpr int kFallbackWarps = 296;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr long long kMaxOverflowQueue = 1ll << 22;
 
-struct Ctrl {            // lives at the head of the workspace
-  unsigned int next_chunk;
+struct Ctrl {            // lives at the head of the workspace (zeroed by a memset node at the start of a call)
+  unsigned int n_live;     // survivors of the current batch (filter kernel appends, clip kernel reads)
   unsigned int n_overflow;
   int n_bad[2];
   unsigned int next_overflow;
   unsigned int pad[3];
 };
+constexpr long long kBatchPairs = 1ll << 24;   // pairs per filter/clip round (bounds the survivor queue: 64 MB of u32)
 
 // ------------------------------------------------------------------------------------------
 __global__ void iou3d_prep_kernel(const float* __restrict__ b1, int n1, const float* __restrict__ b2,
                                   int n2, float* __restrict__ rec, float4* __restrict__ sph,
                                   uint8_t* __restrict__ rowflags, float eps_c, float eps_nz,
-                                  int do_check, Ctrl* ctrl) {
+                                  int do_check) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) {
-    ctrl->next_chunk = 0; ctrl->n_overflow = 0; ctrl->next_overflow = 0;
-  }
   if (i >= n1 + n2) return;
   const float* src = i < n1 ? b1 + 24 * (size_t)i : b2 + 24 * (size_t)(i - n1);
   float r[kRecFloats];
@@ -62,41 +64,76 @@ __global__ void iou3d_prep_kernel(const float* __restrict__ b1, int n1, const fl
 }
 
 // Paired mode (pair k = boxes1[k] x boxes2[k]): every box belongs to exactly one pair, so building the 256-byte record of a
-// box whose pair is rejected by the bounding-sphere test is wasted work and wasted HBM traffic (272 B written per box vs
-// 96 B read) — in the sparse regime that is ~all of them.  One thread per PAIR: both spheres from the raw corners, the test,
-// and the two records only for surviving pairs; rejected pairs get a NaN radius so that the pair kernel's own sphere test
-// (d2 <= (r1+r2)^2) fails without reading anything else.  Traffic per rejected pair: 192 B in + 32 B + 32 B + 8..12 B out.
-__global__ void iou3d_prep_paired_kernel(const float* __restrict__ b1, const float* __restrict__ b2, int n,
-                                         float* __restrict__ rec, float4* __restrict__ sph, Ctrl* ctrl) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k == 0) { ctrl->next_chunk = 0; ctrl->n_overflow = 0; ctrl->next_overflow = 0; }
-  if (k >= n) return;
-  const float* s1 = b1 + 24 * (size_t)k;
-  const float* s2 = b2 + 24 * (size_t)k;
-  float c1[4], c2[4];
-  box_sphere(s1, c1);
-  box_sphere(s2, c2);
-  const float dx = c1[0] - c2[0], dy = c1[1] - c2[1], dz = c1[2] - c2[2];
-  const float rs = c1[3] + c2[3];
-  const bool live = (dx * dx + dy * dy + dz * dz) <= rs * rs;
-  if (!live) {
-    const float qnan = __int_as_float(0x7fc00000);
-    sph[k] = make_float4(0.f, 0.f, 0.f, qnan);
-    sph[n + k] = make_float4(0.f, 0.f, 0.f, qnan);
-    return;
+// box whose pair is rejected by the bounding-sphere test is wasted work and wasted HBM traffic — in the sparse regime that
+// is ~all of them.  Fused prep + filter, one thread per PAIR: the block's 128 + 128 boxes are staged through shared memory
+// with coalesced 16-byte loads (rows padded to 25 words: conflict-free per-thread reads), both spheres come from the raw
+// corners, rejected pairs get their zeros here; only surviving pairs get records + a queue entry.
+// Traffic per rejected pair: 192 B in + 4..12 B out.
+constexpr int kPairedBlock = 128;
+constexpr int kRowPad = 25;
+__global__ void __launch_bounds__(kPairedBlock)
+iou3d_prep_paired_kernel(const float* __restrict__ b1, const float* __restrict__ b2, long long k0, int nbatch, int n,
+                         float* __restrict__ rec, float4* __restrict__ sph, float* __restrict__ vol,
+                         float* __restrict__ iou, int* __restrict__ nfaces, unsigned* __restrict__ queue, Ctrl* ctrl) {
+  __shared__ float sbox[2][kPairedBlock * kRowPad];
+  const int tid = threadIdx.x;
+  const long long kb = k0 + (long long)blockIdx.x * kPairedBlock;        // first pair of the block
+  const int nblk = (int)min((long long)kPairedBlock, k0 + nbatch - kb);
+  const float* g[2] = {b1 + 24 * kb, b2 + 24 * kb};
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if ((reinterpret_cast<uintptr_t>(g[s]) & 15) == 0) {
+      const float4* g4 = reinterpret_cast<const float4*>(g[s]);
+      for (int q = tid; q < nblk * 6; q += kPairedBlock) {
+        const float4 v = __ldg(g4 + q);
+        const int row = q / 6, col = (q - row * 6) * 4;
+        float* d = &sbox[s][row * kRowPad + col];
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    } else {
+      for (int q = tid; q < nblk * 24; q += kPairedBlock) {
+        const int row = q / 24;
+        sbox[s][row * kRowPad + (q - row * 24)] = __ldg(g[s] + q);
+      }
+    }
   }
-  float r[kRecFloats];
-  float s4[4];
-  build_box_record(s1, r, s4);
-  float4* dst = reinterpret_cast<float4*>(rec + (size_t)k * kRecFloats);
+  __syncthreads();
+  bool live = false;
+  const long long k = kb + tid;
+  if (tid < nblk) {
+    const float* s1 = &sbox[0][tid * kRowPad];
+    const float* s2 = &sbox[1][tid * kRowPad];
+    float c1[4], c2[4];
+    box_sphere(s1, c1);
+    box_sphere(s2, c2);
+    const float dx = c1[0] - c2[0], dy = c1[1] - c2[1], dz = c1[2] - c2[2];
+    const float rs = c1[3] + c2[3];
+    live = (dx * dx + dy * dy + dz * dz) <= rs * rs;
+    if (!live) {
+      iou[k] = 0.f;
+      if (vol) vol[k] = 0.f;
+      if (nfaces) nfaces[k] = 0;
+    } else {
+      float r[kRecFloats];
+      float s4[4];
+      build_box_record(s1, r, s4);
+      float4* dst = reinterpret_cast<float4*>(rec + (size_t)k * kRecFloats);
 #pragma unroll
-  for (int q = 0; q < kRecFloats / 4; ++q) dst[q] = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-  sph[k] = make_float4(s4[0], s4[1], s4[2], s4[3]);
-  build_box_record(s2, r, s4);
-  dst = reinterpret_cast<float4*>(rec + (size_t)(n + k) * kRecFloats);
+      for (int q = 0; q < kRecFloats / 4; ++q) dst[q] = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+      build_box_record(s2, r, s4);
+      dst = reinterpret_cast<float4*>(rec + (size_t)(n + k) * kRecFloats);
 #pragma unroll
-  for (int q = 0; q < kRecFloats / 4; ++q) dst[q] = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-  sph[n + k] = make_float4(s4[0], s4[1], s4[2], s4[3]);
+      for (int q = 0; q < kRecFloats / 4; ++q) dst[q] = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    }
+  }
+  const unsigned m = __ballot_sync(kFull, live);
+  if (m) {
+    const int lane = tid & 31;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(&ctrl->n_live, (unsigned)__popc(m));
+    base = __shfl_sync(kFull, base, 0);
+    if (live) queue[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)(k - k0);
+  }
 }
 
 __global__ void iou3d_count_bad_kernel(const uint8_t* __restrict__ rowflags, int n1, Ctrl* ctrl,
@@ -316,51 +353,99 @@ __device__ __forceinline__ void pair_to_ij(const PairArgs& A, long long k, int* 
   else { *i = (int)(k / A.n2); *j = A.n1 + (int)(k % A.n2); }
 }
 
+// Sphere test (+ dt-row validity) of the pairs [k0, k0 + nbatch): 4 consecutive pairs per thread, zeros written with one
+// 16-byte store per output array (the arrays are 16-byte aligned and k0 is a multiple of 4 whenever `vec` is set),
+// survivors appended to the queue as offsets from k0 (one atomic per warp).
+__global__ void __launch_bounds__(256)
+iou3d_filter_kernel(PairArgs A, long long k0, int nbatch, unsigned* __restrict__ queue, int vec) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long kq = k0 + 4 * t;
+  const int cnt = (int)max(0ll, min(4ll, k0 + nbatch - kq));
+  unsigned livemask = 0;
+  if (cnt > 0) {
+    int i = 0, j = 0;
+    pair_to_ij(A, kq, &i, &j);
+    float4 s1 = __ldg(A.sph + i);
+    bool rowok = A.rowflags ? (A.rowflags[i] == 3) : true;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (u < cnt) {
+        if (u > 0) {
+          if (A.ngroups > 0) {
+            const int pi = i;
+            pair_to_ij(A, kq + u, &i, &j);
+            if (i != pi) { s1 = __ldg(A.sph + i); rowok = A.rowflags ? (A.rowflags[i] == 3) : true; }
+          } else if (A.n2 == 0) {                           // paired records: (k, n1 + k)
+            ++i; ++j; s1 = __ldg(A.sph + i); rowok = A.rowflags ? (A.rowflags[i] == 3) : true;
+          } else {
+            ++j;                                            // cross mode, row-major (n2 >= 1)
+            if (j == A.n1 + A.n2) { j = A.n1; ++i; s1 = __ldg(A.sph + i); rowok = A.rowflags ? (A.rowflags[i] == 3) : true; }
+          }
+        }
+        const float4 s2 = __ldg(A.sph + j);
+        const float dx = s1.x - s2.x, dy = s1.y - s2.y, dz = s1.z - s2.z;
+        const float rs = s1.w + s2.w;
+        if (((dx * dx + dy * dy + dz * dz) <= rs * rs) && rowok) livemask |= 1u << u;
+      }
+    }
+    if (vec && cnt == 4) {
+      *reinterpret_cast<float4*>(A.iou + kq) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (A.vol) *reinterpret_cast<float4*>(A.vol + kq) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (A.nfaces) *reinterpret_cast<int4*>(A.nfaces + kq) = make_int4(0, 0, 0, 0);
+    } else {
+      for (int u = 0; u < cnt; ++u) {
+        A.iou[kq + u] = 0.f;
+        if (A.vol) A.vol[kq + u] = 0.f;
+        if (A.nfaces) A.nfaces[kq + u] = 0;
+      }
+    }
+  }
+  // queue append: exclusive warp scan of the per-thread survivor counts
+  const int lane = threadIdx.x & 31;
+  const int mine = __popc(livemask);
+  int incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(kFull, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const int total = __shfl_sync(kFull, incl, 31);
+  if (total == 0) return;
+  unsigned base = 0;
+  if (lane == 31) base = atomicAdd(&A.ctrl->n_live, (unsigned)total);
+  base = __shfl_sync(kFull, base, 31);
+  unsigned pos = base + (unsigned)(incl - mine);
+  const unsigned rel = (unsigned)(kq - k0);
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (livemask & (1u << u)) queue[pos++] = rel + u;
+}
+
+// Survivor queue -> one pair per warp, static stride over the queue (no atomics; the per-pair work varies ~3x, the
+// queue order is effectively random, so the tail is a few per cent once every warp holds tens of pairs).
 __global__ void __launch_bounds__(32 * kWarpsPerBlock)
-iou3d_pair_kernel(PairArgs A) {
+iou3d_clip_kernel(PairArgs A, long long k0, const unsigned* __restrict__ queue) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* rec = smem + warp * (128 + 4 * 9 * kCap);
   float* buf = rec + 128;
-  const long long nchunks = (A.npairs + 31) / 32;
-  while (true) {
-    unsigned c = 0;
-    if (lane == 0) c = atomicAdd(&A.ctrl->next_chunk, 1u);
-    c = __shfl_sync(kFull, c, 0);
-    if ((long long)c >= nchunks) break;
-    long long k = (long long)c * 32 + lane;
-    bool valid = k < A.npairs;
-    int i = 0, j = 0;
-    bool live = false;
-    if (valid) {
-      pair_to_ij(A, k, &i, &j);
-      float4 s1 = __ldg(A.sph + i), s2 = __ldg(A.sph + j);
-      float dx = s1.x - s2.x, dy = s1.y - s2.y, dz = s1.z - s2.z;
-      float rs = s1.w + s2.w;
-      live = (dx * dx + dy * dy + dz * dz) <= rs * rs;
-      if (A.rowflags) live = live && (A.rowflags[i] == 3);
-    }
-    float my_vol = 0.f, my_iou = 0.f; int my_nf = 0;
-    unsigned todo = __ballot_sync(kFull, live);
-    while (todo) {
-      int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      int pi = __shfl_sync(kFull, i, src), pj = __shfl_sync(kFull, j, src);
-      float v, u;
-      int nf = process_pair<kCap>(A.rec + (size_t)pi * kRecFloats, A.rec + (size_t)pj * kRecFloats,
-                                  rec, buf, lane, &v, &u);
-      if (nf < 0 && lane == 0) {
+  const unsigned n_live = A.ctrl->n_live;
+  const unsigned W = gridDim.x * kWarpsPerBlock;
+  for (unsigned q = warp * gridDim.x + blockIdx.x; q < n_live; q += W) {
+    const long long k = k0 + (long long)__ldg(queue + q);
+    int i, j;
+    pair_to_ij(A, k, &i, &j);
+    float v, u;
+    int nf = process_pair<kCap>(A.rec + (size_t)i * kRecFloats, A.rec + (size_t)j * kRecFloats, rec, buf, lane, &v, &u);
+    if (lane == 0) {
+      if (nf < 0) {
         unsigned slot = atomicAdd(&A.ctrl->n_overflow, 1u);
-        if (slot < A.overflow_cap) A.overflow[slot] = (unsigned long long)((long long)c * 32 + src);
+        if (slot < A.overflow_cap) A.overflow[slot] = (unsigned long long)k;
         else { v = __int_as_float(0x7fc00000); u = v; }   // queue full: flagged NaN / nfaces -1
       }
-      v = __shfl_sync(kFull, v, 0); u = __shfl_sync(kFull, u, 0);
-      if (lane == src) { my_vol = v; my_iou = u; my_nf = nf; }
-    }
-    if (valid) {
-      A.iou[k] = my_iou;
-      if (A.vol) A.vol[k] = my_vol;
-      if (A.nfaces) A.nfaces[k] = my_nf;
+      A.iou[k] = u;
+      if (A.vol) A.vol[k] = v;
+      if (A.nfaces) A.nfaces[k] = nf;
     }
   }
 }
@@ -395,7 +480,7 @@ iou3d_overflow_kernel(PairArgs A, float* slabs) {
 
 // ---- workspace layout -------------------------------------------------------------------------
 struct WsLayout {
-  size_t ctrl, rec, sph, flags, overflow, slabs, total;
+  size_t ctrl, rec, sph, flags, overflow, slabs, queue, total;
 };
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static WsLayout ws_layout_pairs(int64_t n1, int64_t n2, int64_t npairs);
@@ -412,6 +497,7 @@ static WsLayout ws_layout_pairs(int64_t n1, int64_t m2, int64_t npairs) {
   L.flags = o; o = align_up(o + (size_t)n1, 256);
   L.overflow = o; o = align_up(o + (size_t)(npairs < kMaxOverflowQueue ? npairs : kMaxOverflowQueue) * 8, 256);
   L.slabs = o; o = align_up(o + (size_t)kFallbackWarps * 4 * 9 * kCapBig * 4, 256);
+  L.queue = o; o = align_up(o + (size_t)(npairs < kBatchPairs ? npairs : kBatchPairs) * 4, 256);
   L.total = o;
   return L;
 }
@@ -442,12 +528,12 @@ static int32_t run_iou(const float* b1, int64_t n1, const float* b2, int64_t n2,
   float4* sph = reinterpret_cast<float4*>(w + L.sph);
   uint8_t* flags = reinterpret_cast<uint8_t*>(w + L.flags);
   int nb = (int)(n1 + m2);
-  static const bool paired_lazy = getenv("C3D_IOU_PAIRED_EAGER_PREP") == nullptr;
-  if (paired && !do_check && !seg && paired_lazy)
-    iou3d_prep_paired_kernel<<<((int)n1 + 127) / 128, 128, 0, st>>>(b1, b2, (int)n1, rec, sph, ctrl);
-  else
+  unsigned* queue = reinterpret_cast<unsigned*>(w + L.queue);
+  cudaMemsetAsync(ctrl, 0, sizeof(Ctrl), st);
+  const bool fused_paired = paired && !do_check && !seg;
+  if (!fused_paired)
     iou3d_prep_kernel<<<(nb + 127) / 128, 128, 0, st>>>(b1, (int)n1, b2, (int)m2, rec, sph, flags, eps_c,
-                                                        eps_nz, do_check ? 1 : 0, ctrl);
+                                                        eps_nz, do_check ? 1 : 0);
   if (do_check) iou3d_count_bad_kernel<<<1, 256, 0, st>>>(flags, (int)n1, ctrl, n_bad);
   if (npairs > 0) {
     PairArgs A;
@@ -464,16 +550,26 @@ static int32_t run_iou(const float* b1, int64_t n1, const float* b2, int64_t n2,
     size_t smem = (size_t)kWarpsPerBlock * (128 + 4 * 9 * kCap) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(iou3d_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(iou3d_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       attr_set = true;
     }
-    long long nchunks = (npairs + 31) / 32;
     int blocks_per_sm = (int)((227 * 1024) / (smem + 1024));
     if (blocks_per_sm > 8) blocks_per_sm = 8;
-    long long grid = (nchunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    long long maxgrid = (long long)kNumSMs * blocks_per_sm;
-    if (grid > maxgrid) grid = maxgrid;
-    iou3d_pair_kernel<<<(unsigned)grid, 32 * kWarpsPerBlock, smem, st>>>(A);
+    const long long maxgrid = (long long)kNumSMs * blocks_per_sm;
+    const int vec = ((reinterpret_cast<uintptr_t>(iou) | reinterpret_cast<uintptr_t>(vol) |
+                      reinterpret_cast<uintptr_t>(nfaces)) & 15) == 0;
+    for (long long k0 = 0; k0 < npairs; k0 += kBatchPairs) {
+      const int nbatch = (int)(npairs - k0 < kBatchPairs ? npairs - k0 : kBatchPairs);
+      if (k0 > 0) cudaMemsetAsync(&ctrl->n_live, 0, sizeof(unsigned), st);
+      if (fused_paired)
+        iou3d_prep_paired_kernel<<<(nbatch + kPairedBlock - 1) / kPairedBlock, kPairedBlock, 0, st>>>(
+            b1, b2, k0, nbatch, (int)n1, rec, sph, vol, iou, nfaces, queue, ctrl);
+      else
+        iou3d_filter_kernel<<<(unsigned)(((nbatch + 3) / 4 + 255) / 256), 256, 0, st>>>(A, k0, nbatch, queue, vec);
+      long long grid = ((long long)nbatch + kWarpsPerBlock - 1) / kWarpsPerBlock;   // one pair per warp at most
+      if (grid > maxgrid) grid = maxgrid;
+      iou3d_clip_kernel<<<(unsigned)grid, 32 * kWarpsPerBlock, smem, st>>>(A, k0, queue);
+    }
     iou3d_overflow_kernel<<<kFallbackWarps, 32, 0, st>>>(A, reinterpret_cast<float*>(w + L.slabs));
   }
   return check_launch("iou3d launch");

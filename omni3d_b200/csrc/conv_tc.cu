@@ -398,12 +398,15 @@ struct ConvSwapSmem {
   static constexpr int kXBytes = 256 * 64 * 2;        // pixels   [256 px][64 k]
   static constexpr int kTileBytes = kWBytes + kXBytes;
   static constexpr int kBarOffset = kStages * kTileBytes;
-  static constexpr int kStgOffset = kBarOffset + 256;        // epilogue transposes: 4 warps x [16 px][kStgPitch] fp32
+  static constexpr int kStgOffset = kBarOffset + 256;        // epilogue transposes: 8 warps x [16 px][kStgPitch] fp32
   static constexpr int kStgPitch = 36;                        // 32 channels + 4: 16-byte aligned rows, <= 2-way bank conflicts
-  static constexpr int kTotal = kStgOffset + 4 * 16 * kStgPitch * 4 + 1024;
+  static constexpr int kEpiWarps = 8;                         // two per TMEM lane quarter: pixel columns 0..127 / 128..255
+  static constexpr int kStatOffset = kStgOffset + kEpiWarps * 16 * kStgPitch * 4;   // [2][128] fp32: statistics of the upper half
+  static constexpr int kTotal = kStatOffset + 2 * 128 * 4 + 1024;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
 };
 
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(ConvSwapSmem::kThreads)
 conv_tc_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                     const ConvKParams P, const int tiles_m) {
   using S = ConvSwapSmem;
@@ -423,7 +426,7 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&tmap_x); ptx::prefetch_tensormap(&tmap_w); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], ConvSwapSmem::kEpiWarps); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<512>(tmem_ptr);
@@ -479,7 +482,11 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       }
     }
   } else {
+    // 8 epilogue warps: warps (2 + q) and (6 + q') ... a warp may only read the TMEM lane quarter (warp & 3); the two warps of
+    // a quarter split the 256 pixel columns in halves, so every scheduler holds two epilogue warps to overlap the
+    // TMEM-load / shared-memory-transpose / store latencies of one with the other.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;                  // 0: pixels 0..127, 1: pixels 128..255
     const int co = q * 32 + lane;                      // TMEM lane = output channel
     const bool cvalid = co < P.Cout;
     const float bias = (P.bias && cvalid) ? __ldg(P.bias + co) : 0.f;
@@ -487,93 +494,109 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // store side of the transposes below: this thread writes pixel (lane >> 1) of a 16-pixel chunk, channels cs..cs+15
     const int sp = lane >> 1, cs = q * 32 + (lane & 1) * 16;
     const bool svalid = cs < P.Cout;
-    float* tr = reinterpret_cast<float*>(smem + S::kStgOffset) + q * (16 * S::kStgPitch);
+    float* tr = reinterpret_cast<float*>(smem + S::kStgOffset) + (warp - 2) * (16 * S::kStgPitch);
+    float* sstat = reinterpret_cast<float*>(smem + S::kStatOffset);
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x) {
       const int tw_i = tile % P.tiles_w, th_i = (tile / P.tiles_w) % P.tiles_h;
       const int img = tile / (P.tiles_w * P.tiles_h);
       const int ho0 = th_i * P.TH, wo0 = tw_i * P.TW;
+      const bool full = (npix == 256) && (ho0 + P.TH <= P.Ho) && (wo0 + P.TW <= P.Wo);   // no pixel of the tile is masked
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tcgen05_fence_after();
-      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)half * 128u;
       float ssum = 0.f, ssq = 0.f;
+      // (ty, tx) of the pixel this thread stores in the current chunk, advanced by 16 pixels per chunk
+      int sty = (half * 128 + sp) / P.TW, stx = (half * 128 + sp) - sty * P.TW;
       uint32_t v[16];
       ptx::tmem_ld_32x32b_x16(tacc, v);
 #pragma unroll 1
-      for (int ch = 0; ch < 16; ++ch) {
+      for (int ch = 0; ch < 8; ++ch) {
         ptx::tmem_ld_wait();
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-        if (ch + 1 < 16) ptx::tmem_ld_32x32b_x16(tacc + (uint32_t)((ch + 1) * 16), v);
-        const int p0 = ch * 16;
-        if (p0 >= npix) continue;                       // (warp-uniform) tile smaller than 256 pixels
-        if (P.stats) {                                  // raw accumulators of the valid pixels; this thread owns channel co
-          int ty = p0 / P.TW, tx = p0 - ty * P.TW;
+        if (ch + 1 < 8) ptx::tmem_ld_32x32b_x16(tacc + (uint32_t)((ch + 1) * 16), v);
+        const int p0 = half * 128 + ch * 16;
+        if (p0 < npix) {                                // (warp-uniform) tile smaller than 256 pixels
+          if (P.stats) {                                // raw accumulators of the valid pixels; this thread owns channel co
+            if (full) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if ((p0 + i < npix) && (ho0 + ty < P.Ho) && (wo0 + tx < P.Wo)) { ssum += f[i]; ssq += f[i] * f[i]; }
-            if (++tx == P.TW) { tx = 0; ++ty; }
-          }
-        }
-        // transpose 32 channels x 16 pixels through shared memory so that a thread stores 16 consecutive channels of one
-        // pixel (2 x 16 B) instead of one 2-byte element per pixel (measured: the scalar version made the layer 8x slower —
-        // one warp per scheduler cannot hide ~40 dependent address instructions per pixel)
+              for (int i = 0; i < 16; ++i) { ssum += f[i]; ssq = fmaf(f[i], f[i], ssq); }
+            } else {
+              int ty = p0 / P.TW, tx = p0 - ty * P.TW;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) tr[i * S::kStgPitch + lane] = f[i] + bias;
-        __syncwarp();
-        const int p = p0 + sp;
-        const int ty = p / P.TW, tx = p - ty * P.TW;
-        const int ho = ho0 + ty, wo = wo0 + tx;
-        if (svalid && p < npix && ho < P.Ho && wo < P.Wo) {
-          float g[16];
-          const float4* src = reinterpret_cast<const float4*>(tr + sp * S::kStgPitch + (lane & 1) * 16);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { const float4 t4 = src[k]; g[4 * k] = t4.x; g[4 * k + 1] = t4.y; g[4 * k + 2] = t4.z; g[4 * k + 3] = t4.w; }
-          const long long pix = (long long)img * P.out_img_stride + (long long)ho * P.out_h_stride +
-                                (long long)wo * P.out_w_stride + P.out_off;
-          if (P.add_mode) {
-            const bf16* abase;
-            if (P.add_mode == 3) abase = reinterpret_cast<const bf16*>(P.out) + pix * P.out_pix_stride;
-            else if (P.add_mode == 1) abase = P.addend + (((long long)img * P.Ho + ho) * P.Wo + wo) * P.add_pix_stride;
-            else abase = P.addend + (((long long)img * (P.Ho >> 1) + (ho >> 1)) * (P.Wo >> 1) + (wo >> 1)) * P.add_pix_stride;
-            const uint4* ap = reinterpret_cast<const uint4*>(abase + cs);
-            const uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
-            const bf16* h0 = reinterpret_cast<const bf16*>(&a0);
-            const bf16* h1 = reinterpret_cast<const bf16*>(&a1);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { g[k] += __bfloat162float(h0[k]); g[8 + k] += __bfloat162float(h1[k]); }
-          }
-          if (P.relu) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) g[k] = fmaxf(g[k], 0.f);
-          }
-          if (P.out_fp32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix * P.out_pix_stride + cs);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) op[k] = make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]);
-          } else {
-            uint32_t pk[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(g[2 * k], g[2 * k + 1]);
-              pk[k] = *reinterpret_cast<uint32_t*>(&h);
+              for (int i = 0; i < 16; ++i) {
+                if ((p0 + i < npix) && (ho0 + ty < P.Ho) && (wo0 + tx < P.Wo)) { ssum += f[i]; ssq = fmaf(f[i], f[i], ssq); }
+                if (++tx == P.TW) { tx = 0; ++ty; }
+              }
             }
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + pix * P.out_pix_stride + cs);
-            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
+          // transpose 32 channels x 16 pixels through shared memory so that a thread stores 16 consecutive channels of one
+          // pixel (2 x 16 B) instead of one 2-byte element per pixel
+#pragma unroll
+          for (int i = 0; i < 16; ++i) tr[i * S::kStgPitch + lane] = f[i] + bias;
+          __syncwarp();
+          const int ho = ho0 + sty, wo = wo0 + stx;
+          if (svalid && (p0 + sp) < npix && ho < P.Ho && wo < P.Wo) {
+            float g[16];
+            const float4* src = reinterpret_cast<const float4*>(tr + sp * S::kStgPitch + (lane & 1) * 16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float4 t4 = src[k]; g[4 * k] = t4.x; g[4 * k + 1] = t4.y; g[4 * k + 2] = t4.z; g[4 * k + 3] = t4.w; }
+            const long long pix = (long long)img * P.out_img_stride + (long long)ho * P.out_h_stride +
+                                  (long long)wo * P.out_w_stride + P.out_off;
+            if (P.add_mode) {
+              const bf16* abase;
+              if (P.add_mode == 3) abase = reinterpret_cast<const bf16*>(P.out) + pix * P.out_pix_stride;
+              else if (P.add_mode == 1) abase = P.addend + (((long long)img * P.Ho + ho) * P.Wo + wo) * P.add_pix_stride;
+              else abase = P.addend + (((long long)img * (P.Ho >> 1) + (ho >> 1)) * (P.Wo >> 1) + (wo >> 1)) * P.add_pix_stride;
+              const uint4* ap = reinterpret_cast<const uint4*>(abase + cs);
+              const uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+              const bf16* h0 = reinterpret_cast<const bf16*>(&a0);
+              const bf16* h1 = reinterpret_cast<const bf16*>(&a1);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) { g[k] += __bfloat162float(h0[k]); g[8 + k] += __bfloat162float(h1[k]); }
+            }
+            if (P.relu) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) g[k] = fmaxf(g[k], 0.f);
+            }
+            if (P.out_fp32) {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix * P.out_pix_stride + cs);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) op[k] = make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]);
+            } else {
+              uint32_t pk[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(g[2 * k], g[2 * k + 1]);
+                pk[k] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + pix * P.out_pix_stride + cs);
+              op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+          __syncwarp();                                 // the transpose tile is rewritten by the next chunk
         }
-        __syncwarp();                                   // the transpose tile is rewritten by the next chunk
+        stx += 16;
+        while (stx >= P.TW) { stx -= P.TW; ++sty; }
       }
-      if (P.stats && cvalid) {
-        float* dst = P.stats + (size_t)tile * 2 * P.Cout;
-        dst[co] = ssum; dst[P.Cout + co] = ssq;
-      }
+      // the accumulator has been read: hand it back to the MMA warp before the statistics hand-shake
       ptx::tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (P.stats) {
+        // the two halves of a channel: upper half -> shared memory -> lower half adds (fixed order) and writes the tile's row
+        if (half == 1) { sstat[co] = ssum; sstat[128 + co] = ssq; }
+        ptx::named_bar_sync(1 + q, 64);
+        if (half == 0 && cvalid) {
+          float* dst = P.stats + (size_t)tile * 2 * P.Cout;
+          dst[co] = ssum + sstat[co]; dst[P.Cout + co] = ssq + sstat[128 + co];
+        }
+        ptx::named_bar_sync(1 + q, 64);                 // sstat is rewritten by the next tile
+      }
     }
   }
   ptx::tcgen05_fence_before();
@@ -1000,7 +1023,7 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
       attr = true;
     }
     const int tiles_m = d->N * P.tiles_h * P.tiles_w;
-    conv_tc_swap_kernel<<<(unsigned)(tiles_m < kNumSMs ? tiles_m : kNumSMs), 192, ConvSwapSmem::kTotal, st>>>(mx, mw, P, tiles_m);
+    conv_tc_swap_kernel<<<(unsigned)(tiles_m < kNumSMs ? tiles_m : kNumSMs), ConvSwapSmem::kThreads, ConvSwapSmem::kTotal, st>>>(mx, mw, P, tiles_m);
     return check_launch("conv_tc_swap_kernel");
   }
   if (persistent) {
