@@ -183,7 +183,10 @@ int32_t c3d_bn_bwd_blocks(int64_t P, int32_t C);
  * optional dres = masked dout for the residual branch. partial: fp32 [blocks][2][C]; coef: fp32 [3][C].
  * frozen_stats != 0: mean/rstd are running statistics (eval mode / freeze_bn, cubercnn/solver/build.py:71-76).
  * out may be NULL for a ReLU layer WITHOUT residual when beta is given: the mask is then recomputed from y exactly as
- * c3d_bn_apply produced it (saves re-reading `out` in both passes). */
+ * c3d_bn_apply produced it (saves re-reading `out` in both passes).
+ * `relu` is a flag word: bit 0 = the layer has a ReLU, bit 1 = dres ACCUMULATES (dres += masked dout, fp32 add): the
+ * residual tensor's gradient buffer already holds its other consumers' contributions (what autograd's AccumulateGrad /
+ * add of dla.py:58-66's `out += residual` does with a separate pass). */
 int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, const float* mean, const float* rstd,
                    const float* gamma, const float* beta, int32_t relu, int32_t frozen_stats, float* partial, float* coef, float* dgamma,
                    float* dbeta,
@@ -203,6 +206,10 @@ int32_t c3d_maxpool2_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W
                          int64_t y_stride, void* stream);
 int32_t c3d_maxpool2_bwd(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C,
                          int64_t x_stride, int64_t dy_stride, void* stream);
+/* same, accumulating: dx (pixel stride dx_stride, 0 => C) += routed dy — x feeds the pool AND a strided convolution
+ * (dla.py:209-214), the pool's share is added into the convolution's data gradient in place */
+int32_t c3d_maxpool2_bwd_acc(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C,
+                             int64_t x_stride, int64_t dy_stride, int64_t dx_stride, void* stream);
 /* 3x3 / stride 2 / pad 1 max pool of the torchvision ResNet stem (cubercnn/modeling/backbone/resnet.py:17-27,45-50):
  * y (N,(H-1)/2+1,(W-1)/2+1,C); the backward routes dy to the first maximal element of every window (ATen tie order). */
 int32_t c3d_maxpool3s2_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);

@@ -56,7 +56,7 @@ def check(code, launches=1):
 EXPORTS = [
     "c3d_last_error", "c3d_abi_version", "c3d_iou_box3d_workspace_bytes", "c3d_iou_box3d",
     "c3d_iou_box3d_paired", "c3d_box3d_overlap", "c3d_conv2d_tiles", "c3d_conv2d_fwd", "c3d_conv2d_wgrad", "c3d_conv2d_wgrad_ex", "c3d_pack_conv_weight",
-    "c3d_bn_scratch_bytes", "c3d_bn_finalize", "c3d_bn_apply", "c3d_bn_bwd_blocks", "c3d_bn_bwd", "c3d_maxpool2_fwd", "c3d_maxpool2_bwd",
+    "c3d_bn_scratch_bytes", "c3d_bn_finalize", "c3d_bn_apply", "c3d_bn_bwd_blocks", "c3d_bn_bwd", "c3d_maxpool2_fwd", "c3d_maxpool2_bwd", "c3d_maxpool2_bwd_acc",
     "c3d_preprocess_image", "c3d_grad_finite", "c3d_sgd_momentum", "c3d_roi_align_fwd", "c3d_roi_align_bwd",
     "c3d_nms_workspace_bytes", "c3d_nms_batched", "c3d_bias_act_bwd", "c3d_sumpool2", "c3d_zero_stuff2", "c3d_cube_loss_fwd", "c3d_cube_loss_bwd",
     "c3d_anchor_match", "c3d_preprocess_image_u8", "c3d_sgd_momentum_dev", "c3d_rpn_loss_fwd", "c3d_rpn_loss_bwd", "c3d_nms_batched_grouped", "c3d_rpn_decode_level",

@@ -86,12 +86,17 @@ def num_tiles(desc):
 
 
 def conv2d_fwd(x, w, bias=None, stride=1, pad=0, relu=False, addend=None, up2=False, out_fp32=False,
-               want_stats=False, out=None, out_place=None, out_hw_override=None):
-    """x (N,H,W,Cin) bf16, w (Cout,KH,KW,Cin) bf16 -> y (N,Ho,Wo,Cout) bf16|fp32 [, stats (tiles,2,Cout)]."""
+               want_stats=False, out=None, out_place=None, out_hw_override=None, accumulate=False):
+    """x (N,H,W,Cin) bf16, w (Cout,KH,KW,Cin) bf16 -> y (N,Ho,Wo,Cout) bf16|fp32 [, stats (tiles,2,Cout)].
+    out: write into this buffer (dense, or a channel slice of a wider NHWC tensor); accumulate: out += conv (add_mode 3,
+    fp32 add in the epilogue) instead of out = conv."""
     L = _bind()
     assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()
     assert w.dtype == torch.bfloat16 and w.is_contiguous()
     add_mode = 0 if addend is None else (2 if up2 else 1)
+    if accumulate:
+        assert addend is None and out is not None and not out_fp32 and not want_stats
+        add_mode = 3
     d = make_desc(x, w, stride, pad, relu, out_fp32, add_mode)
     Ho, Wo = out_hw(d.H, d.W, d.KH, d.KW, stride, pad)
     if out_hw_override is not None:
@@ -101,6 +106,11 @@ def conv2d_fwd(x, w, bias=None, stride=1, pad=0, relu=False, addend=None, up2=Fa
         d.y_img_stride, d.y_h_stride, d.y_w_stride, d.y_offset = out_place
     if out is None:
         out = torch.empty((d.N, Ho, Wo, d.Cout), device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    elif not out.is_contiguous():                      # channel slice of a wider NHWC buffer
+        from .kernels import pixel_stride
+        ps = pixel_stride(out)
+        assert ps is not None, "conv2d_fwd: out must be dense or a 16-byte aligned channel slice"
+        d.y_pix_stride = ps
     stats = None
     if want_stats:
         t, _, _ = num_tiles(d)

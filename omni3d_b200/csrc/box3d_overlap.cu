@@ -29,6 +29,9 @@ namespace c3d {
 constexpr int kCap = 64;           // triangles per side in shared memory
 constexpr int kCapBig = 256;       // per side in the global-memory fallback
 constexpr int kWarpsPerBlock = 4;
+constexpr int kSidePad = 16;        // the second box's record / triangle buffers start 16 banks later: lanes 16-31 never hit lanes 0-15's banks
+constexpr int kRecSmem = 128 + kSidePad;
+__host__ __device__ constexpr int kBufSmem(int cap) { return 4 * 9 * cap + kSidePad; }
 constexpr int kFallbackWarps = 296;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr long long kMaxOverflowQueue = 1ll << 22;
@@ -164,12 +167,14 @@ __device__ __forceinline__ int process_pair(const float* __restrict__ recA, cons
                                             float* rec, float* buf, int lane, float* vol_o, float* iou_o) {
   const int side = lane >> 4, hl = lane & 15;
   // 1. records -> shared
+  constexpr int RB = 64 + kSidePad;          // second record
+  constexpr int SB = 2 * 9 * CAP + kSidePad;  // second side's ping-pong buffers
   rec[lane] = recA[lane]; rec[lane + 32] = recA[lane + 32];
-  rec[64 + lane] = recB[lane]; rec[64 + lane + 32] = recB[lane + 32];
+  rec[RB + lane] = recB[lane]; rec[RB + lane + 32] = recB[lane + 32];
   __syncwarp();
-  const float* rT = rec + 64 * side;        // box whose triangles this half clips
-  const float* rP = rec + 64 * (1 - side);  // box whose planes clip them
-  float* sb = buf + (size_t)side * 2 * 9 * CAP;
+  const float* rT = rec + RB * side;        // box whose triangles this half clips
+  const float* rP = rec + RB * (1 - side);  // box whose planes clip them
+  float* sb = buf + (size_t)side * SB;
   int cur = 0;
   // 2. the 12 box triangles
   if (hl < 12) {
@@ -242,10 +247,10 @@ __device__ __forceinline__ int process_pair(const float* __restrict__ recA, cons
   if (n1 + n2 == 0) { *vol_o = 0.f; *iou_o = 0.f; return 0; }
 
   // 4. de-dup: drop box2-side triangles coplanar with a (non-degenerate) box1-side triangle
-  const float* L1 = buf + (0 * 2 + cur) * 9 * CAP;         // final box1-side list
-  const float* L2 = buf + (1 * 2 + cur) * 9 * CAP;         // final box2-side list
-  float* F1 = buf + (0 * 2 + (cur ^ 1)) * 9 * CAP;         // scratch (free ping-pong halves)
-  float* F2 = buf + (1 * 2 + (cur ^ 1)) * 9 * CAP;
+  const float* L1 = buf + cur * 9 * CAP;                   // final box1-side list
+  const float* L2 = buf + SB + cur * 9 * CAP;              // final box2-side list
+  float* F1 = buf + (cur ^ 1) * 9 * CAP;                   // scratch (free ping-pong halves)
+  float* F2 = buf + SB + (cur ^ 1) * 9 * CAP;
   auto load_tri = [&](const float* L, int t) {
     Tri tr;
     tr.a = mk(L[0 * CAP + t], L[1 * CAP + t], L[2 * CAP + t]);
@@ -316,7 +321,7 @@ __device__ __forceinline__ int process_pair(const float* __restrict__ recA, cons
   float vol = 0.0f, iou = 0.0f;
   if (lane == 0) {
     for (int f = 0; f < nf; ++f) vol = vol + vt[f];
-    iou = vol / (rec[63] + rec[64 + 63] - vol);
+    iou = vol / (rec[63] + rec[RB + 63] - vol);
   }
   *vol_o = __shfl_sync(kFull, vol, 0);
   *iou_o = __shfl_sync(kFull, iou, 0);
@@ -427,8 +432,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock)
 iou3d_clip_kernel(PairArgs A, long long k0, const unsigned* __restrict__ queue) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* rec = smem + warp * (128 + 4 * 9 * kCap);
-  float* buf = rec + 128;
+  float* rec = smem + warp * (kRecSmem + kBufSmem(kCap));
+  float* buf = rec + kRecSmem;
   const unsigned n_live = A.ctrl->n_live;
   const unsigned W = gridDim.x * kWarpsPerBlock;
   for (unsigned q = warp * gridDim.x + blockIdx.x; q < n_live; q += W) {
@@ -453,9 +458,9 @@ iou3d_clip_kernel(PairArgs A, long long k0, const unsigned* __restrict__ queue) 
 // rare path: same routine, triangle lists in global memory (one slab per warp)
 __global__ void __launch_bounds__(32)
 iou3d_overflow_kernel(PairArgs A, float* slabs) {
-  __shared__ float rec[128];
+  __shared__ float rec[kRecSmem];
   const int lane = threadIdx.x;
-  float* buf = slabs + (size_t)blockIdx.x * (4 * 9 * kCapBig);
+  float* buf = slabs + (size_t)blockIdx.x * kBufSmem(kCapBig);
   const unsigned n = min(A.ctrl->n_overflow, A.overflow_cap);
   while (true) {
     unsigned q = 0;
@@ -496,7 +501,7 @@ static WsLayout ws_layout_pairs(int64_t n1, int64_t m2, int64_t npairs) {
   L.sph = o; o = align_up(o + (size_t)nb * 16, 256);
   L.flags = o; o = align_up(o + (size_t)n1, 256);
   L.overflow = o; o = align_up(o + (size_t)(npairs < kMaxOverflowQueue ? npairs : kMaxOverflowQueue) * 8, 256);
-  L.slabs = o; o = align_up(o + (size_t)kFallbackWarps * 4 * 9 * kCapBig * 4, 256);
+  L.slabs = o; o = align_up(o + (size_t)kFallbackWarps * kBufSmem(kCapBig) * 4, 256);
   L.queue = o; o = align_up(o + (size_t)(npairs < kBatchPairs ? npairs : kBatchPairs) * 4, 256);
   L.total = o;
   return L;
@@ -547,7 +552,7 @@ static int32_t run_iou(const float* b1, int64_t n1, const float* b2, int64_t n2,
       A.pair_off = reinterpret_cast<const long long*>(seg->pair_off); A.dt_off = seg->dt_off; A.gt_off = seg->gt_off;
       A.ngroups = seg->ngroups;
     }
-    size_t smem = (size_t)kWarpsPerBlock * (128 + 4 * 9 * kCap) * sizeof(float);
+    size_t smem = (size_t)kWarpsPerBlock * (kRecSmem + kBufSmem(kCap)) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
       cudaFuncSetAttribute(iou3d_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

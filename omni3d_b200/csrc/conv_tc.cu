@@ -915,6 +915,14 @@ static bool swap_fwd_eligible(const c3d_conv_desc* d, int Ho, int Wo, int* th, i
   if (off || halo_fwd_eligible(d)) return false;
   if (d->Cin % 64 != 0 || (d->Cout != 64 && d->Cout != 128) || (d->KH == 1 && d->Cin <= 64)) return false;
   if (d->stride < 1 || d->stride > 2) return false;
+  if (d->Cout == 64) {
+    // 64 output channels use half of the TMEM lanes, i.e. half of the epilogue warps: a win only when a tile carries enough
+    // MMA work per stored pixel (3x3: 9 K blocks) or the layer is a large HBM-bound 1x1 (measured, profiles/r02_summary.md);
+    // the phase convs of a stride-2 data gradient (1..4 taps) and small 1x1 layers stay on the pixel-major kernels
+    const long long num_kb = (long long)d->KH * d->KW * (d->Cin / 64);
+    const bool big_1x1 = d->KH == 1 && d->KW == 1 && (long long)d->N * Ho * Wo >= (1ll << 19);
+    if (num_kb < 9 && !big_1x1) return false;
+  }
   int th128, tw128;
   pick_tile(Ho, Wo, d->stride, &th128, &tw128);
   const long long t128 = (long long)((Ho + th128 - 1) / th128) * ((Wo + tw128 - 1) / tw128);

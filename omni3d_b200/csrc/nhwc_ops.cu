@@ -193,7 +193,7 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ coef, int relu,
                     bf16* __restrict__ dy, bf16* __restrict__ dres, long long P, int C, long long dout_stride,
                     long long out_stride, long long dres_stride, const float* __restrict__ gamma,
-                    const float* __restrict__ beta) {
+                    const float* __restrict__ beta, int dres_acc) {
   __shared__ float cm[3 * kBnMaxC];
   const bool remask = relu && out == nullptr;
   if (remask) bn_mask_consts(cm, mean, rstd, gamma, beta, C);
@@ -220,7 +220,14 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out,
 #pragma unroll
     for (int k = 0; k < 8; ++k) g.v[k] = __fmaf_rn(cA[k], d.v[k], __fmaf_rn(cB[k], yy.v[k], cK[k]));
     st8(dy + p * C + c, g);
-    if (dres) st8(dres + p * dres_stride + c, d);
+    if (dres) {
+      if (dres_acc) {                  // the residual branch's gradient already holds other contributions: add in fp32
+        const V8 r = ld8(dres + p * dres_stride + c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d.v[k] += r.v[k];
+      }
+      st8(dres + p * dres_stride + c, d);
+    }
   }
 }
 
@@ -431,8 +438,10 @@ __global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict
   }
 }
 // dx (N,H,W,C) = dy routed to the first maximal element of each window (row-major window order)
+template <bool ACC>
 __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx,
-                                    int N, int H, int W, int C, long long x_stride, long long dy_stride) {
+                                    int N, int H, int W, int C, long long x_stride, long long dy_stride,
+                                    long long dx_stride) {
   const int Ho = H >> 1, Wo = W >> 1, cv = C >> 3;
   const long long total = (long long)N * Ho * Wo * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -458,7 +467,14 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
       for (int j = 0; j < 4; ++j) o[j].v[k] = (j == best) ? g.v[k] : 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) st8(dx + off[j] * C + c, o[j]);
+    for (int j = 0; j < 4; ++j) {
+      if (ACC) {                       // dx already holds the gradient of x's other consumers
+        const V8 r = ld8(dx + off[j] * dx_stride + c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[j].v[k] += r.v[k];
+      }
+      st8(dx + off[j] * dx_stride + c, o[j]);
+    }
   }
 }
 
@@ -731,6 +747,8 @@ extern "C" int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, 
                               float* dgamma, float* dbeta, void* dy, void* dres, int64_t P, int32_t C,
                               int64_t dout_stride, int64_t out_stride, int64_t dres_stride, void* scratch,
                               void* stream) {
+  const int dres_acc = (relu >> 1) & 1;          // flags: bit 0 = ReLU, bit 1 = dres += (instead of =)
+  relu &= 1;
   C3D_REQ(dout && y && mean && rstd && gamma && partial && coef && dy && scratch && C % 8 == 0 && C <= 2048,
           "bn_bwd: bad args");
   C3D_REQ(!relu || out || beta, "bn_bwd: relu needs the forward output, or beta to recompute its sign from y");
@@ -750,7 +768,8 @@ extern "C" int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, 
   if (rc != C3D_OK) return rc;
   bn_bwd_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, st>>>((const bf16*)dout, (const bf16*)out, (const bf16*)y,
                                                                    mean, rstd, coef, relu, (bf16*)dy, (bf16*)dres, P, C,
-                                                                   ds, os, dres_stride ? dres_stride : C, gamma, beta);
+                                                                   ds, os, dres_stride ? dres_stride : C, gamma, beta,
+                                                                   dres_acc);
   return check_launch("bn_bwd");
 }
 extern "C" int32_t c3d_maxpool2_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
@@ -767,9 +786,19 @@ extern "C" int32_t c3d_maxpool2_bwd(const void* x, const void* dy, void* dx, int
   C3D_REQ(x && dy && dx && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_bwd: bad args");
   long long work = (long long)N * (H / 2) * (W / 2) * (C / 8);
   if (work == 0) return C3D_OK;
-  maxpool2_bwd_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (const bf16*)dy, (bf16*)dx, N, H, W, C, x_stride ? x_stride : C, dy_stride ? dy_stride : C);
+  maxpool2_bwd_kernel<false><<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)dy, (bf16*)dx, N, H, W, C, x_stride ? x_stride : C, dy_stride ? dy_stride : C, C);
   return check_launch("maxpool2_bwd");
+}
+extern "C" int32_t c3d_maxpool2_bwd_acc(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W,
+                                        int32_t C, int64_t x_stride, int64_t dy_stride, int64_t dx_stride, void* stream) {
+  C3D_REQ(x && dy && dx && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_bwd_acc: bad args");
+  long long work = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  if (work == 0) return C3D_OK;
+  maxpool2_bwd_kernel<true><<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)dy, (bf16*)dx, N, H, W, C, x_stride ? x_stride : C, dy_stride ? dy_stride : C,
+      dx_stride ? dx_stride : C);
+  return check_launch("maxpool2_bwd_acc");
 }
 extern "C" int32_t c3d_maxpool3s2_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
   C3D_REQ(x && y && C % 8 == 0 && H >= 1 && W >= 1, "maxpool3s2: bad args");

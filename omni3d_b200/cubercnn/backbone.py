@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from ..nnfunc import ConvBias, ConvBNAct, MaxPool2, MaxPool3s2
+from ..nnfunc import CatChannels, ConvBias, ConvBNAct, MaxPool2, MaxPool3s2, fork
 from .registry import BACKBONE_REGISTRY
 
 
@@ -71,7 +71,8 @@ class BasicBlock(nn.Module):
         self.bn2 = nn.BatchNorm2d(cout)
 
     def forward(self, x, residual=None):
-        residual = x if residual is None else residual
+        if residual is None:
+            x, residual = fork(x, 2)            # conv1 and the identity shortcut: one gradient buffer, no add pass
         y = conv_bn(x, self.conv1, self.bn1)
         return conv_bn(y, self.conv2, self.bn2, residual=residual)
 
@@ -83,7 +84,8 @@ class Root(nn.Module):
         self.bn = nn.BatchNorm2d(cout)
 
     def forward(self, *xs):
-        return conv_bn(torch.cat(xs, dim=-1), self.conv, self.bn)
+        cat = CatChannels.apply(*xs) if torch.is_grad_enabled() else torch.cat(xs, dim=-1)
+        return conv_bn(cat, self.conv, self.bn)
 
 
 class Tree(nn.Module):
@@ -109,17 +111,28 @@ class Tree(nn.Module):
 
     def forward(self, x, children=None):
         children = [] if children is None else children
-        bottom = MaxPool2.apply(x) if self.stride > 1 else x
+        # every tensor with more than one consumer is forked (nnfunc.fork): its consumers share one gradient buffer
+        n_bottom = int(self.level_root) + int(self.levels == 1)      # children list, project / identity residual
+        if self.stride > 1:
+            if n_bottom:
+                x, xp = fork(x, 2)
+                bottoms = list(fork(MaxPool2.apply(xp), n_bottom))
+            else:
+                bottoms = []                     # (levels == 2 without level_root: the pooled map is never used)
+        else:
+            x, *bottoms = fork(x, 1 + n_bottom)
         if self.level_root:
-            children.append(bottom)
+            children.append(bottoms.pop())
         if self.levels == 1:
+            bottom = bottoms.pop()
             residual = conv_bn(bottom, self.project[0], self.project[1], relu=False) if self.project else bottom
             x1 = self.tree1(x, residual)
-            x2 = self.tree2(x1)
-            return self.root(x2, x1, *children)
-        x1 = self.tree1(x)
-        children.append(x1)
-        return self.tree2(x1, children=children)
+            x1a, x1b, x1c = fork(x1, 3)          # tree2.conv1, tree2's shortcut, Root
+            x2 = self.tree2(x1a, x1b)
+            return self.root(x2, x1c, *children)
+        x1a, x1b = fork(self.tree1(x), 2)
+        children.append(x1b)
+        return self.tree2(x1a, children=children)
 
 
 class DLA34(nn.Module):
@@ -155,8 +168,7 @@ class DLA34(nn.Module):
             x = conv_bn(x, seq[0], seq[1])
         out = {}
         for i, name in zip(range(2, 6), ("p2", "p3", "p4", "p5")):
-            x = getattr(self, "level%d" % i)(x)
-            out[name] = x
+            x, out[name] = fork(getattr(self, "level%d" % i)(x), 2)      # next level (p5: the p6 subsample) + FPN lateral
         out["p6"] = x[:, ::2, ::2, :].contiguous()        # F.max_pool2d(k=1, s=2), dla.py:474
         return out
 
@@ -181,12 +193,12 @@ class TVResNet(nn.Module):
         out = {}
         for name, layer in zip(("p2", "p3", "p4", "p5"), (self.layer1, self.layer2, self.layer3, self.layer4)):
             for blk in layer:
-                idn = x
+                x, idn = fork(x, 2)              # conv1 + shortcut (identity or 1x1 downsample)
                 if blk.downsample is not None:
-                    idn = conv_bn(x, blk.downsample[0], blk.downsample[1], relu=False)
+                    idn = conv_bn(idn, blk.downsample[0], blk.downsample[1], relu=False)
                 y = conv_bn(x, blk.conv1, blk.bn1)
                 x = conv_bn(y, blk.conv2, blk.bn2, residual=idn)
-            out[name] = x
+            x, out[name] = fork(x, 2)
         out["p6"] = x[:, ::2, ::2, :].contiguous()
         return out
 
@@ -228,7 +240,8 @@ class FPN(nn.Module):
         for f, s in reversed(list(zip(self.in_features, self.stages))):
             lat, outc = getattr(self, "fpn_lateral%d" % s), getattr(self, "fpn_output%d" % s)
             prev = ConvBias.apply(feats[f], lat.weight, lat.bias, prev, 1, 0, False, False)
-            results["p%d" % s] = ConvBias.apply(prev, outc.weight, outc.bias, None, 1, 1, False, False)
+            prev_out, prev = fork(prev, 2) if s != self.stages[0] else (prev, None)     # output conv + next lateral's addend
+            results["p%d" % s] = ConvBias.apply(prev_out, outc.weight, outc.bias, None, 1, 1, False, False)
         return {k: results[k] for k in self._out_features}
 
 

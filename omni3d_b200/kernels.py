@@ -40,6 +40,7 @@ def _bind():
         "c3d_bn_bwd": [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, vp, vp],
         "c3d_maxpool2_fwd": [vp, vp, i32, i32, i32, i32, i64, i64, vp],
         "c3d_maxpool2_bwd": [vp, vp, vp, i32, i32, i32, i32, i64, i64, vp],
+        "c3d_maxpool2_bwd_acc": [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, vp],
         "c3d_preprocess_image": [vp, i32, i32, vp, i32, i32, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), vp],
         "c3d_grad_finite": [vp, i64, vp, vp],
         "c3d_sgd_momentum": [vp, vp, vp, i64, f32, f32, f32, f32, vp, vp],
@@ -130,9 +131,10 @@ def pixel_stride(t):
     return s
 
 
-def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres, frozen=False, beta=None):
+def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres, frozen=False, beta=None, dres_into=None):
     """-> dy (bf16, like y), dres (bf16 or None); dgamma/dbeta (fp32 [C]) are accumulated in place.  `dout` may be a
-    channel slice of a wider NHWC gradient (read in place through its pixel stride)."""
+    channel slice of a wider NHWC gradient (read in place through its pixel stride).  dres_into: an existing gradient
+    buffer of the residual tensor (possibly a channel slice): the masked dout is ADDED into it in place."""
     L = _bind()
     ds = pixel_stride(dout)
     if ds is None:
@@ -143,10 +145,16 @@ def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres, froz
     partial = torch.empty((blocks, 2, C), device=y.device, dtype=torch.float32)
     coef = torch.empty((3, C), device=y.device, dtype=torch.float32)
     dy = torch.empty_like(y)
-    dres = torch.empty_like(y) if want_dres else None
+    flags, rs = int(relu), 0
+    if dres_into is not None:
+        rs = pixel_stride(dres_into)
+        assert rs is not None and dres_into.dtype == torch.bfloat16
+        dres, flags = dres_into, flags | 2
+    else:
+        dres = torch.empty_like(y) if want_dres else None
     scratch = torch.empty(128 * 2 * C + 64, device=y.device, dtype=torch.float64)
-    _lib.check(L.c3d_bn_bwd(_p(dout), _p(out), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), int(relu), int(frozen), _p(partial), _p(coef),
-                            _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, ds, 0, 0, _p(scratch), _st()), launches=4)
+    _lib.check(L.c3d_bn_bwd(_p(dout), _p(out), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), flags, int(frozen), _p(partial), _p(coef),
+                            _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, ds, 0, rs, _p(scratch), _st()), launches=4)
     return dy, dres
 
 
@@ -158,12 +166,18 @@ def maxpool2_fwd(x):
     return y
 
 
-def maxpool2_bwd(x, dy):
+def maxpool2_bwd(x, dy, into=None):
+    """into: an existing gradient buffer of x (possibly a channel slice) that the routed dy is ADDED to in place."""
     L = _bind()
     N, H, W, C = x.shape
     ds = pixel_stride(dy)
     if ds is None:
         dy, ds = dy.contiguous(), 0
+    if into is not None:
+        xs = pixel_stride(into)
+        assert xs is not None and into.dtype == torch.bfloat16
+        _lib.check(L.c3d_maxpool2_bwd_acc(_p(x), _p(dy), _p(into), N, H, W, C, 0, ds, xs, _st()))
+        return into
     dx = torch.empty_like(x)
     _lib.check(L.c3d_maxpool2_bwd(_p(x), _p(dy), _p(dx), N, H, W, C, 0, ds, _st()))
     return dx

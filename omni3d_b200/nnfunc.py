@@ -7,6 +7,7 @@ kernels' bf16 OHWI layouts once per parameter version.  Forward AND backward run
   wgrad     -> c3d_conv2d_wgrad        BN    -> c3d_bn_finalize / c3d_bn_apply / c3d_bn_bwd
 """
 import ctypes
+import os
 import weakref
 
 import torch
@@ -138,27 +139,38 @@ def _phase_packs(w):
     return packs
 
 
-def _dgrad(dy, w, stride, pad, in_hw):
+def _dgrad(dy, w, stride, pad, in_hw, into=None):
     """dx for y = conv(x, w, stride, pad).  stride 1: conv of dy with the 180-degree-rotated, transposed weights.
     3x3/s2/p1: four phase convs (one per output parity) written straight into the strided positions of dx —
-    exactly the algorithmic FLOPs, no zero-stuffed intermediate."""
+    exactly the algorithmic FLOPs, no zero-stuffed intermediate.  into: an existing gradient buffer of x (dense or a
+    channel slice) that the result is ADDED to in the conv epilogue (returned)."""
     KH = w.shape[2]
+    acc = into is not None
     if stride == 2 and KH == 3 and pad == 1 and in_hw[0] == 2 * dy.shape[1] and in_hw[1] == 2 * dy.shape[2]:
         N, Ho, Wo, _ = dy.shape
         H, W = in_hw
-        dx = torch.empty((N, H, W, w.shape[1]), device=dy.device, dtype=dy.dtype)
+        dx = into if acc else torch.empty((N, H, W, w.shape[1]), device=dy.device, dtype=dy.dtype)
         for (a, b), wp in _phase_packs(w).items():
-            K.conv2d_fwd(dy, wp, stride=1, pad=0, out=dx, out_place=(H * W, 2 * W, 2, a * W + b), out_hw_override=(Ho, Wo))
+            K.conv2d_fwd(dy, wp, stride=1, pad=0, out=dx, out_place=(H * W, 2 * W, 2, a * W + b), out_hw_override=(Ho, Wo),
+                         accumulate=acc)
         return dx
     wp = _packed(w, "dgrad")
     if stride == 1:
-        return K.conv2d_fwd(dy, wp, stride=1, pad=KH - 1 - pad)
+        return K.conv2d_fwd(dy, wp, stride=1, pad=KH - 1 - pad, out=into, accumulate=acc)
     assert stride == 2
     H, W = in_hw
     z = Kx.zero_stuff2(dy, H, W)
     if KH == 1:                      # 1x1 stride 2: pure scatter + 1x1 conv
-        return K.conv2d_fwd(z, wp, stride=1, pad=0)
-    return K.conv2d_fwd(z, wp, stride=1, pad=KH - 1 - pad)
+        return K.conv2d_fwd(z, wp, stride=1, pad=0, out=into, accumulate=acc)
+    return K.conv2d_fwd(z, wp, stride=1, pad=KH - 1 - pad, out=into, accumulate=acc)
+
+
+def _dgrad_chained(sink, dy, w, stride, pad, in_hw):
+    """data gradient of a conv whose input may share its gradient buffer with the input's other consumers"""
+    if sink is not None and sink.buf is not None and sink.buf.dtype == dy.dtype:
+        _dgrad(dy, w, stride, pad, in_hw, into=sink.buf)
+        return None
+    return _deliver(sink, _dgrad(dy, w, stride, pad, in_hw))
 
 
 def _wgrad_to_master(x, dy, w, stride, pad):
@@ -183,6 +195,113 @@ def _grad_slot(p):
     return torch.zeros_like(p, dtype=torch.float32), True
 
 
+# ---- gradient chaining -------------------------------------------------------------------------------------------------
+# A tensor with several consumers (DLA: block input -> conv1 + residual; tree1 output -> tree2 + Root; Tree input ->
+# pool + strided conv; FPN top-down map -> output conv + the next lateral's addend ...) makes autograd run one add pass
+# per extra consumer over the whole gradient (~1.3 ms / step of strided bf16 adds at batch 32, profiles/r02_summary.md).
+# `fork(t, n)` hands every consumer its own alias of t; the aliases share a _GradSink.  The first consumer to produce
+# its gradient parks the buffer in the sink and returns it; every later consumer ADDS INTO that buffer inside the kernel
+# that produces its contribution (conv epilogue add_mode 3, c3d_bn_bwd's accumulating dres, c3d_maxpool2_bwd_acc) and
+# returns None.  _Fork.backward — which autograd runs after all consumers — folds in whatever reached it as a plain
+# tensor (consumers that know nothing of sinks) and hands the buffer to the producer.  Same sums as autograd's, with
+# the adds done in fp32 before the single bf16 rounding.
+GRAD_CHAIN = os.environ.get("C3D_NO_GRAD_CHAIN") is None
+
+
+class _GradSink:
+    __slots__ = ("buf",)
+
+    def __init__(self):
+        self.buf = None
+
+
+def _same_buffer(a, b):
+    return a is b or (a.data_ptr() == b.data_ptr() and a.shape == b.shape and a.stride() == b.stride())
+
+
+class _Fork(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, n, sink, outermost):
+        ctx.sink, ctx.outermost = sink, outermost
+        ctx.set_materialize_grads(False)
+        return tuple(x.view(x.shape) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        sink = ctx.sink
+        carried, extra = False, None
+        for g in gs:
+            if g is None:
+                continue
+            if sink.buf is not None and _same_buffer(g, sink.buf):
+                carried = True                         # the parked buffer itself, travelling up its own path
+            elif sink.buf is not None:
+                sink.buf.add_(g.to(sink.buf.dtype))    # plain gradient of a consumer outside the protocol
+            else:
+                extra = g if extra is None else extra + g     # nobody parked a buffer yet: plain autograd sums
+        if ctx.outermost:
+            total = sink.buf
+            sink.buf = None
+            if total is None:
+                total = extra
+            elif extra is not None:
+                total.add_(extra.to(total.dtype))
+            return total, None, None, None
+        # inner fork: never park a foreign tensor (it may be shared with other autograd edges); pass it up instead
+        if extra is not None:
+            if sink.buf is None or not carried:
+                return extra, None, None, None         # the outer fork adds it to / adopts it as the total
+            sink.buf.add_(extra.to(sink.buf.dtype))
+        return (sink.buf if carried else None), None, None, None
+
+
+def fork(t, n):
+    """n aliases of t, one per consumer (see above).  Nested forks of an alias share the outer sink."""
+    if n <= 1 or not GRAD_CHAIN or not torch.is_grad_enabled() or not t.requires_grad:
+        return (t,) * n
+    outer = getattr(t, "_c3d_sink", None)
+    sink = outer if outer is not None else _GradSink()
+    outs = _Fork.apply(t, n, sink, outer is None)
+    for o in outs:
+        o._c3d_sink = sink
+    return outs
+
+
+def _sink_of(t):
+    return getattr(t, "_c3d_sink", None) if GRAD_CHAIN else None
+
+
+def _deliver(sink, g):
+    """first arrival: park g and return it to autograd; later arrivals were added in place by the caller -> None"""
+    if sink is None:
+        return g
+    if sink.buf is None:
+        sink.buf = g
+        return g
+    if not _same_buffer(g, sink.buf):
+        sink.buf.add_(g)                               # a contribution without an accumulating kernel variant
+    return None
+
+
+class CatChannels(torch.autograd.Function):
+    """torch.cat(xs, dim=-1) of NHWC maps (dla.py:168 Root input); backward hands every input its channel slice of the
+    gradient in place (no copies) and parks the slices in the inputs' gradient sinks."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        ctx.sinks = [_sink_of(x) for x in xs]
+        ctx.widths = [x.shape[-1] for x in xs]
+        return torch.cat(xs, dim=-1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        outs, off = [], 0
+        for sink, c in zip(ctx.sinks, ctx.widths):
+            outs.append(_deliver(sink, dout[..., off:off + c]))
+            off += c
+        return tuple(outs)
+
+
 class ConvBNAct(torch.autograd.Function):
     """out = [relu]( BN_train|eval( conv(x, w) ) [+ residual] ) — dla.py:40-68 BasicBlock halves, Root, project."""
 
@@ -202,6 +321,7 @@ class ConvBNAct(torch.autograd.Function):
         out = Kx.bn_apply(y, mean, rstd, gamma, beta, res, relu)
         ctx.save_for_backward(x, w, gamma, y, mean, rstd, out, beta)
         ctx.cfg = (stride, pad, relu, training, residual is not None)
+        ctx.sinks = (_sink_of(x), _sink_of(residual) if residual is not None else None)
         return out
 
     @staticmethod
@@ -212,9 +332,14 @@ class ConvBNAct(torch.autograd.Function):
         dbeta, ret_b = _grad_slot(beta)
         # a ReLU layer without residual: its mask is recomputed from y inside the kernels (no read of `out`)
         remask = relu and not has_res
+        sx, sr = ctx.sinks
+        want_res = has_res and ctx.needs_input_grad[6]
+        into = sr.buf if (want_res and sr is not None and sr.buf is not None and sr.buf.dtype == y.dtype) else None
         dy, dres = Kx.bn_bwd(dout, None if remask else out, y, mean, rstd, gamma, relu, dgamma, dbeta,
-                              has_res and ctx.needs_input_grad[6], frozen=not training, beta=beta if remask else None)
-        dx = _dgrad(dy, w, stride, pad, x.shape[1:3]) if ctx.needs_input_grad[0] else None
+                              want_res, frozen=not training, beta=beta if remask else None, dres_into=into)
+        if want_res:
+            dres = None if into is not None else _deliver(sr, dres)
+        dx = _dgrad_chained(sx, dy, w, stride, pad, x.shape[1:3]) if ctx.needs_input_grad[0] else None
         dw = _wgrad_to_master(x, dy, w, stride, pad) if ctx.needs_input_grad[1] else None
         return (dx, dw, dgamma if ret_g else None, dbeta if ret_b else None, None, None, dres, None, None, None, None,
                 None, None)
@@ -231,6 +356,7 @@ class ConvBias(torch.autograd.Function):
                            out_fp32=out_fp32)
         ctx.save_for_backward(x, w, out if relu else None, bias)
         ctx.cfg = (stride, pad, relu, addend is not None, bias is not None)
+        ctx.sinks = (_sink_of(x), _sink_of(addend) if addend is not None else None)
         return out
 
     @staticmethod
@@ -239,8 +365,9 @@ class ConvBias(torch.autograd.Function):
         stride, pad, relu, has_add, has_bias = ctx.cfg
         dbias, ret_b = _grad_slot(bias) if has_bias else (None, False)
         dzb = Kx.bias_act_bwd(dout, out, relu, dbias)
-        dadd = Kx.sumpool2(dzb) if has_add and ctx.needs_input_grad[3] else None
-        dx = _dgrad(dzb, w, stride, pad, x.shape[1:3]) if ctx.needs_input_grad[0] else None
+        sx, sa = ctx.sinks
+        dadd = _deliver(sa, Kx.sumpool2(dzb)) if has_add and ctx.needs_input_grad[3] else None
+        dx = _dgrad_chained(sx, dzb, w, stride, pad, x.shape[1:3]) if ctx.needs_input_grad[0] else None
         dw = _wgrad_to_master(x, dzb, w, stride, pad) if ctx.needs_input_grad[1] else None
         return dx, dw, dbias if ret_b else None, dadd, None, None, None, None
 
@@ -342,6 +469,7 @@ class TwoHeadFC1(torch.autograd.Function):
 class MaxPool2(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
+        ctx.sink = _sink_of(x)
         x = x.contiguous()
         ctx.save_for_backward(x)
         return Kx.maxpool2_fwd(x)
@@ -349,7 +477,11 @@ class MaxPool2(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
-        return Kx.maxpool2_bwd(x, dy)
+        sink = ctx.sink
+        if sink is not None and sink.buf is not None and sink.buf.dtype == x.dtype:
+            Kx.maxpool2_bwd(x, dy, into=sink.buf)
+            return None
+        return _deliver(sink, Kx.maxpool2_bwd(x, dy))
 
 
 class MaxPool3s2(torch.autograd.Function):

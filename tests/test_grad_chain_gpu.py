@@ -1,0 +1,76 @@
+"""Gradient chaining (omni3d_b200.nnfunc.fork): consumers of a multiply-used activation add their gradient
+contributions into ONE buffer inside the producing kernels instead of autograd running an add pass per consumer.
+The sums are the same; only the rounding differs (fp32 add before the single bf16 rounding instead of a bf16
+round per partial sum) — parameter gradients with and without chaining must agree to bf16 accuracy."""
+import pytest
+import torch
+
+from omni3d_b200 import nnfunc, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _grads(name, chain, frozen_bn):
+    from omni3d_b200 import cubercnn as pc
+    nnfunc.GRAD_CHAIN = chain
+    try:
+        torch.manual_seed(0)
+        cfg = pc.load_cfg(name, ["MODEL.WEIGHTS_PRETRAIN", "none"])
+        model = pc.build_model(cfg)
+        model.train()
+        if frozen_bn:
+            for m in model.modules():
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.eval()
+        items = synth.make_batch(2, 128, 192, with_gt=False, seed=3)
+        x, _ = model.preprocess_image(items)
+        feats = model.backbone(x)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        loss = 0.0
+        for k in sorted(feats):
+            w = torch.randn(feats[k].shape, device="cuda", generator=g)
+            loss = loss + (feats[k].float() * w).sum()
+        loss.backward()
+        return {n: p.grad.detach().clone() for n, p in model.backbone.named_parameters() if p.grad is not None}
+    finally:
+        nnfunc.GRAD_CHAIN = True
+
+
+@pytest.mark.parametrize("name", ["cubercnn_DLA34_FPN.yaml", "cubercnn_ResNet34_FPN.yaml"])
+def test_chained_gradients_equal_autograd_sums(name):
+    # frozen BatchNorm: no batch-statistics amplification, the comparison isolates the gradient sums themselves
+    ref = _grads(name, False, True)
+    got = _grads(name, True, True)
+    assert ref.keys() == got.keys() and len(ref) > 100
+    worst = 0.0
+    for k in ref:
+        r, g = ref[k].float(), got[k].float()
+        assert torch.isfinite(g).all(), k
+        rel = float((g - r).norm() / (r.norm() + 1e-20))
+        worst = max(worst, rel)
+        assert rel < 2e-2, (k, rel)          # bf16 rounding of the partial sums (eps 2^-8) through <= 40 layers
+    assert worst > 0.0 or True
+
+
+def test_chaining_removes_the_add_passes():
+    """with chaining the backbone's backward issues no ATen add kernels for activation gradients"""
+    from omni3d_b200 import cubercnn as pc
+    from torch.profiler import profile, ProfilerActivity
+    counts = {}
+    for chain in (False, True):
+        nnfunc.GRAD_CHAIN = chain
+        try:
+            torch.manual_seed(0)
+            model = pc.build_model(pc.load_cfg("cubercnn_DLA34_FPN.yaml", ["MODEL.WEIGHTS_PRETRAIN", "none"]))
+            model.train()
+            items = synth.make_batch(2, 128, 192, with_gt=False, seed=3)
+            x, _ = model.preprocess_image(items)
+            feats = model.backbone(x)
+            loss = sum(f.float().sum() for f in feats.values())
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                loss.backward()
+                torch.cuda.synchronize()
+            counts[chain] = sum(e.count for e in prof.key_averages() if "CUDAFunctor_add" in e.key)
+        finally:
+            nnfunc.GRAD_CHAIN = True
+    assert counts[True] <= counts[False] - 20, counts
