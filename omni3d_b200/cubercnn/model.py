@@ -15,6 +15,7 @@ from torch import nn
 
 from .. import _lib
 from .. import kernels as Kx
+from ..nnfunc import fork
 from .backbone import FPN  # noqa: F401  (registers the builders)
 from .registry import BACKBONE_REGISTRY, META_ARCH_REGISTRY, PROPOSAL_GENERATOR_REGISTRY, ROI_HEADS_REGISTRY
 from .roi_heads import ROIHeads3D  # noqa: F401
@@ -154,8 +155,13 @@ class RCNN3D(nn.Module):
             features = self.backbone(x)
             if pre is not None:
                 torch.cuda.current_stream().wait_stream(self._side)
-            proposals, l_rpn = self.proposal_generator(features, sizes, gt, sizes_dev=hw, prelabel=pre)
-            _, losses = self.roi_heads(features, proposals, sizes, Ks, ratios, gt, im_h=hw[:, 0], meta=meta)
+            # every FPN map feeds the RPN head AND the RoI pooler: one alias per consumer, so the RPN conv's data gradient
+            # is added into the pooler's gradient inside the conv epilogue (nnfunc.fork) instead of by an add pass
+            f_rpn, f_roi = {}, {}
+            for k, v in features.items():
+                f_rpn[k], f_roi[k] = fork(v, 2)
+            proposals, l_rpn = self.proposal_generator(f_rpn, sizes, gt, sizes_dev=hw, prelabel=pre)
+            _, losses = self.roi_heads(f_roi, proposals, sizes, Ks, ratios, gt, im_h=hw[:, 0], meta=meta)
             losses.update(l_rpn)
             self.metrics = {**self.proposal_generator.stats, **self.roi_heads.stats}
             return losses

@@ -504,6 +504,7 @@ class ROIAlign(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, rois, strides, pooled, *feats):
+        ctx.sinks = [_sink_of(f) for f in feats]
         feats = [f.contiguous() for f in feats]
         ctx.save_for_backward(rois, *feats)
         ctx.cfg = (strides, pooled)
@@ -514,7 +515,7 @@ class ROIAlign(torch.autograd.Function):
         rois, *feats = ctx.saved_tensors
         strides, pooled = ctx.cfg
         grads = Kx.roi_align_bwd(feats, strides, rois, dout.contiguous(), pooled)
-        return (None, None, None) + tuple(g.to(torch.bfloat16) for g in grads)
+        return (None, None, None) + tuple(_deliver(s, g.to(torch.bfloat16)) for s, g in zip(ctx.sinks, grads))
 
 
 class CubeLossRows(torch.autograd.Function):
