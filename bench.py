@@ -92,6 +92,10 @@ def peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _hbm_peak_gbs():
+    return peaks()[1]
+
+
 # ---------------------------------------------------------------------------------------------------------
 def physical_cores():
     try:
@@ -231,7 +235,9 @@ def conv_roofline(trainer, items, peak_tflops, peak_src, conv_fwd_gmac):
         out = o_f(x, w, *a, **k)
         e1.record()
         y = out[0] if isinstance(out, tuple) else out
-        rec.append((e0, e1, 2.0 * y.shape[0] * y.shape[1] * y.shape[2] * w.shape[0] * w.shape[1] * w.shape[2] * w.shape[3], "fwd"))
+        rec.append((e0, e1, 2.0 * y.shape[0] * y.shape[1] * y.shape[2] * w.shape[0] * w.shape[1] * w.shape[2] * w.shape[3], "fwd",
+                    x.numel() * x.element_size() + y.shape[0] * y.shape[1] * y.shape[2] * w.shape[0] * y.element_size()
+                    + w.numel() * 2))
         return out
 
     def wgrad(x, dy, KH, KW, stride=1, pad=0, dw=None, oihw=False):
@@ -239,7 +245,8 @@ def conv_roofline(trainer, items, peak_tflops, peak_src, conv_fwd_gmac):
         e0.record()
         out = o_w(x, dy, KH, KW, stride, pad, dw, oihw)
         e1.record()
-        rec.append((e0, e1, 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * KH * KW * x.shape[3], "wgrad"))
+        rec.append((e0, e1, 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * KH * KW * x.shape[3], "wgrad",
+                    (x.numel() + dy.numel()) * 2 + dy.shape[3] * KH * KW * x.shape[3] * 4))
         return out
 
     K.conv2d_fwd, K.conv2d_wgrad = fwd, wgrad
@@ -254,7 +261,7 @@ def conv_roofline(trainer, items, peak_tflops, peak_src, conv_fwd_gmac):
     finally:
         K.conv2d_fwd, K.conv2d_wgrad = o_f, o_w
         trainer.use_graph = graph_mode
-    ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
+    ms = sum(r[0].elapsed_time(r[1]) for r in rec)
     # ALGORITHMIC conv FLOPs of one train step: bottom-up (DLA34 25.081 | ResNet34 29.904) + FPN 20.913 +
     # RPN head 20.244 GMAC/img forward; backward = dgrad (no dgrad for the 0.963-GMAC stem) + wgrad.  Executed FLOPs are higher
     # (stem Cin 3 padded to 16, zero-stuffed stride-2 dgrad) and are NOT what is credited here.
@@ -262,14 +269,34 @@ def conv_roofline(trainer, items, peak_tflops, peak_src, conv_fwd_gmac):
     fl = n_img * 2.0 * (3 * conv_fwd_gmac * 1e9 - 0.963e9)
     ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
     by = {}
-    for a, b, f, kind in rec:
+    # per-launch roofline: a launch can be no faster than max(FLOPs / tensor peak, algorithmic bytes / HBM peak) — the 1x1 and
+    # <= 32-channel layers of the family are HBM-bound (arithmetic intensity below the ridge peak_tflops / hbm), the 3x3 layers
+    # with >= 64 channels tensor-bound; `per_launch_model` sums both against the measured time
+    hbm = _hbm_peak_gbs()
+    cls = {"tensor_bound": [0.0, 0.0, 0.0, 0], "hbm_bound": [0.0, 0.0, 0.0, 0]}     # ms, flops, bytes, launches
+    attainable_ms = 0.0
+    for a, b, f, kind, nbytes in rec:
         t = by.setdefault(kind, [0.0, 0.0, 0])
-        t[0] += a.elapsed_time(b); t[1] += f; t[2] += 1
+        dt = a.elapsed_time(b)
+        t[0] += dt; t[1] += f; t[2] += 1
+        t_tensor, t_hbm = f / (peak_tflops * 1e12) * 1e3, nbytes / (hbm * 1e9) * 1e3
+        attainable_ms += max(t_tensor, t_hbm)
+        c = cls["tensor_bound" if t_tensor >= t_hbm else "hbm_bound"]
+        c[0] += dt; c[1] += f; c[2] += nbytes; c[3] += 1
+    model = {"attainable_ms": attainable_ms, "measured_ms": ms, "frac": attainable_ms / ms if ms else 0.0, "hbm_peak_gbs": hbm,
+             "tensor_bound": {"ms": cls["tensor_bound"][0], "launches": cls["tensor_bound"][3],
+                              "tflops": cls["tensor_bound"][1] / (cls["tensor_bound"][0] * 1e-3) / 1e12 if cls["tensor_bound"][0] else 0.0,
+                              "frac_of_tensor_peak": (cls["tensor_bound"][1] / (cls["tensor_bound"][0] * 1e-3) / 1e12 / peak_tflops)
+                              if cls["tensor_bound"][0] else 0.0},
+             "hbm_bound": {"ms": cls["hbm_bound"][0], "launches": cls["hbm_bound"][3],
+                           "GBps": cls["hbm_bound"][2] / (cls["hbm_bound"][0] * 1e-3) / 1e9 if cls["hbm_bound"][0] else 0.0,
+                           "frac_of_hbm_peak": (cls["hbm_bound"][2] / (cls["hbm_bound"][0] * 1e-3) / 1e9 / hbm)
+                           if cls["hbm_bound"][0] else 0.0}}
     return {"bound": "tensor", "kernel": "conv_tc_* / conv_halo_* / conv_wgrad_tc_kernel (tcgen05 implicit GEMM, fwd + dgrad + wgrad)",
             "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": _top_kernel_traffic(),
             "peak_source": peak_src + ", bf16 sustained (kernel timed inside a long step)",
             "launches_per_step": len(rec), "conv_ms_per_step": ms, "algorithmic_tflop_per_step": fl / 1e12,
-            "executed_tflop_per_step": sum(f for _, _, f, _ in rec) / 1e12,
+            "executed_tflop_per_step": sum(r[2] for r in rec) / 1e12, "per_launch_model": model,
             "breakdown": {k: {"ms": v[0], "tflops": v[1] / (v[0] * 1e-3) / 1e12 if v[0] else 0, "launches": v[2]}
                           for k, v in by.items()}}
 

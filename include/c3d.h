@@ -98,6 +98,12 @@ typedef struct {
   /* optional distance between consecutive input images in PIXELS (0 => dense H*W): lets a batch of row blocks of a
    * larger matrix be read in place (the cube head's RoIs are the first Fc of every image's S pooled RoIs) */
   int64_t x_img_stride;
+  /* optional split of the output channels over two places of the output tensor: channels >= y_split_c (a multiple of 16)
+   * are written y_split_off ELEMENTS further than their position inside the pixel.  Used by the merged stride-2 data
+   * gradient: ONE 2x2 convolution of dy produces the 2x2 block of dx pixels of every dy pixel as 4*Cin output channels —
+   * (row parity a, column parity b, ci) — the b halves are adjacent pixels, the a halves are W*Cin elements apart.  0 => off */
+  int32_t y_split_c, pad_;
+  int64_t y_split_off;
 } c3d_conv_desc;
 
 /* number of 128-pixel output tiles (= rows of the BatchNorm partial-statistics buffer) and tile shape */

@@ -18,7 +18,8 @@ class ConvDesc(ctypes.Structure):
                 ("x_pix_stride", ctypes.c_int64), ("y_pix_stride", ctypes.c_int64),
                 ("add_pix_stride", ctypes.c_int64), ("y_img_stride", ctypes.c_int64), ("y_h_stride", ctypes.c_int64),
                 ("y_w_stride", ctypes.c_int64), ("y_offset", ctypes.c_int64), ("out_h", ctypes.c_int32),
-                ("out_w", ctypes.c_int32), ("x_img_stride", ctypes.c_int64)]
+                ("out_w", ctypes.c_int32), ("x_img_stride", ctypes.c_int64), ("y_split_c", ctypes.c_int32),
+                ("pad_", ctypes.c_int32), ("y_split_off", ctypes.c_int64)]
 
 
 _bound = False
@@ -75,7 +76,7 @@ def make_desc(x, w, stride=1, pad=0, relu=False, out_fp32=False, add_mode=0):
     N, H, W, Cin = x.shape
     Cout, KH, KW, Cin2 = w.shape
     assert Cin == Cin2, (x.shape, w.shape)
-    return ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, int(relu), int(out_fp32), add_mode, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+    return ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, int(relu), int(out_fp32), add_mode, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
 
 
 def num_tiles(desc):
@@ -86,7 +87,7 @@ def num_tiles(desc):
 
 
 def conv2d_fwd(x, w, bias=None, stride=1, pad=0, relu=False, addend=None, up2=False, out_fp32=False,
-               want_stats=False, out=None, out_place=None, out_hw_override=None, accumulate=False):
+               want_stats=False, out=None, out_place=None, out_hw_override=None, accumulate=False, split=None):
     """x (N,H,W,Cin) bf16, w (Cout,KH,KW,Cin) bf16 -> y (N,Ho,Wo,Cout) bf16|fp32 [, stats (tiles,2,Cout)].
     out: write into this buffer (dense, or a channel slice of a wider NHWC tensor); accumulate: out += conv (add_mode 3,
     fp32 add in the epilogue) instead of out = conv."""
@@ -104,6 +105,8 @@ def conv2d_fwd(x, w, bias=None, stride=1, pad=0, relu=False, addend=None, up2=Fa
         d.out_h, d.out_w = Ho, Wo
     if out_place is not None:        # (img_stride, h_stride, w_stride, offset) in pixels of `out`
         d.y_img_stride, d.y_h_stride, d.y_w_stride, d.y_offset = out_place
+    if split is not None:            # (first channel of the second half, its extra offset in elements): c3d.h y_split_*
+        d.y_split_c, d.y_split_off = split
     if out is None:
         out = torch.empty((d.N, Ho, Wo, d.Cout), device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
     elif not out.is_contiguous():                      # channel slice of a wider NHWC buffer
@@ -111,6 +114,9 @@ def conv2d_fwd(x, w, bias=None, stride=1, pad=0, relu=False, addend=None, up2=Fa
         ps = pixel_stride(out)
         assert ps is not None, "conv2d_fwd: out must be dense or a 16-byte aligned channel slice"
         d.y_pix_stride = ps
+    elif out.dim() == 4 and out.shape[-1] != d.Cout:   # split placement: the conv's channels span several pixels of `out`
+        assert split is not None
+        d.y_pix_stride = out.shape[-1]
     stats = None
     if want_stats:
         t, _, _ = num_tiles(d)
@@ -146,7 +152,7 @@ def conv2d_wgrad(x, dy, KH, KW, stride=1, pad=0, dw=None, oihw=False):
     assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
     if dw is None:
         dw = torch.zeros((Cout, Cin, KH, KW) if oihw else (Cout, KH, KW, Cin), device=x.device, dtype=torch.float32)
-    d = ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+    d = ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
     _lib.check(L.c3d_conv2d_wgrad_ex(ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw), int(oihw), _stream()))
     return dw
 

@@ -49,6 +49,8 @@ struct ConvKParams {
   void* out;
   long long out_pix_stride;  // elements
   long long out_img_stride, out_h_stride, out_w_stride, out_off;   // output pixel index = img*is + ho*hs + wo*ws + off
+  int split_c;               // 0, or: output channels >= split_c live split_off elements further (second output row of the
+  long long split_off;       // merged stride-2 data gradient: channel j of pixel (h,w) = dx[2h + j / split_c][2w + ..])
   float* stats;              // [tiles_m][2][Cout] partial (sum, sum of squares) or null
 };
 
@@ -95,6 +97,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& P, const u
     for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
     if (ch + 1 < kChunks) ptx::tmem_ld_32x32b_x16(tacc + (uint32_t)((ch + 1) * 16), v);
     const int c0 = n0 + ch * 16;
+    const long long coff = c0 + ((P.split_c && c0 >= P.split_c) ? P.split_off : 0);   // channel offset inside the pixel
     if (P.stats) {
       // per-channel sum / sum-of-squares over the valid rows of this tile (raw fp32 accumulators).  Each warp transposes its
       // 32 rows x 16 channels through a private 16 x 33-word shared-memory tile (row r writes column r: conflict-free; lane
@@ -121,7 +124,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& P, const u
         for (int i = 0; i < 16; ++i) f[i] += __ldg(P.bias + c0 + i);
       }
       if (P.add_mode) {
-        const bf16* abase = P.add_mode == 3 ? reinterpret_cast<const bf16*>(P.out) + pix * P.out_pix_stride
+        const bf16* abase = P.add_mode == 3 ? reinterpret_cast<const bf16*>(P.out) + pix * P.out_pix_stride + (coff - c0)
                                             : P.addend + apix * P.add_pix_stride;
         const uint4* ap = reinterpret_cast<const uint4*>(abase + c0);
         uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
@@ -137,7 +140,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& P, const u
     }
     if (P.out_fp32) {
       if (live) {
-        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix * P.out_pix_stride + c0);
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix * P.out_pix_stride + coff);
 #pragma unroll
         for (int i = 0; i < 4; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
       }
@@ -153,7 +156,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& P, const u
     // 128-byte row segments is SLOWER — 1x1 64->256 @160: 0.38 -> 0.72 ms; the write path already merges the two half-sector
     // stores and the extra shared-memory round trip only lengthens a latency-bound epilogue)
     if (live) {
-      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + pix * P.out_pix_stride + c0);
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + pix * P.out_pix_stride + coff);
       op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
@@ -494,6 +497,7 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // store side of the transposes below: this thread writes pixel (lane >> 1) of a 16-pixel chunk, channels cs..cs+15
     const int sp = lane >> 1, cs = q * 32 + (lane & 1) * 16;
     const bool svalid = cs < P.Cout;
+    const long long csoff = cs + ((P.split_c && cs >= P.split_c) ? P.split_off : 0);      // channel offset inside the pixel
     float* tr = reinterpret_cast<float*>(smem + S::kStgOffset) + (warp - 2) * (16 * S::kStgPitch);
     float* sstat = reinterpret_cast<float*>(smem + S::kStatOffset);
     int acc = 0; uint32_t acc_phase = 0;
@@ -547,7 +551,7 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                                   (long long)wo * P.out_w_stride + P.out_off;
             if (P.add_mode) {
               const bf16* abase;
-              if (P.add_mode == 3) abase = reinterpret_cast<const bf16*>(P.out) + pix * P.out_pix_stride;
+              if (P.add_mode == 3) abase = reinterpret_cast<const bf16*>(P.out) + pix * P.out_pix_stride + (csoff - cs);
               else if (P.add_mode == 1) abase = P.addend + (((long long)img * P.Ho + ho) * P.Wo + wo) * P.add_pix_stride;
               else abase = P.addend + (((long long)img * (P.Ho >> 1) + (ho >> 1)) * (P.Wo >> 1) + (wo >> 1)) * P.add_pix_stride;
               const uint4* ap = reinterpret_cast<const uint4*>(abase + cs);
@@ -562,7 +566,7 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
               for (int k = 0; k < 16; ++k) g[k] = fmaxf(g[k], 0.f);
             }
             if (P.out_fp32) {
-              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix * P.out_pix_stride + cs);
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix * P.out_pix_stride + csoff);
 #pragma unroll
               for (int k = 0; k < 4; ++k) op[k] = make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]);
             } else {
@@ -572,7 +576,7 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 __nv_bfloat162 h = __floats2bfloat162_rn(g[2 * k], g[2 * k + 1]);
                 pk[k] = *reinterpret_cast<uint32_t*>(&h);
               }
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + pix * P.out_pix_stride + cs);
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(P.out) + pix * P.out_pix_stride + csoff);
               op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
@@ -964,7 +968,8 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   if (Cout % 128 != 0) BN = (Cout % 64 == 0) ? 64 : (Cout % 32 == 0 ? 32 : 16);
   // persistent + double-buffered TMEM pays off for the tensor-bound shapes; the tiny-K / memory-bound ones
   // (Cin < 64, or 1x1 with Cin <= 64) run better as many short CTAs (measured, profiles/)
-  const bool persistent = !non_persistent && BK == 64 && BN >= 64 && !(d->KH == 1 && Cin <= 64);
+  static const bool p1x1 = getenv("C3D_CONV_P1X1") != nullptr;      // lab: one-K-block 1x1 layers on the persistent kernel
+  const bool persistent = !non_persistent && BK == 64 && BN >= 64 && (p1x1 || !(d->KH == 1 && Cin <= 64));
   if (persistent && allow_n256 && Cout % 256 == 0) BN = 256;
   const int Ho = d->out_h > 0 ? d->out_h : (d->H + 2 * d->pad - d->KH) / d->stride + 1;
   const int Wo = d->out_w > 0 ? d->out_w : (d->W + 2 * d->pad - d->KW) / d->stride + 1;
@@ -995,6 +1000,9 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   } else {
     P.out_img_stride = (long long)Ho * Wo; P.out_h_stride = Wo; P.out_w_stride = 1; P.out_off = 0;
   }
+  P.split_c = d->y_split_c; P.split_off = d->y_split_off;
+  if (P.split_c && (P.split_c % 16 != 0 || d->add_mode == 1 || d->add_mode == 2 || stats))
+    return set_error(C3D_EINVAL, "conv2d: y_split_c must be a multiple of 16 without addend / statistics");
   P.stats = stats;
   const long long xps = d->x_pix_stride ? d->x_pix_stride : Cin;
 

@@ -616,7 +616,9 @@ __global__ void pack_conv_weights_batched_kernel(const PackDesc* __restrict__ de
     if (D.phase[0]) {               // 3x3 only: parity a = (kh != 1), position inside the phase: kh 1 -> 0 | kh 2 -> 0, kh 0 -> 1
       const int a = kh != 1, b = kw != 1;
       const int ph = a ? (kh == 2 ? 0 : 1) : 0, pw = b ? (kw == 2 ? 0 : 1) : 0;
-      const int KHp = a ? 2 : 1, KWp = b ? 2 : 1;
+      // pad_ != 0: "merged" layout — the four phases are row blocks [(a,b)*Cin, +Cin) of ONE (4*Cin, 2, 2, Cout) weight (a 2x2
+      // convolution of dy with 4*Cin output channels, include/c3d.h y_split_*); taps a phase does not use stay zero
+      const int KHp = (a || D.pad_) ? 2 : 1, KWp = (b || D.pad_) ? 2 : 1;
       D.phase[a * 2 + b][(((long long)ci * KHp + ph) * KWp + pw) * D.Cout + co] = v;
     }
   }

@@ -90,14 +90,19 @@ def prepack_model(model):
             phase = m.stride[0] == 2 and KH == 3 and KW == 3 and m.padding[0] == 1
             f = torch.empty((O, KH, KW, I), device=dev, dtype=torch.bfloat16)
             g = torch.empty((I, KH, KW, O), device=dev, dtype=torch.bfloat16)
-            ph = {(a, b): torch.empty((I, 2 if a else 1, 2 if b else 1, O), device=dev, dtype=torch.bfloat16)
-                  for a in (0, 1) for b in (0, 1)} if phase else None
+            merged = phase and _merge_phases(I, O)
+            if merged:          # ONE (4*I, 2, 2, O) weight: row block (a,b) = phase (a,b); unused taps stay zero for ever
+                mg = torch.zeros((4 * I, 2, 2, O), device=dev, dtype=torch.bfloat16)
+                ph = {"merged": mg, **{(a, b): mg[(2 * a + b) * I:(2 * a + b + 1) * I] for a in (0, 1) for b in (0, 1)}}
+            else:
+                ph = {(a, b): torch.empty((I, 2 if a else 1, 2 if b else 1, O), device=dev, dtype=torch.bfloat16)
+                      for a in (0, 1) for b in (0, 1)} if phase else None
             d = arr[i]
             d.src, d.fwd, d.dgrad = w.data_ptr(), f.data_ptr(), g.data_ptr()
             for a in (0, 1):
                 for b in (0, 1):
                     d.phase[a * 2 + b] = ph[(a, b)].data_ptr() if ph else None
-            d.start, d.Cout, d.Cin, d.KH, d.KW, d.ohwi = start, O, I, KH, KW, int(ohwi)
+            d.start, d.Cout, d.Cin, d.KH, d.KW, d.ohwi, d.pad_ = start, O, I, KH, KW, int(ohwi), int(bool(merged))
             start += w.numel()
             bufs.append((w, f, g, ph))
         table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
@@ -117,6 +122,17 @@ def prepack_model(model):
     return plan["n"]
 
 
+_MERGE_MAX_O = int(os.environ.get("C3D_DGRAD_MERGE_MAX_O", "256"))
+
+
+def _merge_phases(I, O):
+    """stride-2 3x3 data gradient as ONE 2x2 convolution of dy with 4*I output channels — (row parity, column parity, ci), the
+    conv epilogue places the two row halves one dx row apart (c3d.h y_split_*) — instead of four phase convs: 1.78x the
+    FLOPs (7 of the 16 taps are zero) but one pass over dy, one launch, full-width tiles.  Measured (batch 32, B200):
+    16->32 @640: 0.591 -> 0.253 ms, 32->64 @320: 0.312 -> 0.111, 64->128 @160: 0.107 -> 0.070, 128->256 @80: 0.075 -> 0.060."""
+    return O <= _MERGE_MAX_O and (2 * I) % 16 == 0 and O % 16 == 0
+
+
 def _phase_packs(w):
     """sub-kernels of a 3x3 / stride-2 / pad-1 conv's data gradient, one per output parity (a,b):
     dx[2i+a, 2j+b] = sum_{k'} dy[i+k'h, j+k'w] * W[.., kh(a,k'h), kw(b,k'w)] with kh(0,.) = [1], kh(1,.) = [2,0].
@@ -129,11 +145,22 @@ def _phase_packs(w):
     if taps is None:          # device-resident index tensors, built once (a python-list index is a host->device copy)
         taps = _tap_index[w.device] = {0: torch.tensor([1], device=w.device), 1: torch.tensor([2, 0], device=w.device)}
     packs = {}
+    O, I = w.shape[0], w.shape[1]
     with torch.no_grad():
-        for a in (0, 1):
-            for b in (0, 1):
-                sub = w.index_select(2, taps[a]).index_select(3, taps[b])   # (Cout,Cin,KH',KW')
-                packs[(a, b)] = sub.permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)
+        if _merge_phases(I, O):
+            mg = torch.zeros((4 * I, 2, 2, O), device=w.device, dtype=torch.bfloat16)
+            for a in (0, 1):
+                for b in (0, 1):
+                    sub = w.index_select(2, taps[a]).index_select(3, taps[b])   # (Cout,Cin,KH',KW')
+                    blk = mg[(2 * a + b) * I:(2 * a + b + 1) * I]
+                    blk[:, :sub.shape[2], :sub.shape[3], :] = sub.permute(1, 2, 3, 0).to(torch.bfloat16)
+                    packs[(a, b)] = blk
+            packs["merged"] = mg
+        else:
+            for a in (0, 1):
+                for b in (0, 1):
+                    sub = w.index_select(2, taps[a]).index_select(3, taps[b])   # (Cout,Cin,KH',KW')
+                    packs[(a, b)] = sub.permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)
     if key is not None:
         _phase_cache[key] = (ver, packs, weakref.ref(w))
     return packs
@@ -150,7 +177,16 @@ def _dgrad(dy, w, stride, pad, in_hw, into=None):
         N, Ho, Wo, _ = dy.shape
         H, W = in_hw
         dx = into if acc else torch.empty((N, H, W, w.shape[1]), device=dy.device, dtype=dy.dtype)
-        for (a, b), wp in _phase_packs(w).items():
+        packs = _phase_packs(w)
+        if "merged" in packs:
+            # channel j = (a, b, ci) of dy-pixel (h, w) is dx[2h + a, 2w + b, ci]: (b, ci) are 2*I contiguous elements, the a = 1
+            # half sits one dx row (W pixels) further
+            I = w.shape[1]
+            ps = dx.stride(2)
+            K.conv2d_fwd(dy, packs["merged"], stride=1, pad=0, out=dx, out_place=(H * W, 2 * W, 2, 0), out_hw_override=(Ho, Wo),
+                         accumulate=acc, split=(2 * I, W * ps - 2 * I))
+            return dx
+        for (a, b), wp in packs.items():
             K.conv2d_fwd(dy, wp, stride=1, pad=0, out=dx, out_place=(H * W, 2 * W, 2, a * W + b), out_hw_override=(Ho, Wo),
                          accumulate=acc)
         return dx

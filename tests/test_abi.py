@@ -58,13 +58,13 @@ def test_host_side_entry_points_without_gpu():
     one-row-per-CTA statistics layout), workspace sizes, EINVAL + c3d_last_error on bad arguments (no CUDA call)."""
     from omni3d_b200 import _lib, conv
     L = conv._bind()
-    d = conv.ConvDesc(32, 640, 640, 16, 16, 3, 3, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)       # DLA level0: halo path
+    d = conv.ConvDesc(32, 640, 640, 16, 16, 3, 3, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)       # DLA level0: halo path
     t, th, tw = conv.num_tiles(d)
     if os.environ.get("C3D_CONV_NO_HALO"):
         assert t == 32 * 640 * 640 // (th * tw)
     else:
         assert (t, th, tw) == (148 * 3, 1, 128)
-    d = conv.ConvDesc(32, 160, 160, 256, 256, 3, 3, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)     # FPN output conv
+    d = conv.ConvDesc(32, 160, 160, 256, 256, 3, 3, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)     # FPN output conv
     t, th, tw = conv.num_tiles(d)
     assert th * tw <= 128 and t == 32 * -(-160 // th) * -(-160 // tw)
     L.c3d_nms_workspace_bytes.restype = ctypes.c_size_t

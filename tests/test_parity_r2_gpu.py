@@ -30,7 +30,8 @@ REAL_SHAPES = [
     ("root_448to128@80", 32, 80, 80, 448, 128, 1, 1, 0),       # Root 1x1, K = 448
     ("l5_512@20", 32, 20, 20, 512, 512, 3, 1, 1),
     ("fpn_lat_64to256@160", 32, 160, 160, 64, 256, 1, 1, 0),
-    ("level1_16to32_s2@640", 32, 640, 640, 16, 32, 3, 2, 1),
+    ("level1_16to32_s2@640", 32, 640, 640, 16, 32, 3, 2, 1),   # data gradient = ONE merged 2x2 conv of dy (split channel placement)
+    ("l2_entry_32to64_s2@320", 32, 320, 320, 32, 64, 3, 2, 1),  # merged data gradient on the swapped kernel (4*32 = 128 channels)
 ]
 
 
