@@ -200,7 +200,9 @@ int32_t c3d_bn_bwd(const void* dout, const void* out, const void* y, const float
                    int64_t dres_stride, void* scratch, void* stream);
 /* backward of the bias(+ReLU) epilogue of the bias convs (FPN / RPN head): dz (bf16) = dout * (out > 0 if relu),
  * dbias (fp32 [C]) += sum over pixels.  dtype_flags: bit 0 = dout is fp32 (else bf16), bit 1 = out is fp32 (else bf16).
- * partial: fp32 [c3d_bn_bwd_blocks(P,C)][C]; scratch: c3d_bn_scratch_bytes(C). */
+ * partial: fp32 [c3d_bn_bwd_blocks(P,C)][C]; scratch: c3d_bn_scratch_bytes(C).
+ * dz may be NULL when relu == 0 and dout is bf16: dz would equal dout (the FPN convs have no activation) and only the
+ * bias gradient is computed — half of the pass's HBM traffic. */
 int32_t c3d_bias_act_bwd(const void* dout, const void* out, int32_t relu, int32_t dtype_flags, void* dz, float* partial,
                          float* dbias, int64_t P, int32_t C, void* scratch, void* stream);
 /* y (N,H/2,W/2,C) = 2x2 block sums of x: gradient of the FPN nearest-x2 upsampling */

@@ -357,7 +357,7 @@ __global__ void bias_act_bwd_kernel(const TIN* __restrict__ dout, const TOUT* __
 #pragma unroll
         for (int k = 0; k < 8; ++k) if (!(o.v[k] > 0.f)) d.v[k] = 0.f;
       }
-      st8(dz + p * C + c, d);
+      if (dz) st8(dz + p * C + c, d);       // (no ReLU and a bf16 dout: dz == dout, the caller passes NULL and keeps dout)
 #pragma unroll
       for (int k = 0; k < 8; ++k) s[k] += d.v[k];
     }
@@ -894,8 +894,9 @@ extern "C" int32_t c3d_sgd_momentum_dev(float* p, const float* g, float* mom, in
 extern "C" int32_t c3d_bias_act_bwd(const void* dout, const void* out, int32_t relu, int32_t dtype_flags, void* dz,
                                     float* partial /*[c3d_bn_bwd_blocks(P,C)][C]*/, float* dbias, int64_t P, int32_t C,
                                     void* scratch, void* stream) {
-  C3D_REQ(dout && dz && partial && scratch && C % 8 == 0 && C <= 2048, "bias_act_bwd: bad args");
+  C3D_REQ(dout && partial && scratch && C % 8 == 0 && C <= 2048, "bias_act_bwd: bad args");
   C3D_REQ(!relu || out, "bias_act_bwd: relu needs the forward output");
+  C3D_REQ(dz || (!relu && !(dtype_flags & 1)), "bias_act_bwd: dz may be NULL only without ReLU and with a bf16 dout (dz == dout)");
   if (P == 0) return C3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = c3d_bn_bwd_blocks(P, C);

@@ -371,11 +371,14 @@ def bias_act_bwd(dout, out, relu, dbias):
     blocks = L.c3d_bn_bwd_blocks(P, C)
     partial = torch.empty((blocks, C), device=dout.device, dtype=torch.float32)
     scratch = torch.empty(128 * 2 * C + 64, device=dout.device, dtype=torch.float64)
-    dz = torch.empty(dout.shape, device=dout.device, dtype=torch.bfloat16)
+    alias = (not relu) and dout.dtype == torch.bfloat16          # no activation: dz IS dout, only the bias gradient is left
+    if alias and dbias is None:
+        return dout
+    dz = None if alias else torch.empty(dout.shape, device=dout.device, dtype=torch.bfloat16)
     flags = int(dout.dtype == torch.float32) | (2 if (out is not None and out.dtype == torch.float32) else 0)
     _lib.check(L.c3d_bias_act_bwd(_p(dout), _p(out), int(relu), flags, _p(dz), _p(partial),
                                   _p(dbias), P, C, _p(scratch), _st()), launches=3 if dbias is not None else 1)
-    return dz
+    return dout if alias else dz
 
 
 def sumpool2(x):
