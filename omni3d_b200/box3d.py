@@ -68,7 +68,7 @@ def iou_box3d(boxes1, boxes2, with_counts=False):
             ws = _workspace(L.c3d_iou_box3d_workspace_bytes(N, M), dev)
             st = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(L.c3d_iou_box3d(_ptr(b1), N, _ptr(b2), M, _ptr(vol), _ptr(iou), _ptr(nf), _ptr(ws),
-                                       ws.numel(), ctypes.c_void_p(st)), launches=3)
+                                       ws.numel(), ctypes.c_void_p(st)), launches=4)
     out = (vol, iou, nf) if with_counts else (vol, iou)
     return tuple(o.cpu() for o in out) if ret_cpu else out
 
@@ -110,7 +110,7 @@ def box3d_overlap(boxes_dt, boxes_gt, eps_coplanar: float = 1e-4, eps_nonzero: f
             ws = _workspace(L.c3d_iou_box3d_workspace_bytes(N, max(M, 1)), dev)
             st = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(L.c3d_box3d_overlap(_ptr(b1), N, _ptr(b2), M, eps_coplanar, eps_nonzero, _ptr(iou),
-                                           _ptr(nbad), _ptr(ws), ws.numel(), ctypes.c_void_p(st)), launches=3)
+                                           _ptr(nbad), _ptr(ws), ws.numel(), ctypes.c_void_p(st)), launches=5)
         bad = nbad.tolist()   # the reference's .any() checks (:158,162) are host syncs too
     if bad[0]:
         print('Warning: skipping {:d} non-coplanar boxes at eval.'.format(int(bad[0])))

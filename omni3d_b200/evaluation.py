@@ -77,7 +77,7 @@ def box3d_overlap_segmented(dt_groups, gt_groups, eps_coplanar=1e-4, eps_nonzero
             st = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(L.c3d_box3d_overlap_segmented(b1.data_ptr(), n_dt, b2.data_ptr(), n_gt, d_off.data_ptr(), g_off.data_ptr(),
                                                      p_off.data_ptr(), G, total, eps_coplanar, eps_nonzero, iou.data_ptr(),
-                                                     nbad.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.c_void_p(st)), launches=4)
+                                                     nbad.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.c_void_p(st)), launches=5)
             out = iou[:total].cpu().numpy()
             bad = nbad.tolist()
     if bad[0]:

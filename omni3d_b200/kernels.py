@@ -102,7 +102,7 @@ def bn_finalize(stats, count, eps, momentum, running_mean, running_var):
     rstd = torch.empty(C, device=stats.device, dtype=torch.float32)
     scratch = torch.empty(128 * 2 * C + 64, device=stats.device, dtype=torch.float64)
     _lib.check(L.c3d_bn_finalize(_p(stats), rows, C, float(count), eps, momentum, _p(running_mean), _p(running_var),
-                                 _p(mean), _p(rstd), _p(scratch), _st()), launches=2)
+                                 _p(mean), _p(rstd), _p(scratch), _st()), launches=1)
     return mean, rstd
 
 
@@ -154,7 +154,7 @@ def bn_bwd(dout, out, y, mean, rstd, gamma, relu, dgamma, dbeta, want_dres, froz
         dres = torch.empty_like(y) if want_dres else None
     scratch = torch.empty(128 * 2 * C + 64, device=y.device, dtype=torch.float64)
     _lib.check(L.c3d_bn_bwd(_p(dout), _p(out), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), flags, int(frozen), _p(partial), _p(coef),
-                            _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, ds, 0, rs, _p(scratch), _st()), launches=4)
+                            _p(dgamma), _p(dbeta), _p(dy), _p(dres), P, C, ds, 0, rs, _p(scratch), _st()), launches=3)
     return dy, dres
 
 
@@ -377,7 +377,7 @@ def bias_act_bwd(dout, out, relu, dbias):
     dz = None if alias else torch.empty(dout.shape, device=dout.device, dtype=torch.bfloat16)
     flags = int(dout.dtype == torch.float32) | (2 if (out is not None and out.dtype == torch.float32) else 0)
     _lib.check(L.c3d_bias_act_bwd(_p(dout), _p(out), int(relu), flags, _p(dz), _p(partial),
-                                  _p(dbias), P, C, _p(scratch), _st()), launches=3 if dbias is not None else 1)
+                                  _p(dbias), P, C, _p(scratch), _st()), launches=2 if dbias is not None else 1)
     return dout if alias else dz
 
 
