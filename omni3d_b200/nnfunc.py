@@ -178,15 +178,19 @@ def _dgrad(dy, w, stride, pad, in_hw, into=None):
         H, W = in_hw
         dx = into if acc else torch.empty((N, H, W, w.shape[1]), device=dy.device, dtype=dy.dtype)
         packs = _phase_packs(w)
-        if "merged" in packs:
-            # channel j = (a, b, ci) of dy-pixel (h, w) is dx[2h + a, 2w + b, ci]: (b, ci) are 2*I contiguous elements, the a = 1
-            # half sits one dx row (W pixels) further
-            I = w.shape[1]
-            ps = dx.stride(2)
+        I = w.shape[1]
+        if "merged" in packs and dx.stride(2) == I:
+            # channel j = (a, b, ci) of dy-pixel (h, w) is dx[2h + a, 2w + b, ci]: in a DENSE dx (b, ci) are 2*I contiguous
+            # elements, the a = 1 half sits one dx row (W pixels) further
             K.conv2d_fwd(dy, packs["merged"], stride=1, pad=0, out=dx, out_place=(H * W, 2 * W, 2, 0), out_hw_override=(Ho, Wo),
-                         accumulate=acc, split=(2 * I, W * ps - 2 * I))
+                         accumulate=acc, split=(2 * I, W * I - 2 * I))
             return dx
-        for (a, b), wp in packs.items():
+        # exact-FLOP phases (wide layers), or the row blocks of the merged weight used one by one (2x2 taps, unused ones zero)
+        # when dx is a channel slice of a wider gradient buffer (adjacent pixels are not adjacent in memory there)
+        for key, wp in packs.items():
+            if key == "merged":
+                continue
+            a, b = key
             K.conv2d_fwd(dy, wp, stride=1, pad=0, out=dx, out_place=(H * W, 2 * W, 2, a * W + b), out_hw_override=(Ho, Wo),
                          accumulate=acc)
         return dx

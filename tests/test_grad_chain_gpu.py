@@ -77,3 +77,77 @@ def test_chaining_removes_the_add_passes():
         finally:
             nnfunc.GRAD_CHAIN = True
     assert counts[True] <= counts[False] - 20, counts
+
+
+# ---- the accumulating kernel variants behind the protocol, one by one ------------------------------------------------
+def _r(*shape, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, device="cuda", generator=g)
+
+
+def test_bn_bwd_accumulating_dres_dense_and_slice():
+    """c3d_bn_bwd flag bit 1: dres += masked dout (fp32 add) into a dense buffer and into a channel slice of a wider one"""
+    from omni3d_b200 import kernels as Kx
+    P, C = 4096, 64
+    y = _r(2, 32, 64, C, seed=1).bfloat16()
+    res = _r(2, 32, 64, C, seed=7).bfloat16()
+    mean, rstd = _r(C, seed=2) * 0.1, torch.rand(C, device="cuda") + 0.5
+    gamma, beta = torch.rand(C, device="cuda") + 0.5, _r(C, seed=3) * 0.3
+    out = Kx.bn_apply(y, mean, rstd, gamma, beta, res, True)
+    dout = _r(2, 32, 64, C, seed=4).bfloat16()
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dy0, dres0 = Kx.bn_bwd(dout, out, y, mean, rstd, gamma, True, dg, db, True)
+    prior = _r(2, 32, 64, C, seed=9).bfloat16()
+    want = (prior.float() + dres0.float()).bfloat16()
+    for wide in (False, True):
+        if wide:
+            buf = torch.zeros(2, 32, 64, 3 * C, device="cuda", dtype=torch.bfloat16)
+            into = buf[..., C:2 * C]
+            into.copy_(prior)
+        else:
+            into = prior.clone()
+        dg2, db2 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        dy1, _ = Kx.bn_bwd(dout, out, y, mean, rstd, gamma, True, dg2, db2, True, dres_into=into)
+        assert torch.equal(dy1, dy0) and torch.equal(dg2, dg) and torch.equal(db2, db)
+        assert torch.equal(into, want)
+        if wide:
+            assert float(buf[..., :C].abs().max()) == 0.0 and float(buf[..., 2 * C:].abs().max()) == 0.0
+
+
+def test_maxpool2_bwd_accumulate():
+    from omni3d_b200 import kernels as Kx
+    x = _r(2, 16, 24, 32, seed=1).bfloat16()
+    dy = _r(2, 8, 12, 32, seed=2).bfloat16()
+    dx = Kx.maxpool2_bwd(x, dy)
+    prior = _r(2, 16, 24, 32, seed=3).bfloat16()
+    into = prior.clone()
+    Kx.maxpool2_bwd(x, dy, into=into)
+    assert torch.equal(into, (prior.float() + dx.float()).bfloat16())
+
+
+@pytest.mark.parametrize("Cin,Cout,k,stride", [(64, 64, 3, 1), (128, 128, 3, 1), (256, 256, 3, 1), (64, 128, 3, 2), (16, 32, 3, 2),
+                                               (256, 128, 1, 1)])
+def test_conv_dgrad_accumulates_into_existing_gradient(Cin, Cout, k, stride):
+    """_dgrad(..., into=buf): buf += dgrad in the conv epilogue (add_mode 3) on every kernel variant — pixel-major, persistent,
+    swapped, the merged stride-2 form with split channel placement — for a dense buffer and a channel slice."""
+    from omni3d_b200 import nnfunc
+    N, H, W = 2, 32, 48
+    pad = k // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    w = torch.nn.Parameter(_r(Cout, Cin, k, k, seed=1) / (k * k * Cin) ** 0.5)
+    dy = _r(N, Ho, Wo, Cout, seed=2).bfloat16()
+    ref = nnfunc._dgrad(dy, w, stride, pad, (H, W)).float()
+    prior = _r(N, H, W, Cin, seed=3).bfloat16()
+    for wide in (False, True):
+        if wide:
+            buf = torch.zeros(N, H, W, Cin + 32, device="cuda", dtype=torch.bfloat16)
+            into = buf[..., 16:16 + Cin]
+            into.copy_(prior)
+        else:
+            into = prior.clone()
+        nnfunc._dgrad(dy, w, stride, pad, (H, W), into=into)
+        got, want = into.float(), prior.float() + ref
+        # `ref` was rounded to bf16 once before the add, the fused path adds in fp32: one bf16 ulp of the sum
+        assert float((got - want).abs().max()) <= 2.0 ** -7 * float(want.abs().max()) + 1e-3
+        if wide:
+            assert float(buf[..., :16].abs().max()) == 0.0 and float(buf[..., 16 + Cin:].abs().max()) == 0.0
