@@ -368,9 +368,19 @@ def iou_block(peak_hbm, peak_src):
     ms = med_ms(lambda: box3d.iou_box3d_paired(a, b), iters=5)
     gbs = 200.0 * n / (ms * 1e-3) / 1e9
     out["sparse_paired"] = {"pairs": n, "ms": ms, "pairs_per_s": n / (ms * 1e-3), "alg_GBps": gbs}
-    out["roofline"] = {"bound": "hbm", "kernel": "iou3d_pair_kernel, 1e6 paired sparse pairs (200 algorithmic B / pair)",
-                       "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm, "traffic": None,
+    # the HBM-bound regime of the path: pairs whose bounding spheres are disjoint (boxes spread over a 100 m cube) are decided
+    # by the fused prep + filter kernel alone — 192 B of corners in, 12 B (vol, iou, face count) out per pair
+    a = torch.from_numpy(boxgen.random_boxes(n, 100.0, 0)).cuda()
+    b = torch.from_numpy(boxgen.random_boxes(n, 100.0, 5)).cuda()
+    ms_d = med_ms(lambda: box3d.iou_box3d_paired(a, b, with_counts=True), iters=5)
+    gbs_d = 204.0 * n / (ms_d * 1e-3) / 1e9
+    out["disjoint_paired"] = {"pairs": n, "ms": ms_d, "pairs_per_s": n / (ms_d * 1e-3), "alg_GBps": gbs_d}
+    out["roofline"] = {"bound": "hbm", "kernel": "iou3d_prep_paired_kernel (+ empty clip / overflow launches), 1e6 paired pairs with "
+                                                 "disjoint bounding spheres (204 algorithmic B / pair)",
+                       "achieved": gbs_d, "peak": peak_hbm, "unit": "GB/s", "frac": gbs_d / peak_hbm, "traffic": None,
                        "peak_source": peak_src + ", hbm copy",
+                       "sparse_paired_note": "L = 10 pairs: about 5 percent survive the sphere test and are clipped (issue-bound "
+                                             f"work): {gbs:.0f} GB/s algorithmic",
                        "dense_note": "dense (overlapping) pairs are issue-slot bound, not HBM bound (8 B / pair in cross mode): "
                                      "see `ncu` for the committed issue-slot / lane-utilisation figures",
                        "ncu": _ncu_iou_issue_pct()}
