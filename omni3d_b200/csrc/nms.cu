@@ -92,17 +92,30 @@ __device__ __forceinline__ int nms_scan_chunks(const unsigned long long* __restr
     }
     emit(c, keep);
     cnt += __popcll(keep);
-    // OR the kept rows' later words into the live bitset
+    // OR the kept rows' later words into the live bitset.  The rows are independent of each other: the loads of kUn kept rows
+    // are issued before any of them is consumed (one kept row at a time was one L2 round trip per kept row — 1000 keeps x
+    // ~600 cycles = most of the 0.56 ms this kernel took per step, profiles/r02_summary.md)
+    constexpr int kUn = 8;
+    const bool w0 = lane > c && lane < wc, w1 = lane + 32 > c && lane + 32 < wc, w2 = lane + 64 > c && lane + 64 < wc,
+               w3 = lane + 96 > c && lane + 96 < wc;
     unsigned long long k = keep;
     while (k) {
-      const int i = __ffsll((long long)k) - 1;
-      k &= k - 1;
-      const unsigned long long* row = rows + (size_t)(base + i) * words;
-      int ww = lane;
-      if (ww > c && ww < wc) r0 |= row[ww];
-      ww = lane + 32; if (ww > c && ww < wc) r1 |= row[ww];
-      ww = lane + 64; if (ww > c && ww < wc) r2 |= row[ww];
-      ww = lane + 96; if (ww > c && ww < wc) r3 |= row[ww];
+      unsigned long long t0[kUn], t1[kUn], t2[kUn], t3[kUn];
+#pragma unroll
+      for (int u = 0; u < kUn; ++u) {
+        t0[u] = t1[u] = t2[u] = t3[u] = 0ull;
+        if (k) {
+          const int i = __ffsll((long long)k) - 1;
+          k &= k - 1;
+          const unsigned long long* row = rows + (size_t)(base + i) * words;
+          if (w0) t0[u] = row[lane];
+          if (w1) t1[u] = row[lane + 32];
+          if (w2) t2[u] = row[lane + 64];
+          if (w3) t3[u] = row[lane + 96];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUn; ++u) { r0 |= t0[u]; r1 |= t1[u]; r2 |= t2[u]; r3 |= t3[u]; }
     }
   }
   return cnt;
