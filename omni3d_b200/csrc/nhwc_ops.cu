@@ -595,31 +595,12 @@ struct PackDesc {
   int Cout, Cin, KH, KW, ohwi, pad_;
 };
 __global__ void pack_conv_weights_batched_kernel(const PackDesc* __restrict__ descs, int n, long long total) {
-  // pass 0: element e of the SOURCE index space -> forward pack (+ the stride-2 phase packs); pass 1: element e of the
-  // DATA-GRADIENT pack's index space (Cin, KH, KW, Cout) <- gathered from the source.  The data-gradient pack is a
-  // Cout <-> Cin transpose: written from the source order it is one 2-byte store per 32-byte sector (0.37 ms per step for
-  // 19 M conv parameters); gathered, the stores are coalesced and the scattered 4-byte reads hit a weight tensor that
-  // sits in L2.
-  for (long long e2 = blockIdx.x * (long long)blockDim.x + threadIdx.x; e2 < 2 * total; e2 += (long long)gridDim.x * blockDim.x) {
-    const bool pass1 = e2 >= total;
-    const long long e = pass1 ? e2 - total : e2;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     int lo = 0, hi = n;
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (descs[mid].start <= e) lo = mid; else hi = mid; }
     const PackDesc D = descs[lo];
     const long long i = e - D.start;
     int kw, kh, ci, co;
-    if (pass1) {
-      if (!D.dgrad) continue;
-      // i indexes dgrad (Cin, KH, KW, Cout): [ci][KH-1-kh][KW-1-kw][co]
-      co = (int)(i % D.Cout); long long t = i / D.Cout;
-      const int rkw = (int)(t % D.KW); t /= D.KW;
-      const int rkh = (int)(t % D.KH); ci = (int)(t / D.KH);
-      kh = D.KH - 1 - rkh; kw = D.KW - 1 - rkw;
-      const long long si = D.ohwi ? (((long long)co * D.KH + kh) * D.KW + kw) * D.Cin + ci
-                                  : (((long long)co * D.Cin + ci) * D.KH + kh) * D.KW + kw;
-      D.dgrad[i] = __float2bfloat16(__ldg(D.src + si));
-      continue;
-    }
     if (D.ohwi) {
       ci = (int)(i % D.Cin); long long t = i / D.Cin;
       kw = (int)(t % D.KW); t /= D.KW;
@@ -631,6 +612,7 @@ __global__ void pack_conv_weights_batched_kernel(const PackDesc* __restrict__ de
     }
     const bf16 v = __float2bfloat16(D.src[i]);
     if (D.fwd) D.fwd[(((long long)co * D.KH + kh) * D.KW + kw) * D.Cin + ci] = v;
+    if (D.dgrad) D.dgrad[(((long long)ci * D.KH + (D.KH - 1 - kh)) * D.KW + (D.KW - 1 - kw)) * D.Cout + co] = v;
     if (D.phase[0]) {               // 3x3 only: parity a = (kh != 1), position inside the phase: kh 1 -> 0 | kh 2 -> 0, kh 0 -> 1
       const int a = kh != 1, b = kw != 1;
       const int ph = a ? (kh == 2 ? 0 : 1) : 0, pw = b ? (kw == 2 ? 0 : 1) : 0;
@@ -857,8 +839,8 @@ extern "C" int32_t c3d_preprocess_image_u8(const uint8_t* img, int32_t H, int32_
 extern "C" int32_t c3d_pack_conv_weights_batched(const void* descs_dev, int32_t n, int64_t total_elems, void* stream) {
   C3D_REQ(descs_dev && n > 0 && total_elems > 0, "pack_conv_weights_batched: bad args");
   static_assert(sizeof(PackDesc) == 88, "c3d_pack_desc layout");
-  pack_conv_weights_batched_kernel<<<grid_for(2 * total_elems, 256), 256, 0, (cudaStream_t)stream>>>((const PackDesc*)descs_dev, n,
-                                                                                                     total_elems);
+  pack_conv_weights_batched_kernel<<<grid_for(total_elems, 256), 256, 0, (cudaStream_t)stream>>>((const PackDesc*)descs_dev, n,
+                                                                                                 total_elems);
   return check_launch("pack_conv_weights_batched");
 }
 extern "C" int32_t c3d_preprocess_batch(const void* const* imgs_host, const int32_t* H_host, const int32_t* W_host, int32_t N,
