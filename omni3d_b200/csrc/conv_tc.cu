@@ -977,6 +977,8 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
   if ((d->add_mode == 1 || d->add_mode == 2) && !addend) return set_error(C3D_EINVAL, "conv2d: addend missing");
   if (d->add_mode == 3 && d->out_fp32) return set_error(C3D_EINVAL, "conv2d: in-place accumulate needs a bf16 output");
   if (d->add_mode < 0 || d->add_mode > 3) return set_error(C3D_EINVAL, "conv2d: add_mode %d", d->add_mode);
+  if (d->y_split_c && (d->y_split_c % 16 != 0 || d->add_mode == 1 || d->add_mode == 2 || stats))
+    return set_error(C3D_EINVAL, "conv2d: y_split_c must be a multiple of 16 without addend / statistics");
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error(C3D_ECUDA, "cuTensorMapEncodeTiled unavailable");
 
@@ -1001,8 +1003,6 @@ extern "C" int32_t c3d_conv2d_fwd(const c3d_conv_desc* d, const void* x, const v
     P.out_img_stride = (long long)Ho * Wo; P.out_h_stride = Wo; P.out_w_stride = 1; P.out_off = 0;
   }
   P.split_c = d->y_split_c; P.split_off = d->y_split_off;
-  if (P.split_c && (P.split_c % 16 != 0 || d->add_mode == 1 || d->add_mode == 2 || stats))
-    return set_error(C3D_EINVAL, "conv2d: y_split_c must be a multiple of 16 without addend / statistics");
   P.stats = stats;
   const long long xps = d->x_pix_stride ? d->x_pix_stride : Cin;
 

@@ -79,3 +79,28 @@ def test_host_side_entry_points_without_gpu():
     assert rc != 0 and b"anchor_match" in L.c3d_last_error()
     with pytest.raises(_lib.C3DError):
         _lib.check(rc)
+
+
+def test_conv_descriptor_argument_checks_without_gpu():
+    """c3d_conv2d_fwd validates the descriptor before any CUDA call: odd outputs have no nearest-x2 addend, the in-place
+    accumulate needs a bf16 output, the split channel placement needs a multiple of 16 and excludes addend / statistics."""
+    from omni3d_b200 import _lib, conv
+    L = conv._bind()
+    L.c3d_last_error.restype = ctypes.c_char_p
+    p = ctypes.c_void_p(256)                       # non-null dummies: every case below is rejected before they are used
+
+    def call(d, addend=p, stats=None):
+        return L.c3d_conv2d_fwd(ctypes.byref(d), p, p, None, addend, p, stats, None)
+
+    d = conv.ConvDesc(2, 9, 11, 64, 64, 3, 3, 1, 1, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)           # up2 addend, 9 x 11 output
+    assert call(d) == _lib.C3D_EINVAL and b"even output" in L.c3d_last_error()
+    d = conv.ConvDesc(2, 8, 8, 64, 64, 3, 3, 1, 1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)             # addend mode without addend
+    assert call(d, addend=None) == _lib.C3D_EINVAL and b"addend missing" in L.c3d_last_error()
+    d = conv.ConvDesc(2, 8, 8, 64, 64, 3, 3, 1, 1, 0, 1, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)             # accumulate into fp32
+    assert call(d) == _lib.C3D_EINVAL and b"bf16 output" in L.c3d_last_error()
+    d = conv.ConvDesc(2, 8, 8, 64, 64, 2, 2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 8, 8, 0, 24, 0, 100)           # split not a multiple of 16
+    assert call(d, addend=None) == _lib.C3D_EINVAL and b"y_split_c" in L.c3d_last_error()
+    d = conv.ConvDesc(2, 8, 8, 64, 64, 3, 3, 3, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)             # stride 3
+    assert call(d, addend=None) == _lib.C3D_EINVAL and b"stride" in L.c3d_last_error()
+    with pytest.raises(_lib.C3DError):
+        _lib.check(_lib.C3D_EINVAL)

@@ -375,7 +375,12 @@ def test_conv_swapped_kernel_epilogue_modes(N, H, W, Cin, Cout, k, s, mode):
         assert (y.float() - want).abs().max().item() <= tol + 1.2e-2 * add.float().abs().max().item()
     elif mode == "up2":
         if Ho % 2 or Wo % 2:
-            pytest.skip("nearest-x2 addend needs an even output")
+            # an odd output has no nearest-x2 source map: the entry point refuses it (C3D_EINVAL) before anything is launched
+            from omni3d_b200 import _lib
+            add = _r(N, (Ho + 1) // 2, (Wo + 1) // 2, Cout, seed=4).bfloat16()
+            with pytest.raises(_lib.C3DError, match="even output"):
+                K.conv2d_fwd(x, w, b, stride=s, pad=p, addend=add, up2=True)
+            return
         add = _r(N, Ho // 2, Wo // 2, Cout, seed=4).bfloat16()
         y = K.conv2d_fwd(x, w, b, stride=s, pad=p, addend=add, up2=True)
         up = add.float().repeat_interleave(2, 1).repeat_interleave(2, 2)
